@@ -1,0 +1,197 @@
+/*
+ * fa_b200.h -- C-ABI of libfa_b200.so: the B200 (sm_100a) implementation of the formantanalyzer
+ * feature-extraction hot path that tabahi/WebSpeechAnalyzer embeds.
+ *
+ * This is the drop-in boundary.  Everything the reference does between
+ * "PCM arrives" and "callback(si, label, seg_time, features)" happens behind these calls:
+ *
+ *   reference interface (file:line, @B = byte offset in /root/reference/dist/main.js line 2)   entry point here
+ *   ---------------------------------------------------------------------------------------   -----------------
+ *   configure(cfg)                       @B3292   (used by /root/reference/src/index.js:393)   fa_config + fa_create
+ *   reset_nodes / reset_segmentor        @B6992 / @B7303 -> reset_segmentation @B25053         fa_create / fa_reset
+ *   LaunchAudioNodes(1, buf, cb, ...)    @B4469   (src/index.js:291)                           fa_submit_pcm + fa_run
+ *   worklet "spectrum-processor" frames  @B6480 (un-vendored) -> spectrum_push @B30392         fa_run stage 1, fa_copy_spectrum / fa_copy_frames
+ *   D()/O()/C() segmentor                @B25717 / @B27088 / @B28506                           fa_run stages 2-3, fa_copy_segments
+ *   straighten_formants / sep_syllables  @B35074 / @B34757                                     fa_copy_formants / fa_copy_syllables
+ *   formant_features / make_syl_features @B32369 / @B34407                                     fa_copy_features
+ *   get_seg_timestamps / get_syls_timestamps @B31504 / @B31114                                 computed by the host shim from fa_segment / fa_syllable
+ *   StopAudioNodes                       @B5699                                                fa_reset
+ *
+ * Rules: plain C types only; every call returns an fa_status (0 = ok, < 0 = error) and never
+ * throws; a handle is not thread-safe, distinct handles are independent; there is no global
+ * state and NO CPU FALLBACK: without a usable sm_100-class device fa_create fails with
+ * FA_ERR_NO_DEVICE.
+ */
+#ifndef FA_B200_H_
+#define FA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FA_N_FEATURES 53 /* /root/reference/src/localstore.js:7 (levels 5 and 13 -> 53) */
+#define FA_ABI_VERSION 1
+
+typedef enum fa_status {
+  FA_OK = 0,
+  FA_ERR_INVALID_ARG = -1,
+  FA_ERR_NO_DEVICE = -2,      /* no CUDA device / not sm_100 class; there is no CPU path */
+  FA_ERR_CUDA = -3,           /* a CUDA runtime call failed; see fa_last_error */
+  FA_ERR_NOT_RUN = -4,        /* results requested before fa_run + fa_sync */
+  FA_ERR_UNKNOWN_UTT = -5,
+  FA_ERR_CAPACITY = -6,       /* destination too small, or an internal table overflowed */
+  FA_ERR_OUT_OF_MEMORY = -7,
+  FA_ERR_BUSY = -8,           /* "Error: Already playing" (@B4469): fa_run while a run is in flight */
+  FA_ERR_UNSUPPORTED = -9     /* e.g. output_level 11/12, fft size outside 256..16384 */
+} fa_status;
+
+/* spec_type (formantanalyzer defaults @B2972; tool-tips /root/reference/index.html:249-282) */
+#define FA_SPEC_MEL 1
+#define FA_SPEC_POWER 2
+#define FA_SPEC_DFFT 3
+
+/* output_level (/root/reference/index.html:170-180) */
+#define FA_LEVEL_BARS 1
+#define FA_LEVEL_SPECTRUM 2
+#define FA_LEVEL_SEGMENTS 3
+#define FA_LEVEL_FORMANTS 4
+#define FA_LEVEL_SEG_FEATURES 5
+#define FA_LEVEL_SYL_FORMANTS 10
+#define FA_LEVEL_SYL_FEATURES 13
+
+typedef struct fa_config {
+  /* ---- formantanalyzer fields (defaults @B2972) ---- */
+  int32_t spec_type;        /* 1 */
+  int32_t output_level;     /* 4 */
+  int32_t plot_len;         /* 200 (only seg_limit_1 for levels <= 2 depends on it) */
+  int32_t n_fft_bins;       /* 256 */
+  int32_t n_mel_bins;       /* 128 */
+  int32_t auto_noise_gate;  /* 1 */
+  double f_min;             /* 50 Hz   */
+  double f_max;             /* 4000 Hz */
+  double window_width_ms;   /* 25 (informational: the analysis window is fft_size samples) */
+  double window_step_ms;    /* 25 */
+  double pause_length_ms;   /* 200 */
+  double min_seg_length_ms; /* 50 */
+  double voiced_max_db;     /* 100 */
+  double voiced_min_db;     /* 10 */
+  double pre_norm_gain;     /* 1000 */
+  double high_f_emph;       /* 0 */
+  /* ---- extension fields: the AnalyserNode front end that replaces the un-vendored worklet ---- */
+  int32_t fft_size;         /* 2048 (power of two, 256..16384) */
+  int32_t clamp_db;         /* 1: clamp the dB view to [min_db, max_db] */
+  int32_t want_spectrum;    /* 1: materialise the dB spectrum [frames][fft_size/2] even for levels >= 3 */
+  int32_t reserved0;
+  double smoothing;         /* smoothingTimeConstant 0.8 */
+  double min_db;            /* -100 */
+  double max_db;            /* -30 */
+  double mag_scale;         /* 0 => fft_size (SURVEY.md finding 3) */
+} fa_config;
+
+typedef struct fa_segment {
+  int32_t start;        /* seg_ci[si][0]: current_frame - len (reference quirk: late by the trailing pause) */
+  int32_t len;          /* seg_ci[si][1] */
+  int32_t stored;       /* index into the per-level stores (formants / features), -1 when the reference's
+                           straighten_formants would have thrown and the segment was dropped (.catch -> L(-1)) */
+  int32_t n_syllables;  /* levels 10/13 */
+  int32_t first_syllable; /* index of its first syllable in the utterance's syllable table */
+  int32_t row_offset;   /* first row of this segment in the utterance's formant table (rows of 9 floats) */
+  double ymax;          /* adaptive maximum `y` at finalisation */
+  double vmin;          /* adaptive minimum `v` at finalisation */
+  double cs_ratio;      /* formant energy / non-formant energy (feature [2]) */
+} fa_segment;
+
+typedef struct fa_syllable {
+  int32_t stored_seg;   /* index of the owning stored segment */
+  int32_t start;        /* frame offset inside the segment */
+  int32_t len;
+  int32_t reserved;
+} fa_syllable;
+
+typedef struct fa_counts {
+  int64_t samples;
+  int32_t sample_rate;
+  int32_t hop;            /* samples per frame step */
+  int32_t frames;
+  int32_t bands;          /* spec_bands */
+  int32_t segments;       /* entries of seg_ci */
+  int32_t stored_segments;
+  int32_t formant_rows;   /* sum of len over stored segments */
+  int32_t syllables;
+  int32_t feature_rows;   /* level 5: stored segments; level 13: syllables */
+  int32_t overflow;       /* non-zero if an internal table overflowed (results invalid) */
+} fa_counts;
+
+typedef struct fa_handle fa_handle;
+
+void fa_config_default(fa_config* cfg);
+int fa_abi_version(void);
+const char* fa_status_string(int status);
+
+int fa_create(const fa_config* cfg, int device, fa_handle** out);
+int fa_destroy(fa_handle* h);
+const char* fa_last_error(const fa_handle* h);
+
+/* Use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the handle's own. */
+int fa_set_stream(fa_handle* h, void* cuda_stream);
+
+/* Drop all submitted utterances and results (StopAudioNodes / a new batch). */
+int fa_reset(fa_handle* h);
+
+/* Copy one utterance of mono float32 PCM (host memory, owned by the caller) into the handle's
+ * pinned staging buffer.  All utterances of one batch share sample_rate.  Returns its index. */
+int fa_submit_pcm(fa_handle* h, int64_t utt_id, const float* pcm, size_t n_samples, int sample_rate);
+int fa_submit_pcm_i16(fa_handle* h, int64_t utt_id, const int16_t* pcm, size_t n_samples, int sample_rate);
+
+/* Asynchronously: H2D copy of the staged PCM, stages 1-4 on the handle's stream, D2H of the result
+ * tables.  fa_sync waits for it. */
+int fa_run(fa_handle* h);
+int fa_sync(fa_handle* h);
+
+/* Device-resident variant for throughput measurement: upload once ... */
+int fa_upload(fa_handle* h);
+/* ... then run only the kernels on the resident PCM (no H2D, no D2H). */
+int fa_run_resident(fa_handle* h);
+/* and fetch the result tables of the last resident run to the host. */
+int fa_download(fa_handle* h);
+
+/* Per-stage device time of the last run in milliseconds (CUDA events on the handle's stream):
+ * [0] spectrum, [1] peaks, [2] segment scan, [3] features, [4] whole run incl. copies. */
+int fa_stage_times(fa_handle* h, float ms[5]);
+/* Number of kernel launches issued by the last run. */
+int fa_launch_count(fa_handle* h);
+
+int fa_num_utterances(const fa_handle* h);
+int fa_result_counts(fa_handle* h, int64_t utt_id, fa_counts* out);
+int fa_total_counts(fa_handle* h, fa_counts* out);
+
+/* Caller-allocated destinations; `cap` counts elements of the destination type's row
+ * (rows for tables).  Return value: rows written (>= 0) or an fa_status (< 0). */
+int fa_copy_spectrum(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows);      /* rows of fft_size/2 dB values */
+int fa_copy_frames(fa_handle* h, int64_t utt_id, uint32_t* dst, size_t cap_rows);     /* rows of `bands` uint32 */
+int fa_copy_segments(fa_handle* h, int64_t utt_id, fa_segment* dst, size_t cap_rows);
+int fa_copy_formants(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows);      /* rows of 9 float32 */
+int fa_copy_energy(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows);        /* rows of 3 float32 */
+int fa_copy_syllables(fa_handle* h, int64_t utt_id, fa_syllable* dst, size_t cap_rows);
+int fa_copy_features(fa_handle* h, int64_t utt_id, double* dst, size_t cap_rows);     /* rows of 53 doubles */
+
+/* Stage-level taps for parity tests (candidate peaks of stage 2: packed lo | hi<<8 | pk<<16 | last<<24). */
+int fa_copy_peak_candidates(fa_handle* h, int64_t utt_id, uint32_t* packed, int32_t* counts, size_t cap_rows,
+                            int32_t* max_per_frame);
+
+/* Host-side helpers that the shims share (no device needed). */
+int fa_hop_samples(const fa_config* cfg, int sample_rate);
+int fa_frames_for(const fa_config* cfg, int sample_rate, size_t n_samples);
+int fa_spec_bands(const fa_config* cfg);
+
+/* Synthetic "glottal pulse through formant resonators" speech; host code,
+ * deterministic in (seed, utt_index).  Used by bench.py and the tests to build workloads. */
+int fa_synth_speech(float* dst, size_t n_samples, int sample_rate, uint64_t seed, uint64_t utt_index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FA_B200_H_ */

@@ -1,0 +1,889 @@
+/*
+ * fa_oracle.c -- TEST INFRASTRUCTURE ONLY.  CPU restatement of the formantanalyzer hot path.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * build, load or call this file.  The product (webspeechanalyzer_b200/, libfa_b200.so) never does.
+ *
+ * PARITY STATUS: "parity unpinned".  The reference (tabahi/WebSpeechAnalyzer) ships no tests, no
+ * golden vectors and no runnable engine for this path in this image (browser JavaScript, no JS
+ * engine here), and its spectrum stage is an un-vendored CDN worklet.  This file restates
+ *   - segmentor  /root/reference/dist/main.js:2@B23403-B31782 (inner module 3),
+ *   - formants   /root/reference/dist/main.js:2@B31782-B38281 (inner module 4),
+ *   - stats      /root/reference/dist/main.js:2@B1065-B2714 == /root/reference/src/stats.js:29-64,
+ * and a builder-defined AnalyserNode front end (W3C Web Audio API; DESIGN.md "Front-end spec").
+ * It is cross-checked against a second, literal transliteration (oracle/literal/refmodules.py),
+ * against the invariants the reference does pin (row width 53: src/localstore.js:7; feature
+ * ranges: dist/nnmodel/1/cats_emotion/model_meta.json) and, where `node` exists, against the
+ * reference's own minified modules through oracle/run_reference_modules.js.
+ *
+ * Build: gcc -O2 -ffp-contract=off -mfma -fPIC -shared -fopenmp (see oracle/build.py).
+ * Floating-point contraction MUST be off: every fused multiply-add below is an explicit fmaf().
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "fa_b200.h"
+#include "fa_jsmath.h"
+#include "fa_tables.h"
+
+#define FAO_API __attribute__((visibility("default")))
+
+/* ============================================================================================
+ * Stage 1 / 1b: canonical float32 front end (builder-defined spec)
+ * ============================================================================================ */
+
+typedef struct {
+  int N, M, logM, B, hop;
+  float *win, *tw, *ws;
+  fa_bandmat bm;
+  float gain, tau, omt, inv2N;
+  float* emph; /* [B] (float)(m * high_f_emph) */
+} fao_plan;
+
+static int fao_plan_init(fao_plan* p, const fa_config* c, int sr) {
+  memset(p, 0, sizeof(*p));
+  if (!fa_tab_valid_fft(c->fft_size)) return -1;
+  p->N = c->fft_size;
+  p->M = p->N / 2;
+  p->logM = fa_tab_log2(p->M);
+  p->B = fa_tab_bands(c);
+  p->hop = fa_tab_hop(sr, c->window_step_ms);
+  p->win = (float*)malloc(sizeof(float) * p->N);
+  p->tw = (float*)malloc(sizeof(float) * p->M);      /* M/2 complex */
+  p->ws = (float*)malloc(sizeof(float) * 2 * p->M);  /* M complex */
+  p->emph = (float*)malloc(sizeof(float) * p->B);
+  fa_tab_window(p->N, p->win);
+  fa_tab_fft_twiddles(p->M, p->tw);
+  fa_tab_split_twiddles(p->M, p->ws);
+  if (fa_tab_bandmat(c, sr, &p->bm) < 0) return -1;
+  p->gain = fa_tab_gain(c);
+  p->tau = (float)c->smoothing;
+  p->omt = (float)(1.0 - c->smoothing);
+  p->inv2N = (float)(1.0 / (2.0 * (double)p->N));
+  for (int m = 0; m < p->B; m++) p->emph[m] = (float)((double)m * c->high_f_emph);
+  return 0;
+}
+
+static void fao_plan_free(fao_plan* p) {
+  free(p->win); free(p->tw); free(p->ws); free(p->emph);
+  fa_tab_bandmat_free(&p->bm);
+}
+
+static unsigned fao_bitrev(unsigned x, int bits) {
+  unsigned r = 0;
+  for (int i = 0; i < bits; i++) { r = (r << 1) | (x & 1u); x >>= 1; }
+  return r;
+}
+
+/* One frame: windowed samples xw[N] -> |X[k]|/N for k in [0, M).  Canonical DAG:
+ * packed real FFT, radix-2 decimation-in-time, 6-FMA butterflies, table twiddles. */
+static void fao_frame_mag(const fao_plan* p, const float* xw, float* re, float* im, float* mag) {
+  const int M = p->M;
+  for (int q = 0; q < M; q++) {
+    unsigned n = fao_bitrev((unsigned)q, p->logM);
+    re[q] = xw[2 * n];
+    im[q] = xw[2 * n + 1];
+  }
+  for (int s = 1; s <= p->logM; s++) {
+    const int half = 1 << (s - 1), stride = M >> s;
+    for (int base = 0; base < M; base += 2 * half) {
+      for (int k = 0; k < half; k++) {
+        const float wr = p->tw[2 * (k * stride)], wi = p->tw[2 * (k * stride) + 1];
+        const int ia = base + k, ib = ia + half;
+        const float ar = re[ia], ai = im[ia], br = re[ib], bi = im[ib];
+        const float nr = fmaf(wr, br, fmaf(-wi, bi, ar));
+        const float ni = fmaf(wr, bi, fmaf(wi, br, ai));
+        re[ia] = nr;
+        im[ia] = ni;
+        re[ib] = fmaf(2.0f, ar, -nr);
+        im[ib] = fmaf(2.0f, ai, -ni);
+      }
+    }
+  }
+  for (int k = 0; k < M; k++) {
+    const int kb = (M - k) & (M - 1);
+    const float ar = re[k], ai = im[k], br = re[kb], bi = im[kb];
+    const float sr_ = ar + br, si = ai - bi, dr = ar - br, di = ai + bi;
+    const float wr = p->ws[2 * k], wi = p->ws[2 * k + 1];
+    const float pp = wi * di, qq = wi * dr;
+    const float tr = fmaf(wr, dr, -pp), ti = fmaf(wr, di, qq);
+    const float xr = sr_ + ti, xi = si - tr;
+    const float m2 = fmaf(xr, xr, xi * xi);
+    mag[k] = sqrtf(m2) * p->inv2N;
+  }
+}
+
+static uint32_t fao_to_u32(float b) {
+  if (!(b > 0.0f)) return 0u; /* also NaN */
+  if (b >= 4294967296.0f) return 0xFFFFFFFFu;
+  return (uint32_t)rintf(b); /* round-half-even (default rounding mode) */
+}
+
+FAO_API int fao_hop(const fa_config* c, int sr) { return fa_tab_hop(sr, c->window_step_ms); }
+FAO_API int fao_bands(const fa_config* c) { return fa_tab_bands(c); }
+FAO_API int fao_num_frames(const fa_config* c, int sr, int64_t n) { return (int)(n / fa_tab_hop(sr, c->window_step_ms)); }
+
+/* PCM -> per frame: dB spectrum [F][N/2] (nullable), smoothed linear magnitude [F][N/2] (nullable),
+ * uint32 band frames [F][B] (nullable).  Returns F, or < 0. */
+FAO_API int fao_frontend(const fa_config* c, const float* pcm, int64_t n, int sr, float* spec_db, float* smooth,
+                         uint32_t* frames) {
+  fao_plan p;
+  if (fao_plan_init(&p, c, sr) != 0) return -1;
+  const int N = p.N, M = p.M, B = p.B;
+  const int F = (int)(n / p.hop);
+  float* xw = (float*)malloc(sizeof(float) * N);
+  float* re = (float*)malloc(sizeof(float) * M);
+  float* im = (float*)malloc(sizeof(float) * M);
+  float* mag = (float*)malloc(sizeof(float) * M);
+  float* xs = (float*)calloc((size_t)M, sizeof(float));
+  float* lin = (float*)malloc(sizeof(float) * M);
+  const float lo_db = (float)c->min_db, hi_db = (float)c->max_db;
+  for (int t = 0; t < F; t++) {
+    const int64_t end = (int64_t)(t + 1) * p.hop, beg = end - N;
+    for (int i = 0; i < N; i++) {
+      const int64_t j = beg + i;
+      const float x = j >= 0 ? pcm[j] : 0.0f;
+      xw[i] = x * p.win[i];
+    }
+    fao_frame_mag(&p, xw, re, im, mag);
+    for (int k = 0; k < M; k++) {
+      xs[k] = fmaf(p.tau, xs[k], p.omt * mag[k]);
+      if (smooth) smooth[(size_t)t * M + k] = xs[k];
+      if (spec_db) {
+        float d = 20.0f * log10f(xs[k]);
+        if (c->clamp_db) d = d < lo_db ? lo_db : (d > hi_db ? hi_db : d);
+        spec_db[(size_t)t * M + k] = d;
+      }
+      lin[k] = xs[k] * p.gain;
+      if (c->spec_type == FA_SPEC_POWER) lin[k] = lin[k] * lin[k];
+    }
+    if (frames) {
+      for (int m = 0; m < B; m++) {
+        float acc = 0.0f;
+        const float* w = p.bm.w + p.bm.off[m];
+        const int k0 = p.bm.k0[m];
+        for (int i = 0; i < p.bm.cnt[m]; i++) acc = fmaf(w[i], lin[k0 + i], acc);
+        if (c->high_f_emph != 0.0) acc = fmaf(acc, p.emph[m], acc);
+        frames[(size_t)t * B + m] = fao_to_u32(acc);
+      }
+    }
+  }
+  free(xw); free(re); free(im); free(mag); free(xs); free(lin);
+  fao_plan_free(&p);
+  return F;
+}
+
+/* float64 "truth" of the dB spectrum (plain W3C AnalyserNode arithmetic in double, O(N log N)),
+ * reported beside the float32 numbers; not part of the parity gate. */
+static void fao_fft64(double* re, double* im, int n, int logn) {
+  for (int i = 0; i < n; i++) {
+    int j = (int)fao_bitrev((unsigned)i, logn);
+    if (j > i) { double t = re[i]; re[i] = re[j]; re[j] = t; t = im[i]; im[i] = im[j]; im[j] = t; }
+  }
+  for (int len = 2; len <= n; len <<= 1) {
+    for (int b = 0; b < n; b += len)
+      for (int k = 0; k < len / 2; k++) {
+        double a = -2.0 * FA_PI * k / len, wr = cos(a), wi = sin(a);
+        int ia = b + k, ib = ia + len / 2;
+        double tr = wr * re[ib] - wi * im[ib], ti = wr * im[ib] + wi * re[ib];
+        re[ib] = re[ia] - tr; im[ib] = im[ia] - ti;
+        re[ia] += tr; im[ia] += ti;
+      }
+  }
+}
+
+FAO_API int fao_frontend_f64(const fa_config* c, const float* pcm, int64_t n, int sr, double* spec_db) {
+  if (!fa_tab_valid_fft(c->fft_size)) return -1;
+  const int N = c->fft_size, M = N / 2, hop = fa_tab_hop(sr, c->window_step_ms), logN = fa_tab_log2(N);
+  const int F = (int)(n / hop);
+  double* re = (double*)malloc(sizeof(double) * N);
+  double* im = (double*)malloc(sizeof(double) * N);
+  double* xs = (double*)calloc((size_t)M, sizeof(double));
+  for (int t = 0; t < F; t++) {
+    const int64_t end = (int64_t)(t + 1) * hop, beg = end - N;
+    for (int i = 0; i < N; i++) {
+      const int64_t j = beg + i;
+      const double x = j >= 0 ? (double)pcm[j] : 0.0, a = (double)i / N;
+      re[i] = x * (0.42 - 0.5 * cos(2 * FA_PI * a) + 0.08 * cos(4 * FA_PI * a));
+      im[i] = 0.0;
+    }
+    fao_fft64(re, im, N, logN);
+    for (int k = 0; k < M; k++) {
+      const double mg = sqrt(re[k] * re[k] + im[k] * im[k]) / N;
+      xs[k] = c->smoothing * xs[k] + (1.0 - c->smoothing) * mg;
+      double d = 20.0 * log10(xs[k]);
+      if (c->clamp_db) d = d < c->min_db ? c->min_db : (d > c->max_db ? c->max_db : d);
+      spec_db[(size_t)t * M + k] = d;
+    }
+  }
+  free(re); free(im); free(xs);
+  return F;
+}
+
+/* ============================================================================================
+ * Stages 2-4: segmentor + formants + features (restatement of the reference)
+ * ============================================================================================ */
+
+typedef struct { int *d; int n, cap; } ivec;
+typedef struct { double *d; int n, cap; } dvec;
+static void ivec_push(ivec* v, int x) {
+  if (v->n == v->cap) { v->cap = v->cap ? 2 * v->cap : 8; v->d = (int*)realloc(v->d, sizeof(int) * v->cap); }
+  v->d[v->n++] = x;
+}
+static void dvec_push(dvec* v, double x) {
+  if (v->n == v->cap) { v->cap = v->cap ? 2 * v->cap : 8; v->d = (double*)realloc(v->d, sizeof(double) * v->cap); }
+  v->d[v->n++] = x;
+}
+
+/* formant track: fields of l[r] at @B35952 ([0]lo [1]hi [2]frame [3]lastFrame [4]velocity [5]lastBin
+ * [6]lastAmp [7]frames[] [8]los[] [9]his[] [10]bins[] [11]amps[] [12]energies[] [13]sumE [14]count
+ * [15]sum(E*bin) [17]sum span) */
+typedef struct {
+  int lo, hi, frame, last_frame;
+  double velocity;
+  int last_bin;
+  double last_amp;
+  ivec frames, los, his, bins;
+  dvec energies;
+  double sum_e, sum_eb;
+  int count, sum_span;
+} fao_track;
+
+typedef struct { int lo, hi, pk; } fao_peak;
+
+typedef struct {
+  /* config-derived (reset_segmentation @B25053) */
+  int level, B, max_voiced_bin, seg_min_frames, auto_gate, plot_len;
+  double window_step, seg_breaker;
+  /* state */
+  int current_frame, no_fm_segs, c_ci, c_started;
+  double y, v, x, v0, T;
+  int w, k;
+  /* formants module state */
+  fao_track* tr;
+  int n_tr, cap_tr;
+  double s_energy, c_energy;
+} fao_state;
+
+struct fao_result {
+  int F, B, level;
+  /* per-frame trace */
+  int *tr_n, *tr_p, *tr_cstart, *tr_cci, *tr_nofm;
+  double *tr_h, *tr_v, *tr_y;
+  /* seg_ci (array u) */
+  ivec seg_start, seg_len, seg_stored; /* stored = index into the stores below or -1 (dropped by the throw) */
+  /* stores (arrays c/d/h/p share the index) */
+  ivec st_len, st_row_off, st_nsyl, st_first_syl;
+  dvec st_y, st_v, st_cs;
+  float* formants; /* rows of 9 */
+  float* energy;   /* rows of 3 */
+  int n_rows, cap_rows;
+  ivec syl_seg, syl_start, syl_len;
+  dvec features; /* rows of 53: level 5 -> one per stored segment, level 13 -> one per syllable */
+  int n_feature_rows;
+  /* callback order (P @B28869): indices into seg_ci, in firing order */
+  ivec cb_si;
+};
+typedef struct fao_result fao_result;
+
+static void track_free(fao_track* t) { free(t->frames.d); free(t->los.d); free(t->his.d); free(t->bins.d); free(t->energies.d); }
+
+/* clear_fm @B35919 */
+static void clear_fm(fao_state* st) {
+  for (int i = 0; i < st->n_tr; i++) track_free(&st->tr[i]);
+  st->n_tr = 0;
+  st->s_energy = 0.0;
+  st->c_energy = 0.0;
+}
+
+/* L() @B25649 */
+static void seg_reset(fao_state* st, int started) {
+  st->c_ci = 0;
+  st->c_started = started;
+  st->no_fm_segs = 0;
+  clear_fm(st);
+}
+
+/* _() @B37340 */
+static double fm_score(int gap, double dist, int count, int bin_old, int bin_new, double amp_old, double amp_new,
+                       double velocity) {
+  double s;
+  if (amp_old >= amp_new) s = amp_new / amp_old;
+  else {
+    if (!(amp_new > 0)) return 0;
+    s = amp_old / amp_new;
+  }
+  if (gap == 0) return s > 0.1 ? 300.0 * s / dist : 0;
+  if (s < 0.001) return 0;
+  if (s >= 1) s = 10; else if (s < 0.1) s = 1; else s *= 10;
+  double t = 10.0 - fabs((double)bin_new - (double)bin_old - velocity);
+  if (t < 0) return 0;
+  if (t < 1) t = 1;
+  int i = count > 10 ? 10 : count;
+  return 10.0 / (double)gap * (t * t + (double)i * s);
+}
+
+static fao_track* track_new(fao_state* st) {
+  if (st->n_tr == st->cap_tr) {
+    st->cap_tr = st->cap_tr ? 2 * st->cap_tr : 64;
+    st->tr = (fao_track*)realloc(st->tr, sizeof(fao_track) * st->cap_tr);
+  }
+  fao_track* t = &st->tr[st->n_tr++];
+  memset(t, 0, sizeof(*t));
+  return t;
+}
+
+/* accumulate_fm @B35952 */
+static void accumulate_fm(fao_state* st, const uint32_t* e, const fao_peak* pk, int u, int n, double g, double vmin) {
+  static const int DIST[4] = {3, 4, 6, 9};
+  if (u < 1) return;
+  int* owner = (int*)malloc(sizeof(int) * u);
+  double* best = (double*)malloc(sizeof(double) * u);
+  for (int o = 0; o < u; o++) { owner[o] = -1; best[o] = 0; }
+  st->s_energy += g;
+  const int ntr = st->n_tr;
+  for (int r = 0; r < ntr; r++) {
+    const fao_track* t = &st->tr[r];
+    int gap = n - t->last_frame;
+    if (gap >= 0 && gap < 4) {
+      for (int o = 0; o < u; o++) {
+        int dist = abs(t->last_bin - pk[o].pk);
+        if (dist < DIST[gap]) {
+          double sc = fm_score(gap, (double)dist, t->frames.n, t->last_bin, pk[o].pk, t->last_amp, (double)e[pk[o].pk],
+                               t->velocity);
+          if (sc > 1 && sc > best[o]) { best[o] = sc; owner[o] = r; }
+        }
+      }
+    }
+  }
+  for (int r = 0; r < ntr; r++) {
+    fao_track* t = &st->tr[r];
+    int first = -1;
+    for (int o = 0; o < u; o++) if (owner[o] == r) { first = o; break; }
+    if (first < 0) continue;
+    int o_bin = pk[first].pk;
+    double amp = (double)e[o_bin];
+    if (amp > vmin) {
+      int lo = pk[first].lo, hi = pk[first].hi;
+      for (int o = first; o < u; o++) if (owner[o] == r) {
+        if (pk[o].hi > hi) hi = pk[o].hi;
+        if (pk[o].lo < lo) lo = pk[o].lo;
+        if (e[pk[o].pk] > e[o_bin]) o_bin = pk[o].pk;
+      }
+      double E = 0;
+      for (int b = lo; b <= hi; b++) E += (double)e[b];
+      int h = t->bins.n;
+      const int* bn = t->bins.d;
+      if (h >= 3) t->velocity = ((double)(o_bin - bn[h - 1] + (bn[h - 2] - bn[h - 1]) + (bn[h - 3] - bn[h - 2]))) / 3;
+      else if (h == 2) t->velocity = ((double)(o_bin - bn[h - 1] + (bn[h - 2] - bn[h - 1]))) / 2;
+      else if (h == 1) t->velocity = (double)(o_bin - bn[h - 1]);
+      t->lo = lo; t->hi = hi; t->frame = n; t->last_frame = n; t->last_bin = o_bin; t->last_amp = amp;
+      ivec_push(&t->frames, n); ivec_push(&t->los, lo); ivec_push(&t->his, hi); ivec_push(&t->bins, o_bin);
+      dvec_push(&t->energies, E);
+      t->sum_e += E; t->count += 1; t->sum_eb += E * (double)o_bin; t->sum_span += hi - lo + 1;
+      st->s_energy -= E;
+      st->c_energy += E;
+    }
+  }
+  for (int o = 0; o < u; o++) if (owner[o] == -1) {
+    int i = pk[o].pk;
+    double amp = (double)e[i];
+    if (amp > vmin) {
+      int lo = pk[o].lo, hi = pk[o].hi;
+      double E = 0;
+      for (int b = lo; b <= hi; b++) E += (double)e[b];
+      fao_track* t = track_new(st);
+      t->lo = lo; t->hi = hi; t->frame = n; t->last_frame = n; t->velocity = 0; t->last_bin = i; t->last_amp = amp;
+      ivec_push(&t->frames, n); ivec_push(&t->los, lo); ivec_push(&t->his, hi); ivec_push(&t->bins, i);
+      dvec_push(&t->energies, E);
+      t->sum_e = E; t->count = 1; t->sum_eb = E * (double)i; t->sum_span = hi - lo + 1;
+    }
+  }
+  free(owner); free(best);
+}
+
+/* get_ranked_formants @B35670: indices of tracks, ascending mean, stable */
+static int ranked_formants(const fao_state* st, int* out) {
+  int n = 0;
+  for (int t = 0; t < st->n_tr; t++) {
+    const fao_track* tk = &st->tr[t];
+    if (tk->count >= 2) {
+      double m = tk->sum_eb / tk->sum_e;
+      if (m >= 7) {
+        int r = 0;
+        while (r < n) {
+          const fao_track* o = &st->tr[out[r]];
+          if (o->sum_eb / o->sum_e > m) break;
+          r++;
+        }
+        memmove(out + r + 1, out + r, sizeof(int) * (n - r));
+        out[r] = t;
+        n++;
+      }
+    }
+  }
+  return n;
+}
+
+/* straighten_formants @B35074.  Returns 0, or -1 where the JS would throw (frame index >= len). */
+static int straighten(const fao_state* st, const int* ranked, int nr, int len, double vmin, float* F, float* Eg) {
+  memset(F, 0, sizeof(float) * 9 * (size_t)len);
+  memset(Eg, 0, sizeof(float) * 3 * (size_t)len);
+  double anchor = 0;
+  int slot = 0;
+  for (int t = 0; t < nr; t++) {
+    const fao_track* tk = &st->tr[ranked[t]];
+    double m = tk->sum_eb / tk->sum_e;
+    if (fabs(m - anchor) > 20 || slot < 0) {
+      anchor = m;
+      slot++;
+      if (slot >= 3) break;
+    }
+    for (int i = 0; i < tk->count; i++) {
+      int sl = slot;
+      int bin = tk->bins.d[i];
+      if (bin > 0) {
+        double E = tk->energies.d[i];
+        int fr = tk->frames.d[i];
+        int span = tk->his.d[i] - tk->los.d[i] + 1;
+        if (fr < 0 || fr >= len) return -1; /* r[d] undefined -> TypeError */
+        float* row = F + 9 * (size_t)fr;
+        float* eg = Eg + 3 * (size_t)fr;
+        if ((double)row[3 * sl] > vmin && (double)row[3 * sl] < (double)bin && sl < 2) sl++;
+        row[3 * sl] = (float)bin;
+        row[3 * sl + 1] = (float)E;
+        row[3 * sl + 2] = (float)span;
+        eg[0] = (float)((double)eg[0] + (double)bin * E);
+        eg[1] = (float)((double)eg[1] + E);
+        eg[2] = (float)((double)eg[2] + (double)span * E);
+      }
+    }
+  }
+  return 0;
+}
+
+/* stats (src/stats.js:29-64) */
+static double array_mean_nz(const double* a, int n) {
+  double s = 0; int c = 0;
+  for (int i = 0; i < n; i++) if (a[i] > 0) { s += a[i]; c++; }
+  return s / (double)c;
+}
+static double std_nz(const double* a, int n, double* mean_out) {
+  double mean = array_mean_nz(a, n), acc = 0;
+  for (int i = 0; i < n; i++) { double d = a[i] - mean; acc += d * d; }
+  if (mean_out) *mean_out = mean;
+  return sqrt(acc / (double)n);
+}
+static double arr_sum(const double* a, int n) { double s = 0; for (int i = 0; i < n; i++) s += a[i]; return s; }
+
+/* formant_features @B32369 (vector assembly @B33436). F: len rows of 9 float32. */
+static void formant_features(const float* F, int len, double ymax, double vmin, double cs, double* out) {
+  double cnt[3] = {0}, runs[3] = {0}, up[3] = {0}, down[3] = {0}, fmean[3] = {0}, fstd[3] = {0}, dbm[3] = {0},
+         dbs[3] = {0}, e_len[3] = {0}, e_cnt[3] = {0}, span[3] = {0}, nacc[3] = {0}, accm[3] = {0}, accs[3] = {0},
+         prom[3] = {0};
+  double* c = (double*)malloc(sizeof(double) * 6 * (size_t)(len > 0 ? len : 1));
+  double *w = c + len, *T = w + len, *k = T + len, *M = k + len, *A = M + len;
+  for (int n = 0; n < 3; n++) {
+    int prev = 0, S = 0, m = 0, na = 0;
+    double L = 0;
+    for (int t = 0; t < len; t++) {
+      double r = (double)F[9 * (size_t)t + 3 * n], a = (double)F[9 * (size_t)t + 3 * n + 1];
+      if (r > 0 && a > 0) {
+        double f = (double)F[9 * (size_t)t + 3 * n + 2], d = 20.0 * fa_js_log10(a);
+        c[m] = r * d; w[m] = r; M[m] = f * d; T[m] = a; k[m] = d; m++;
+        if (prev) {
+          double j = r - (double)F[9 * (size_t)(t - 1) + 3 * n];
+          if (j > 1) up[n] += j; else if (j < -1) down[n] += -1 * j;
+          if (a > L) { L = a; S = 1; }
+          else if (S == 1 && a < L / 2) { if (L > 10) A[na++] = d; L = 0; S = -1; }
+        }
+        if (!prev) runs[n] += 1;
+        prev = 1;
+        cnt[n] += 1;
+      } else { prev = 0; S = 0; L = 0; }
+    }
+    if (runs[n] > 0) {
+      double e = arr_sum(T, m);
+      e_len[n] = e / (double)len * 100 / ymax;
+      e_cnt[n] = e / cnt[n] * 100 / ymax;
+      double o = arr_sum(k, m);
+      fmean[n] = arr_sum(c, m) / o;
+      fstd[n] = std_nz(w, m, NULL);
+      span[n] = arr_sum(M, m) / o;
+      dbs[n] = std_nz(k, m, &dbm[n]);
+      nacc[n] = na;
+      if (na > 0) {
+        accs[n] = std_nz(A, na, &accm[n]);
+        prom[n] = 100 * (accm[n] / (o / (double)m) - 1);
+      }
+    }
+  }
+  int q = 0;
+  out[q++] = len; out[q++] = sqrt((double)len); out[q++] = cs; out[q++] = fa_js_log10(ymax); out[q++] = vmin;
+  for (int e = 0; e < 3; e++) {
+    out[q++] = fmean[e]; out[q++] = fstd[e]; out[q++] = dbm[e]; out[q++] = dbs[e]; out[q++] = e_len[e];
+    out[q++] = e_cnt[e]; out[q++] = span[e]; out[q++] = cnt[e]; out[q++] = runs[e]; out[q++] = up[e];
+    out[q++] = down[e]; out[q++] = nacc[e]; out[q++] = accm[e]; out[q++] = accs[e]; out[q++] = prom[e];
+    out[q++] = 100 * cnt[e] / (double)len;
+  }
+  free(c);
+}
+
+/* C() @B28506 */
+static void noise_gate(fao_state* st, double e) {
+  st->w++;
+  if (e > st->y || (st->w > 40 && e > 2 * st->v)) {
+    if (e >= st->y) { st->w = 0; st->x = st->y = e; }
+    else if (e > st->x / 100) { st->y -= fa_js_parse_int(st->y / 8); st->w = 35; }
+    double t = fa_js_log10(st->y);
+    if (t > 7) st->v = fa_js_parse_int(fa_js_pow(10, t - 3) / 20);
+    else if (t > 6) st->v = fa_js_parse_int(fa_js_pow(10, t - 3) / 2);
+    else if (t > 4) st->v = fa_js_parse_int(fa_js_pow(10, t - 2) / 2);
+    else if (t > 2) st->v = fa_js_parse_int(fa_js_pow(10, t / 3));
+    else if (t > 1) st->v = fa_js_parse_int(st->y / 10);
+    else st->v = 1;
+    st->v0 = st->v;
+    if (st->k > 0 && st->T / (double)st->k < 30 * st->v) { seg_reset(st, 0); st->k = 0; st->T = 0; }
+    st->T += st->y;
+    st->k += 1;
+  } else if (st->v > 10 && st->v > st->v0 / 10 && st->w > 20) {
+    st->v -= fa_js_parse_int(st->v0 / 20);
+    if (st->v < 10) st->v = 10;
+  }
+}
+
+static void rows_reserve(fao_result* R, int extra) {
+  if (R->n_rows + extra > R->cap_rows) {
+    R->cap_rows = 2 * (R->n_rows + extra) + 64;
+    R->formants = (float*)realloc(R->formants, sizeof(float) * 9 * (size_t)R->cap_rows);
+    R->energy = (float*)realloc(R->energy, sizeof(float) * 3 * (size_t)R->cap_rows);
+  }
+}
+
+/* sep_syllables @B34757: emits [start,len] pairs */
+static int sep_syllables(const float* Eg, int len, double vmin, int* starts, int* lens) {
+  int start = -1, quiet = 0, loud = 0, n = 0;
+  for (int e = 0; e < len; e++) {
+    if ((double)Eg[3 * (size_t)e + 1] > vmin) { quiet = 0; loud++; if (start < 0) start = e; }
+    else quiet++;
+    if ((loud > 20 && quiet > 0) || (loud > 10 && quiet > 1) || (loud > 0 && quiet > 4) || (e >= len - 1 && loud > 4)) {
+      int end = e - quiet;
+      if (end - start > 1) { starts[n] = start; lens[n] = end - start; n++; start = -1; loud = 0; }
+    }
+  }
+  return n;
+}
+
+/* O() @B27088. Returns 1 stored, 0 ignored, -1 rejected (JS throw). */
+static int finalize_segment(fao_state* st, fao_result* R, int n_arg) {
+  int len = n_arg - st->no_fm_segs;
+  if (!(len > st->seg_min_frames && st->c_started >= 2)) return 0;
+  if (!(st->level == 3 || st->level == 4 || st->level == 5 || st->level == 10 || st->level == 11 || st->level == 13))
+    return -1;
+  int start = st->current_frame - len;
+  int* ranked = (int*)malloc(sizeof(int) * (size_t)(st->n_tr > 0 ? st->n_tr : 1));
+  int nr = ranked_formants(st, ranked);
+  ivec_push(&R->seg_start, start);
+  ivec_push(&R->seg_len, len);
+  ivec_push(&R->seg_stored, -1);
+  int si = R->seg_start.n - 1;
+  int rc = 1;
+  if (st->level >= 4) {
+    rows_reserve(R, len);
+    float* F = R->formants + 9 * (size_t)R->n_rows;
+    float* Eg = R->energy + 3 * (size_t)R->n_rows;
+    if (straighten(st, ranked, nr, len, st->v, F, Eg) != 0) rc = -1;
+    else {
+      int stored = R->st_len.n;
+      R->seg_stored.d[si] = stored;
+      ivec_push(&R->st_len, len);
+      ivec_push(&R->st_row_off, R->n_rows);
+      dvec_push(&R->st_y, st->y);
+      dvec_push(&R->st_v, st->v);
+      double cs = st->c_energy / st->s_energy;
+      dvec_push(&R->st_cs, cs);
+      int nsyl = 0;
+      ivec_push(&R->st_first_syl, R->syl_seg.n);
+      if (st->level == 10 || st->level == 11 || st->level == 13) {
+        int* ss = (int*)malloc(sizeof(int) * 2 * (size_t)len);
+        nsyl = sep_syllables(Eg, len, st->v, ss, ss + len);
+        for (int i = 0; i < nsyl; i++) {
+          ivec_push(&R->syl_seg, stored); ivec_push(&R->syl_start, ss[i]); ivec_push(&R->syl_len, ss[len + i]);
+          if (st->level == 13) {
+            double row[FA_N_FEATURES];
+            formant_features(F + 9 * (size_t)ss[i], ss[len + i], st->y, st->v, cs, row);
+            for (int q = 0; q < FA_N_FEATURES; q++) dvec_push(&R->features, row[q]);
+            R->n_feature_rows++;
+          }
+        }
+        free(ss);
+      }
+      ivec_push(&R->st_nsyl, nsyl);
+      if (st->level == 5) {
+        double row[FA_N_FEATURES];
+        formant_features(F, len, st->y, st->v, cs, row);
+        for (int q = 0; q < FA_N_FEATURES; q++) dvec_push(&R->features, row[q]);
+        R->n_feature_rows++;
+      }
+      R->n_rows += len;
+    }
+  } else {
+    /* level 3: raw ranked tracks only; record the segment with an empty store entry */
+    int stored = R->st_len.n;
+    R->seg_stored.d[si] = stored;
+    ivec_push(&R->st_len, 0); ivec_push(&R->st_row_off, R->n_rows); dvec_push(&R->st_y, st->y); dvec_push(&R->st_v, st->v);
+    dvec_push(&R->st_cs, st->c_energy / st->s_energy); ivec_push(&R->st_first_syl, R->syl_seg.n); ivec_push(&R->st_nsyl, 0);
+  }
+  free(ranked);
+  return rc;
+}
+
+/* v-independent candidate scan (stage 2 on the GPU): emits every peak the reference's scan WOULD
+ * close if e[pk] > v held, with the trimmed bounds.  packed = lo | hi<<8 | pk<<16 | lastbin<<24. */
+FAO_API int fao_peak_candidates(const uint32_t* e, int B, uint32_t* packed, double* gsum) {
+  int n = 0, lo = 0, pk = 0, hi = 0, flat = 0, dir = 0;
+  double g = 0;
+#define FAO_EMIT(last)                                                    \
+  do {                                                                    \
+    int l2 = lo, h2 = hi;                                                 \
+    double thr = (double)e[pk] / 10;                                      \
+    while (l2 < pk && (double)e[l2] < thr) l2++;                          \
+    while (h2 > pk && (double)e[h2] < thr) h2--;                          \
+    packed[n++] = (uint32_t)l2 | ((uint32_t)h2 << 8) | ((uint32_t)pk << 16) | ((uint32_t)(last) << 24); \
+  } while (0)
+  for (int a = 1; a < B; a++) {
+    g += (double)e[a];
+    if (e[a] > e[a - 1] && (a < 2 || e[a] > e[a - 2]) && (a < 3 || e[a] > e[a - 3])) {
+      if (dir == -1 || dir == 0) {
+        if (dir == -1 && lo <= pk && pk < hi) FAO_EMIT(0);
+        lo = a - 1; pk = a;
+      } else if (dir == 1) pk = a;
+      dir = 1;
+    } else if (e[a] < e[a - 1] && (a < 2 || e[a] < e[a - 2]) && (a < 3 || e[a] < e[a - 3])) {
+      if (dir == 1 || dir == -1) { hi = a; dir = -1; }
+    } else if (dir == -1) {
+      flat++;
+      if (flat > 2) {
+        flat = 0;
+        if (lo <= pk && pk < hi) FAO_EMIT(0);
+        dir = 0;
+      }
+    } else if (dir == 1 && e[a] > e[a - 1]) pk = a;
+    if (a == B - 1 && dir == 1) {
+      hi = a; pk = a;
+      if (lo < pk && pk <= hi) FAO_EMIT(1);
+    }
+  }
+#undef FAO_EMIT
+  if (gsum) *gsum = g;
+  return n;
+}
+
+/* one frame of D() @B25717 (literal v-dependent scan). Returns finalisation result or -2 if none. */
+static int process_frame(fao_state* st, fao_result* R, const uint32_t* e, int frame_idx) {
+  const int B = st->B;
+  const double v = st->v;
+  int t = st->c_ci, n = 0, i = 0, l = 0, s = 0, c = 0, u = 0, p = 0;
+  double d = 0, h = 2 * v, g = 0;
+  fao_peak* f = (fao_peak*)malloc(sizeof(fao_peak) * (size_t)B);
+#define FAO_CLOSE(upd)                                                  \
+  do {                                                                  \
+    if ((upd) && (double)e[l] > h) { h = (double)e[l]; p = l; }         \
+    double thr = (double)e[l] / 10;                                     \
+    while (i < l && (double)e[i] < thr) i++;                            \
+    while (s > l && (double)e[s] < thr) s--;                            \
+    f[n].lo = i; f[n].hi = s; f[n].pk = l; n++; d += (double)e[l];      \
+  } while (0)
+  for (int a = 1; a < B; a++) {
+    g += (double)e[a];
+    if (e[a] > e[a - 1] && (a < 2 || e[a] > e[a - 2]) && (a < 3 || e[a] > e[a - 3])) {
+      if (u == -1 || u == 0) {
+        if (u == -1 && (double)e[l] > v && i <= l && l < s) FAO_CLOSE(1);
+        i = a - 1; l = a;
+      } else if (u == 1) l = a;
+      u = 1;
+    } else if (e[a] < e[a - 1] && (a < 2 || e[a] < e[a - 2]) && (a < 3 || e[a] < e[a - 3])) {
+      if (u == 1 || u == -1) { s = a; u = -1; }
+    } else if (u == -1) {
+      c++;
+      if (c > 2) {
+        c = 0;
+        if ((double)e[l] > v && i <= l && l < s) FAO_CLOSE(1);
+        u = 0;
+      }
+    } else if (u == 1 && e[a] > e[a - 1]) l = a;
+    if (a == B - 1 && u == 1) {
+      s = a; l = a;
+      if ((double)e[l] > v && i < l && l <= s) FAO_CLOSE(0);
+    }
+  }
+#undef FAO_CLOSE
+  int fin = -2;
+  if (st->c_started < 0) {
+    double ratio = d > h ? h * (double)(n - 1) / (d - h) : 0;
+    if (n > 0 && p > 7 && p < st->max_voiced_bin && n > 4 && ratio > 4) { seg_reset(st, 0); st->c_started = 0; }
+    else st->no_fm_segs++;
+  }
+  if (st->c_started >= 0) {
+    if (n == 0 || p < 7 || p >= st->max_voiced_bin || (n > 3 && d / (g - d) < 0.1)) {
+      st->no_fm_segs++;
+      if (st->c_started < 2) st->c_started--;
+      else if ((double)st->no_fm_segs >= st->seg_breaker) fin = finalize_segment(st, R, st->c_ci + 1);
+      else if (st->auto_gate) noise_gate(st, h);
+    } else {
+      if (st->auto_gate) noise_gate(st, h);
+      accumulate_fm(st, e, f, n, t, g, st->v);
+      if (st->c_started < 2) st->c_started++; else st->no_fm_segs = 0;
+    }
+  }
+  st->c_ci++;
+  if (R->tr_n) {
+    R->tr_n[frame_idx] = n; R->tr_p[frame_idx] = p; R->tr_h[frame_idx] = h; R->tr_v[frame_idx] = st->v;
+    R->tr_y[frame_idx] = st->y; R->tr_cstart[frame_idx] = st->c_started; R->tr_cci[frame_idx] = st->c_ci;
+    R->tr_nofm[frame_idx] = st->no_fm_segs;
+  }
+  free(f);
+  return fin;
+}
+
+/* P() @B28869: which seg_ci indices fire a callback, in order.  The stores are indexed by `stored`;
+ * the reference indexes seg_ci (u) with the SAME counter, which misaligns after a dropped segment
+ * (quirk 15) -- we record the store index and let the host shim reproduce j()/V(). */
+static void fire_callbacks(fao_result* R, int* processed) {
+  while (*processed < R->st_len.n) {
+    int e = (*processed)++;
+    int fire = 0;
+    if (R->level == 13) fire = R->st_nsyl.d[e] > 0;
+    else if (R->level == 10) fire = R->st_nsyl.d[e] > 0;
+    else if (R->level == 5 || R->level == 4) fire = R->st_len.d[e] > 0;
+    else if (R->level == 3) fire = 1;
+    if (fire) ivec_push(&R->cb_si, e);
+  }
+}
+
+FAO_API fao_result* fao_analyze_frames(const fa_config* c, const uint32_t* frames, int F, int want_trace) {
+  fao_result* R = (fao_result*)calloc(1, sizeof(fao_result));
+  fao_state st;
+  memset(&st, 0, sizeof(st));
+  const int B = fa_tab_bands(c);
+  const double step = c->window_step_ms, pause = c->pause_length_ms, minlen = c->min_seg_length_ms;
+  R->F = F; R->B = B; R->level = c->output_level;
+  st.level = c->output_level; st.B = B; st.plot_len = c->plot_len;
+  st.max_voiced_bin = (int)fa_js_parse_int(0.7 * (double)B);
+  st.window_step = step / 1e3;
+  st.seg_breaker = pause > 2 * step ? pause / step : 250 / step;
+  st.seg_min_frames = (int)fa_js_parse_int(minlen / step);
+  st.auto_gate = c->auto_noise_gate;
+  st.c_started = -1;
+  if (st.auto_gate) { st.y = 50; st.v = 2; }
+  else { st.y = fa_js_pow(10, c->voiced_max_db / 20); st.v = fa_js_pow(10, c->voiced_min_db / 20); }
+  st.x = st.y; st.v0 = st.v;
+  if (want_trace && F > 0) {
+    R->tr_n = (int*)calloc(F, sizeof(int)); R->tr_p = (int*)calloc(F, sizeof(int));
+    R->tr_cstart = (int*)calloc(F, sizeof(int)); R->tr_cci = (int*)calloc(F, sizeof(int));
+    R->tr_nofm = (int*)calloc(F, sizeof(int));
+    R->tr_h = (double*)calloc(F, sizeof(double)); R->tr_v = (double*)calloc(F, sizeof(double));
+    R->tr_y = (double*)calloc(F, sizeof(double));
+  }
+  int processed = 0;
+  if (c->output_level >= 3) {
+    for (int t = 0; t < F; t++) {
+      st.current_frame++;
+      int fin = process_frame(&st, R, frames + (size_t)t * B, t);
+      if (fin != -2) { /* the promise's micro-task: runs before the next frame */
+        seg_reset(&st, -1);
+        if (fin >= 0) fire_callbacks(R, &processed);
+      }
+    }
+    /* segment_truncate @B30800 */
+    int fin = finalize_segment(&st, R, st.c_ci);
+    seg_reset(&st, 1);
+    if (fin >= 0) fire_callbacks(R, &processed);
+  }
+  clear_fm(&st);
+  free(st.tr);
+  return R;
+}
+
+FAO_API void fao_free(fao_result* R) {
+  if (!R) return;
+  free(R->tr_n); free(R->tr_p); free(R->tr_cstart); free(R->tr_cci); free(R->tr_nofm); free(R->tr_h); free(R->tr_v);
+  free(R->tr_y); free(R->seg_start.d); free(R->seg_len.d); free(R->seg_stored.d); free(R->st_len.d);
+  free(R->st_row_off.d); free(R->st_nsyl.d); free(R->st_first_syl.d); free(R->st_y.d); free(R->st_v.d);
+  free(R->st_cs.d); free(R->formants); free(R->energy); free(R->syl_seg.d); free(R->syl_start.d);
+  free(R->syl_len.d); free(R->features.d); free(R->cb_si.d);
+  free(R);
+}
+
+/* ---- accessors for ctypes ---- */
+FAO_API void fao_counts(const fao_result* R, int* out /*[8]*/) {
+  out[0] = R->F; out[1] = R->seg_start.n; out[2] = R->st_len.n; out[3] = R->n_rows; out[4] = R->syl_seg.n;
+  out[5] = R->n_feature_rows; out[6] = R->cb_si.n; out[7] = R->B;
+}
+FAO_API void fao_get_segments(const fao_result* R, fa_segment* dst) {
+  for (int i = 0; i < R->seg_start.n; i++) {
+    fa_segment* s = &dst[i];
+    memset(s, 0, sizeof(*s));
+    s->start = R->seg_start.d[i]; s->len = R->seg_len.d[i]; s->stored = R->seg_stored.d[i];
+    if (s->stored >= 0) {
+      int k = s->stored;
+      s->n_syllables = R->st_nsyl.d[k]; s->first_syllable = R->st_first_syl.d[k]; s->row_offset = R->st_row_off.d[k];
+      s->ymax = R->st_y.d[k]; s->vmin = R->st_v.d[k]; s->cs_ratio = R->st_cs.d[k];
+    } else { s->first_syllable = -1; s->row_offset = -1; }
+  }
+}
+FAO_API void fao_get_formants(const fao_result* R, float* F9, float* E3) {
+  if (F9) memcpy(F9, R->formants, sizeof(float) * 9 * (size_t)R->n_rows);
+  if (E3) memcpy(E3, R->energy, sizeof(float) * 3 * (size_t)R->n_rows);
+}
+FAO_API void fao_get_syllables(const fao_result* R, fa_syllable* dst) {
+  for (int i = 0; i < R->syl_seg.n; i++) {
+    dst[i].stored_seg = R->syl_seg.d[i]; dst[i].start = R->syl_start.d[i]; dst[i].len = R->syl_len.d[i]; dst[i].reserved = 0;
+  }
+}
+FAO_API void fao_get_features(const fao_result* R, double* dst) {
+  memcpy(dst, R->features.d, sizeof(double) * (size_t)R->features.n);
+}
+FAO_API void fao_get_callbacks(const fao_result* R, int* dst) { memcpy(dst, R->cb_si.d, sizeof(int) * (size_t)R->cb_si.n); }
+FAO_API int fao_get_trace(const fao_result* R, int* n, int* p, double* h, double* v, double* y, int* cstart, int* cci,
+                          int* nofm) {
+  if (!R->tr_n) return -1;
+  size_t F = (size_t)R->F;
+  memcpy(n, R->tr_n, sizeof(int) * F); memcpy(p, R->tr_p, sizeof(int) * F); memcpy(h, R->tr_h, sizeof(double) * F);
+  memcpy(v, R->tr_v, sizeof(double) * F); memcpy(y, R->tr_y, sizeof(double) * F);
+  memcpy(cstart, R->tr_cstart, sizeof(int) * F); memcpy(cci, R->tr_cci, sizeof(int) * F);
+  memcpy(nofm, R->tr_nofm, sizeof(int) * F);
+  return 0;
+}
+
+/* ---- whole path on a batch, OpenMP over utterances (bench.py cpu_baseline / --impl reference) ---- */
+FAO_API int64_t fao_run_batch(const fa_config* c, const float* pcm, const int64_t* offsets, int n_utt, int sr,
+                              int n_threads, int64_t* out_rows /* nullable: feature rows per utterance */) {
+  int64_t total_frames = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads) reduction(+ : total_frames)
+  for (int u = 0; u < n_utt; u++) {
+    const int64_t n = offsets[u + 1] - offsets[u];
+    const int B = fa_tab_bands(c);
+    int F = (int)(n / fa_tab_hop(sr, c->window_step_ms));
+    uint32_t* frames = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(F > 0 ? F : 1) * B);
+    float* spec = c->want_spectrum || c->output_level <= 2
+                      ? (float*)malloc(sizeof(float) * (size_t)(F > 0 ? F : 1) * (c->fft_size / 2))
+                      : NULL;
+    fao_frontend(c, pcm + offsets[u], n, sr, spec, NULL, frames);
+    fao_result* R = fao_analyze_frames(c, frames, F, 0);
+    if (out_rows) out_rows[u] = R->n_feature_rows;
+    total_frames += F;
+    fao_free(R);
+    free(frames);
+    free(spec);
+  }
+  return total_frames;
+}
+
+/* jsmath taps for the literal transliteration and for tests */
+FAO_API double fao_js_log10(double x) { return fa_js_log10(x); }
+FAO_API double fao_js_log(double x) { return fa_js_log(x); }
+FAO_API double fao_js_pow(double x, double y) { return fa_js_pow(x, y); }
