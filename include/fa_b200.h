@@ -32,6 +32,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define FA_API __attribute__((visibility("default")))
+#else
+#define FA_API
+#endif
+
 #define FA_N_FEATURES 53 /* /root/reference/src/localstore.js:7 (levels 5 and 13 -> 53) */
 #define FA_ABI_VERSION 1
 
@@ -127,69 +133,69 @@ typedef struct fa_counts {
 
 typedef struct fa_handle fa_handle;
 
-void fa_config_default(fa_config* cfg);
-int fa_abi_version(void);
-const char* fa_status_string(int status);
+FA_API void fa_config_default(fa_config* cfg);
+FA_API int fa_abi_version(void);
+FA_API const char* fa_status_string(int status);
 
-int fa_create(const fa_config* cfg, int device, fa_handle** out);
-int fa_destroy(fa_handle* h);
-const char* fa_last_error(const fa_handle* h);
+FA_API int fa_create(const fa_config* cfg, int device, fa_handle** out);
+FA_API int fa_destroy(fa_handle* h);
+FA_API const char* fa_last_error(const fa_handle* h);
 
 /* Use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the handle's own. */
-int fa_set_stream(fa_handle* h, void* cuda_stream);
+FA_API int fa_set_stream(fa_handle* h, void* cuda_stream);
 
 /* Drop all submitted utterances and results (StopAudioNodes / a new batch). */
-int fa_reset(fa_handle* h);
+FA_API int fa_reset(fa_handle* h);
 
 /* Copy one utterance of mono float32 PCM (host memory, owned by the caller) into the handle's
  * pinned staging buffer.  All utterances of one batch share sample_rate.  Returns its index. */
-int fa_submit_pcm(fa_handle* h, int64_t utt_id, const float* pcm, size_t n_samples, int sample_rate);
-int fa_submit_pcm_i16(fa_handle* h, int64_t utt_id, const int16_t* pcm, size_t n_samples, int sample_rate);
+FA_API int fa_submit_pcm(fa_handle* h, int64_t utt_id, const float* pcm, size_t n_samples, int sample_rate);
+FA_API int fa_submit_pcm_i16(fa_handle* h, int64_t utt_id, const int16_t* pcm, size_t n_samples, int sample_rate);
 
 /* Asynchronously: H2D copy of the staged PCM, stages 1-4 on the handle's stream, D2H of the result
  * tables.  fa_sync waits for it. */
-int fa_run(fa_handle* h);
-int fa_sync(fa_handle* h);
+FA_API int fa_run(fa_handle* h);
+FA_API int fa_sync(fa_handle* h);
 
 /* Device-resident variant for throughput measurement: upload once ... */
-int fa_upload(fa_handle* h);
+FA_API int fa_upload(fa_handle* h);
 /* ... then run only the kernels on the resident PCM (no H2D, no D2H). */
-int fa_run_resident(fa_handle* h);
+FA_API int fa_run_resident(fa_handle* h);
 /* and fetch the result tables of the last resident run to the host. */
-int fa_download(fa_handle* h);
+FA_API int fa_download(fa_handle* h);
 
 /* Per-stage device time of the last run in milliseconds (CUDA events on the handle's stream):
  * [0] spectrum, [1] peaks, [2] segment scan, [3] features, [4] whole run incl. copies. */
-int fa_stage_times(fa_handle* h, float ms[5]);
+FA_API int fa_stage_times(fa_handle* h, float ms[5]);
 /* Number of kernel launches issued by the last run. */
-int fa_launch_count(fa_handle* h);
+FA_API int fa_launch_count(fa_handle* h);
 
-int fa_num_utterances(const fa_handle* h);
-int fa_result_counts(fa_handle* h, int64_t utt_id, fa_counts* out);
-int fa_total_counts(fa_handle* h, fa_counts* out);
+FA_API int fa_num_utterances(const fa_handle* h);
+FA_API int fa_result_counts(fa_handle* h, int64_t utt_id, fa_counts* out);
+FA_API int fa_total_counts(fa_handle* h, fa_counts* out);
 
 /* Caller-allocated destinations; `cap` counts elements of the destination type's row
  * (rows for tables).  Return value: rows written (>= 0) or an fa_status (< 0). */
-int fa_copy_spectrum(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows);      /* rows of fft_size/2 dB values */
-int fa_copy_frames(fa_handle* h, int64_t utt_id, uint32_t* dst, size_t cap_rows);     /* rows of `bands` uint32 */
-int fa_copy_segments(fa_handle* h, int64_t utt_id, fa_segment* dst, size_t cap_rows);
-int fa_copy_formants(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows);      /* rows of 9 float32 */
-int fa_copy_energy(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows);        /* rows of 3 float32 */
-int fa_copy_syllables(fa_handle* h, int64_t utt_id, fa_syllable* dst, size_t cap_rows);
-int fa_copy_features(fa_handle* h, int64_t utt_id, double* dst, size_t cap_rows);     /* rows of 53 doubles */
+FA_API int fa_copy_spectrum(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows);      /* rows of fft_size/2 dB values */
+FA_API int fa_copy_frames(fa_handle* h, int64_t utt_id, uint32_t* dst, size_t cap_rows);     /* rows of `bands` uint32 */
+FA_API int fa_copy_segments(fa_handle* h, int64_t utt_id, fa_segment* dst, size_t cap_rows);
+FA_API int fa_copy_formants(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows);      /* rows of 9 float32 */
+FA_API int fa_copy_energy(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows);        /* rows of 3 float32 */
+FA_API int fa_copy_syllables(fa_handle* h, int64_t utt_id, fa_syllable* dst, size_t cap_rows);
+FA_API int fa_copy_features(fa_handle* h, int64_t utt_id, double* dst, size_t cap_rows);     /* rows of 53 doubles */
 
 /* Stage-level taps for parity tests (candidate peaks of stage 2: packed lo | hi<<8 | pk<<16 | last<<24). */
-int fa_copy_peak_candidates(fa_handle* h, int64_t utt_id, uint32_t* packed, int32_t* counts, size_t cap_rows,
+FA_API int fa_copy_peak_candidates(fa_handle* h, int64_t utt_id, uint32_t* packed, int32_t* counts, size_t cap_rows,
                             int32_t* max_per_frame);
 
 /* Host-side helpers that the shims share (no device needed). */
-int fa_hop_samples(const fa_config* cfg, int sample_rate);
-int fa_frames_for(const fa_config* cfg, int sample_rate, size_t n_samples);
-int fa_spec_bands(const fa_config* cfg);
+FA_API int fa_hop_samples(const fa_config* cfg, int sample_rate);
+FA_API int fa_frames_for(const fa_config* cfg, int sample_rate, size_t n_samples);
+FA_API int fa_spec_bands(const fa_config* cfg);
 
 /* Synthetic "glottal pulse through formant resonators" speech; host code,
  * deterministic in (seed, utt_index).  Used by bench.py and the tests to build workloads. */
-int fa_synth_speech(float* dst, size_t n_samples, int sample_rate, uint64_t seed, uint64_t utt_index);
+FA_API int fa_synth_speech(float* dst, size_t n_samples, int sample_rate, uint64_t seed, uint64_t utt_index);
 
 #ifdef __cplusplus
 }

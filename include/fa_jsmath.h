@@ -22,7 +22,7 @@
 
 #if defined(__CUDACC__)
 #define FA_HD __host__ __device__ __forceinline__
-#define FA_HD_NOINLINE __host__ __device__
+#define FA_HD_NOINLINE static __host__ __device__
 #else
 #define FA_HD static inline
 #define FA_HD_NOINLINE static

@@ -1,0 +1,77 @@
+"""ctypes binding of libfa_b200.so -- the C-ABI declared in include/fa_b200.h.
+
+There is deliberately no fallback: if the CUDA library is missing this module raises, and if no
+sm_100 device is present fa_create returns FA_ERR_NO_DEVICE (surfaced as FaError).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from ._ctypes_defs import FaConfig, FaCounts, FaSegment, FaSyllable
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfa_b200.so")
+
+FA_OK = 0
+FA_ERR_INVALID_ARG, FA_ERR_NO_DEVICE, FA_ERR_CUDA, FA_ERR_NOT_RUN, FA_ERR_UNKNOWN_UTT = -1, -2, -3, -4, -5
+FA_ERR_CAPACITY, FA_ERR_OUT_OF_MEMORY, FA_ERR_BUSY, FA_ERR_UNSUPPORTED = -6, -7, -8, -9
+
+# every symbol include/fa_b200.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "fa_config_default", "fa_abi_version", "fa_status_string", "fa_create", "fa_destroy", "fa_last_error",
+    "fa_set_stream", "fa_reset", "fa_submit_pcm", "fa_submit_pcm_i16", "fa_run", "fa_sync", "fa_upload",
+    "fa_run_resident", "fa_download", "fa_stage_times", "fa_launch_count", "fa_num_utterances", "fa_result_counts",
+    "fa_total_counts", "fa_copy_spectrum", "fa_copy_frames", "fa_copy_segments", "fa_copy_formants", "fa_copy_energy",
+    "fa_copy_syllables", "fa_copy_features", "fa_copy_peak_candidates", "fa_hop_samples", "fa_frames_for",
+    "fa_spec_bands", "fa_synth_speech",
+]
+
+
+class FaError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"fa_b200 status {status}: {message}")
+        self.status = status
+        self.message = message
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libfa_b200.so (built in-tree by webspeechanalyzer_b200/build.py).  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m webspeechanalyzer_b200.build` "
+            "(or __graft_entry__.build()).  There is no CPU fallback for the hot path.")
+    L = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    cfgp = C.POINTER(FaConfig)
+    L.fa_config_default.argtypes = [cfgp]; L.fa_config_default.restype = None
+    L.fa_abi_version.restype = C.c_int
+    L.fa_status_string.argtypes = [C.c_int]; L.fa_status_string.restype = C.c_char_p
+    L.fa_create.argtypes = [cfgp, C.c_int, C.POINTER(H)]
+    L.fa_destroy.argtypes = [H]
+    L.fa_last_error.argtypes = [H]; L.fa_last_error.restype = C.c_char_p
+    L.fa_set_stream.argtypes = [H, C.c_void_p]
+    L.fa_reset.argtypes = [H]
+    L.fa_submit_pcm.argtypes = [H, C.c_int64, C.c_void_p, C.c_size_t, C.c_int]
+    L.fa_submit_pcm_i16.argtypes = [H, C.c_int64, C.c_void_p, C.c_size_t, C.c_int]
+    for n in ("fa_run", "fa_sync", "fa_upload", "fa_run_resident", "fa_download", "fa_launch_count", "fa_num_utterances"):
+        getattr(L, n).argtypes = [H]
+    L.fa_stage_times.argtypes = [H, C.POINTER(C.c_float)]
+    L.fa_result_counts.argtypes = [H, C.c_int64, C.POINTER(FaCounts)]
+    L.fa_total_counts.argtypes = [H, C.POINTER(FaCounts)]
+    for n in ("fa_copy_spectrum", "fa_copy_frames", "fa_copy_segments", "fa_copy_formants", "fa_copy_energy",
+              "fa_copy_syllables", "fa_copy_features"):
+        getattr(L, n).argtypes = [H, C.c_int64, C.c_void_p, C.c_size_t]
+    L.fa_copy_peak_candidates.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32)]
+    L.fa_hop_samples.argtypes = [cfgp, C.c_int]
+    L.fa_frames_for.argtypes = [cfgp, C.c_int, C.c_size_t]
+    L.fa_spec_bands.argtypes = [cfgp]
+    L.fa_synth_speech.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_uint64]
+    _lib = L
+    return L

@@ -1,0 +1,58 @@
+"""Builds webspeechanalyzer_b200/libfa_b200.so (hand-written CUDA for sm_100a behind the C-ABI of include/fa_b200.h).
+
+In-tree build with nvcc: the .so travels to the GPU box with the repo snapshot.  --fmad=false and
+-ffp-contract=off are part of the arithmetic contract: every fused multiply-add in the
+kernels is an explicit fmaf(), so the float32 / float64 DAGs match the CPU oracle bit for bit.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libfa_b200.so")
+SOURCES = ["fa_spectrum.cu", "fa_peaks.cu", "fa_segment.cu", "fa_features.cu", "fa_capi.cu", "fa_synth.cpp"]
+HEADERS = [os.path.join(CSRC, "fa_internal.cuh")] + [os.path.join(ROOT, "include", h)
+                                                      for h in ("fa_b200.h", "fa_jsmath.h", "fa_tables.h")]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
+         "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "-diag-suppress", "39,222",
+         "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    procs = []
+    for s in SOURCES:
+        o = os.path.join(objdir, os.path.splitext(s)[0] + ".o")
+        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(o)
+    for s, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(out)
+        if p.returncode:
+            raise RuntimeError(f"nvcc failed on {s}")
+    subprocess.check_call([NVCC, "-shared", "-o", LIB + ".tmp"] + objs + ["-Xcompiler", "-fPIC", "-cudart", "static"])
+    os.replace(LIB + ".tmp", LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,698 @@
+// fa_capi.cu -- the C-ABI of libfa_b200.so (include/fa_b200.h): handles, batches, HBM layout, launches.
+//
+// HBM layout of one batch (all sizes derived from the submitted utterances; F = total frames):
+//   pcm        float32 [sum of 4-aligned utterance lengths + pad]     read once by K1
+//   spec_db    float32 [F][fft_size/2]         (only when the spectrum is wanted)      written once by K1
+//   frames     uint32  [F][bands]              K1 -> K2, K3
+//   cand/ncand/gsum  uint32 [F][maxp], int32 [F], float64 [F]       K2 -> K3
+//   track table / point pool / row scratch     K3 workspace, per utterance, sized from its frame count
+//   segs / syls / formants[F][9] / energy[F][3] / features          K3, K4 outputs, per-utterance regions
+//   dense segs / syls / formants / energy / features + offsets      K5 gather -> one D2H copy each
+// There is no CPU fallback: every entry point that computes needs the device.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "fa_internal.cuh"
+#include "fa_jsmath.h"
+#include "fa_tables.h"
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostBuf {  // pinned
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes, size_t keep = 0) {
+    if (bytes <= cap) return cudaSuccess;
+    size_t want = std::max(bytes, cap * 2);
+    void* q = nullptr;
+    cudaError_t e = cudaHostAlloc(&q, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) { want = bytes; e = cudaHostAlloc(&q, want, cudaHostAllocDefault); }
+    if (e != cudaSuccess) return e;
+    if (p && keep) memcpy(q, p, keep);
+    if (p) cudaFreeHost(p);
+    p = q;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Utt {
+  int64_t id;
+  long long off;     // first sample in the staging buffer (multiple of 4)
+  long long n;       // samples
+  long long row0;    // first frame row
+  int frames;
+};
+
+}  // namespace
+
+struct fa_handle {
+  fa_config cfg;
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::string err;
+  int sample_rate = 0, hop = 0, B = 0, N = 0, M = 0, logM = 0, maxp = 0;
+  bool tables_ready = false;
+  int tables_sr = 0;
+  std::vector<Utt> utts;
+  std::unordered_map<int64_t, int> index;
+  long long staged = 0;        // floats used in h_pcm
+  long long total_frames = 0;
+  HostBuf h_pcm, h_meta, h_counts, h_off, h_segs, h_syls, h_formants, h_energy, h_features;
+  DevBuf d_pcm, d_meta, d_spec, d_frames, d_cand, d_ncand, d_gsum, d_counter;
+  DevBuf d_win, d_tw, d_tws, d_ws, d_bmi, d_bmw, d_emph;
+  DevBuf d_trkbase, d_trk_i, d_trk_d, d_trk_slot, d_pt_i, d_pt_e, d_rows, d_rowlist;
+  DevBuf d_segs, d_syls, d_formants, d_energy, d_features, d_counts, d_off;
+  DevBuf g_segs, g_syls, g_formants, g_energy, g_features;
+  int n_weights = 0;
+  long long track_total = 0;
+  bool uploaded = false, ran = false, downloaded = false, want_spec = false;
+  long long tot[4] = {0, 0, 0, 0};  // segs, rows, syls, feat
+  cudaEvent_t ev[8] = {};
+  float stage_ms[5] = {0, 0, 0, 0, 0};
+  int launches = 0;
+};
+
+namespace {
+
+int fail(fa_handle* h, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (h) {
+    h->err = what;
+    if (e != cudaSuccess) { h->err += ": "; h->err += cudaGetErrorString(e); }
+  }
+  return code;
+}
+
+#define FA_CUDA(call)                                                        \
+  do {                                                                       \
+    cudaError_t e__ = (call);                                                \
+    if (e__ != cudaSuccess) return fail(h, e__ == cudaErrorMemoryAllocation ? FA_ERR_OUT_OF_MEMORY : FA_ERR_CUDA, #call, e__); \
+  } while (0)
+
+bool level_supported(int lvl) {
+  return lvl == FA_LEVEL_BARS || lvl == FA_LEVEL_SPECTRUM || lvl == FA_LEVEL_FORMANTS || lvl == FA_LEVEL_SEG_FEATURES ||
+         lvl == FA_LEVEL_SYL_FORMANTS || lvl == FA_LEVEL_SYL_FEATURES;
+}
+
+int validate(const fa_config* c, std::string* why) {
+  if (!fa_tab_valid_fft(c->fft_size)) { *why = "fft_size must be a power of two in [256, 16384]"; return FA_ERR_UNSUPPORTED; }
+  if (!level_supported(c->output_level)) { *why = "output_level not supported (levels 1, 2, 4, 5, 10, 13)"; return FA_ERR_UNSUPPORTED; }
+  if (c->spec_type < 1 || c->spec_type > 3) { *why = "Invalid reset_nodes config"; return FA_ERR_INVALID_ARG; }
+  const int B = fa_tab_bands(c);
+  if (B < 8 || B > FA_MAX_BANDS) { *why = "Invalid spec_bands"; return FA_ERR_INVALID_ARG; }
+  if (!(c->window_step_ms > 0) || !(c->f_max > c->f_min) || !(c->f_min >= 0)) { *why = "Invalid reset_nodes config"; return FA_ERR_INVALID_ARG; }
+  if (!(c->smoothing >= 0.0 && c->smoothing <= 1.0)) { *why = "smoothingTimeConstant must be in [0, 1]"; return FA_ERR_INVALID_ARG; }
+  return FA_OK;
+}
+
+int build_tables(fa_handle* h, int sr) {
+  const fa_config& c = h->cfg;
+  const int N = c.fft_size, M = N / 2;
+  h->N = N; h->M = M; h->logM = fa_tab_log2(M); h->B = fa_tab_bands(&c);
+  h->hop = fa_tab_hop(sr, c.window_step_ms);
+  h->maxp = h->B / 2 + 4;
+  std::vector<float> win(N), tw(M), ws(2 * M), tws(2 * (size_t)(M - 1)), emph(h->B);
+  fa_tab_window(N, win.data());
+  fa_tab_fft_twiddles(M, tw.data());
+  fa_tab_split_twiddles(M, ws.data());
+  for (int s = 1; s <= h->logM; s++) {
+    const int half = 1 << (s - 1), stride = M >> s, off = half - 1;
+    for (int j = 0; j < half; j++) {
+      tws[2 * (size_t)(off + j)] = tw[2 * (size_t)(j * stride)];
+      tws[2 * (size_t)(off + j) + 1] = tw[2 * (size_t)(j * stride) + 1];
+    }
+  }
+  fa_bandmat bm;
+  if (fa_tab_bandmat(&c, sr, &bm) < 0) return fail(h, FA_ERR_OUT_OF_MEMORY, "band matrix");
+  for (int m = 0; m < h->B; m++) emph[m] = (float)((double)m * c.high_f_emph);
+  h->n_weights = bm.n_weights;
+  std::vector<int> bmi(3 * (size_t)h->B + 1);
+  for (int m = 0; m < h->B; m++) { bmi[m] = bm.k0[m]; bmi[h->B + m] = bm.cnt[m]; bmi[2 * h->B + m] = bm.off[m]; }
+  bmi[3 * (size_t)h->B] = bm.off[h->B];
+  cudaStream_t s = h->stream;
+  int rc = FA_OK;
+  do {
+#define FA_UP(buf, vec)                                                                                   \
+  {                                                                                                       \
+    cudaError_t e = buf.reserve(std::max<size_t>(16, vec.size() * sizeof(vec[0])));                      \
+    if (e == cudaSuccess && !vec.empty())                                                                 \
+      e = cudaMemcpyAsync(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice, s);     \
+    if (e != cudaSuccess) { rc = fail(h, FA_ERR_CUDA, "table upload", e); break; }                        \
+  }
+    FA_UP(h->d_win, win);
+    FA_UP(h->d_tw, tw);
+    FA_UP(h->d_tws, tws);
+    FA_UP(h->d_ws, ws);
+    FA_UP(h->d_bmi, bmi);
+    FA_UP(h->d_emph, emph);
+    {
+      std::vector<float> w(bm.w, bm.w + std::max(1, bm.n_weights));
+      FA_UP(h->d_bmw, w);
+    }
+#undef FA_UP
+    cudaError_t e = cudaStreamSynchronize(s);  // the vectors above die at scope exit
+    if (e != cudaSuccess) rc = fail(h, FA_ERR_CUDA, "table upload sync", e);
+  } while (0);
+  fa_tab_bandmat_free(&bm);
+  if (rc == FA_OK) { h->tables_ready = true; h->tables_sr = sr; }
+  return rc;
+}
+
+Utt* find_utt(fa_handle* h, int64_t id) {
+  auto it = h->index.find(id);
+  return it == h->index.end() ? nullptr : &h->utts[it->second];
+}
+
+}  // namespace
+
+extern "C" {
+
+void fa_config_default(fa_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->spec_type = 1; c->output_level = 4; c->plot_len = 200; c->n_fft_bins = 256; c->n_mel_bins = 128;
+  c->auto_noise_gate = 1; c->f_min = 50; c->f_max = 4000; c->window_width_ms = 25; c->window_step_ms = 25;
+  c->pause_length_ms = 200; c->min_seg_length_ms = 50; c->voiced_max_db = 100; c->voiced_min_db = 10;
+  c->pre_norm_gain = 1000; c->high_f_emph = 0; c->fft_size = 2048; c->clamp_db = 1; c->want_spectrum = 0;
+  c->smoothing = 0.8; c->min_db = -100; c->max_db = -30; c->mag_scale = 0;
+}
+
+int fa_abi_version(void) { return FA_ABI_VERSION; }
+
+const char* fa_status_string(int s) {
+  switch (s) {
+    case FA_OK: return "ok";
+    case FA_ERR_INVALID_ARG: return "invalid argument";
+    case FA_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (there is no CPU fallback)";
+    case FA_ERR_CUDA: return "CUDA error";
+    case FA_ERR_NOT_RUN: return "results requested before fa_run/fa_sync";
+    case FA_ERR_UNKNOWN_UTT: return "unknown utterance id";
+    case FA_ERR_CAPACITY: return "capacity exceeded";
+    case FA_ERR_OUT_OF_MEMORY: return "out of memory";
+    case FA_ERR_BUSY: return "Error: Already playing";
+    case FA_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown status";
+  }
+}
+
+int fa_hop_samples(const fa_config* c, int sr) { return fa_tab_hop(sr, c->window_step_ms); }
+int fa_frames_for(const fa_config* c, int sr, size_t n) { return (int)(n / (size_t)fa_tab_hop(sr, c->window_step_ms)); }
+int fa_spec_bands(const fa_config* c) { return fa_tab_bands(c); }
+
+int fa_create(const fa_config* cfg, int device, fa_handle** out) {
+  if (!cfg || !out) return FA_ERR_INVALID_ARG;
+  *out = nullptr;
+  std::string why;
+  const int v = validate(cfg, &why);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return FA_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) return FA_ERR_NO_DEVICE;
+  if (v != FA_OK) return v;
+  fa_handle* h = new fa_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return FA_ERR_CUDA;
+  }
+  h->stream = h->own_stream;
+  for (auto& e : h->ev) cudaEventCreate(&e);
+  h->want_spec = cfg->want_spectrum || cfg->output_level <= 2;
+  *out = h;
+  return FA_OK;
+}
+
+int fa_destroy(fa_handle* h) {
+  if (!h) return FA_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (DevBuf* b : {&h->d_pcm, &h->d_meta, &h->d_spec, &h->d_frames, &h->d_cand, &h->d_ncand, &h->d_gsum, &h->d_counter,
+                    &h->d_win, &h->d_tw, &h->d_tws, &h->d_ws, &h->d_bmi, &h->d_bmw, &h->d_emph, &h->d_trkbase, &h->d_trk_i,
+                    &h->d_trk_d, &h->d_trk_slot, &h->d_pt_i, &h->d_pt_e, &h->d_rows, &h->d_rowlist, &h->d_segs, &h->d_syls,
+                    &h->d_formants, &h->d_energy, &h->d_features, &h->d_counts, &h->d_off, &h->g_segs, &h->g_syls,
+                    &h->g_formants, &h->g_energy, &h->g_features})
+    b->release();
+  for (HostBuf* b : {&h->h_pcm, &h->h_meta, &h->h_counts, &h->h_off, &h->h_segs, &h->h_syls, &h->h_formants, &h->h_energy,
+                     &h->h_features})
+    b->release();
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return FA_OK;
+}
+
+const char* fa_last_error(const fa_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int fa_set_stream(fa_handle* h, void* s) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->stream = s ? reinterpret_cast<cudaStream_t>(s) : h->own_stream;
+  return FA_OK;
+}
+
+int fa_reset(fa_handle* h) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->utts.clear();
+  h->index.clear();
+  h->staged = 0;
+  h->total_frames = 0;
+  h->uploaded = h->ran = h->downloaded = false;
+  return FA_OK;
+}
+
+static int submit_common(fa_handle* h, int64_t utt_id, size_t n, int sr, float** dst) {
+  if (!h || sr <= 0) return fail(h, FA_ERR_INVALID_ARG, "Invalid audio source");
+  if (h->index.count(utt_id)) return fail(h, FA_ERR_INVALID_ARG, "duplicate utterance id");
+  cudaSetDevice(h->device);
+  if (h->utts.empty()) h->sample_rate = sr;
+  else if (sr != h->sample_rate) return fail(h, FA_ERR_INVALID_ARG, "all utterances of a batch must share the sample rate");
+  if (h->uploaded || h->ran) return fail(h, FA_ERR_BUSY, "Error: Already playing");
+  const long long off = h->staged;
+  const long long padded = ((long long)n + 3) & ~3ll;
+  FA_CUDA(h->h_pcm.reserve((size_t)(off + padded + 16) * sizeof(float), (size_t)off * sizeof(float)));
+  Utt u;
+  u.id = utt_id; u.off = off; u.n = (long long)n;
+  u.frames = (int)(n / (size_t)fa_tab_hop(sr, h->cfg.window_step_ms));
+  u.row0 = h->total_frames;
+  h->index[utt_id] = (int)h->utts.size();
+  h->utts.push_back(u);
+  h->staged = off + padded;
+  h->total_frames += u.frames;
+  *dst = h->h_pcm.as<float>() + off;
+  for (long long i = (long long)n; i < padded; i++) (*dst)[i] = 0.f;
+  return (int)h->utts.size() - 1;
+}
+
+int fa_submit_pcm(fa_handle* h, int64_t utt_id, const float* pcm, size_t n, int sr) {
+  if (!pcm && n) return fail(h, FA_ERR_INVALID_ARG, "Invalid audio source");
+  float* dst = nullptr;
+  const int rc = submit_common(h, utt_id, n, sr, &dst);
+  if (rc < 0) return rc;
+  if (n) memcpy(dst, pcm, n * sizeof(float));
+  return rc;
+}
+
+int fa_submit_pcm_i16(fa_handle* h, int64_t utt_id, const int16_t* pcm, size_t n, int sr) {
+  if (!pcm && n) return fail(h, FA_ERR_INVALID_ARG, "Invalid audio source");
+  float* dst = nullptr;
+  const int rc = submit_common(h, utt_id, n, sr, &dst);
+  if (rc < 0) return rc;
+  for (size_t i = 0; i < n; i++) dst[i] = (float)pcm[i] * (1.0f / 32768.0f);
+  return rc;
+}
+
+int fa_upload(fa_handle* h) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  if (h->utts.empty()) return fail(h, FA_ERR_INVALID_ARG, "Invalid audio source");
+  if (!h->tables_ready || h->tables_sr != h->sample_rate) {
+    const int rc = build_tables(h, h->sample_rate);
+    if (rc != FA_OK) return rc;
+  }
+  const int n = (int)h->utts.size();
+  const long long F = h->total_frames;
+  cudaStream_t s = h->stream;
+  // meta: utt_off[n], utt_len[n], frame_off[n+1], track_base[n+1]
+  FA_CUDA(h->h_meta.reserve(sizeof(long long) * (4 * (size_t)n + 2)));
+  long long* m = h->h_meta.as<long long>();
+  long long tb = 0;
+  for (int i = 0; i < n; i++) {
+    m[i] = h->utts[i].off;
+    m[n + i] = h->utts[i].n;
+    m[2 * n + i] = h->utts[i].row0;
+    m[3 * n + 1 + i] = tb;
+    tb += (long long)h->utts[i].frames * 16 + 64;
+  }
+  m[2 * n + n] = F;
+  m[3 * n + 1 + n] = tb;
+  h->track_total = tb;
+  FA_CUDA(h->d_meta.reserve(sizeof(long long) * (4 * (size_t)n + 2)));
+  FA_CUDA(cudaMemcpyAsync(h->d_meta.p, m, sizeof(long long) * (4 * (size_t)n + 2), cudaMemcpyHostToDevice, s));
+  FA_CUDA(h->d_pcm.reserve((size_t)(h->staged + 16) * sizeof(float)));
+  FA_CUDA(cudaMemcpyAsync(h->d_pcm.p, h->h_pcm.p, (size_t)(h->staged + 16) * sizeof(float), cudaMemcpyHostToDevice, s));
+  // outputs / workspaces
+  const size_t Fz = (size_t)std::max<long long>(F, 1), nz = (size_t)n;
+  if (h->want_spec) FA_CUDA(h->d_spec.reserve(Fz * h->M * sizeof(float)));
+  FA_CUDA(h->d_frames.reserve(Fz * h->B * sizeof(uint32_t)));
+  FA_CUDA(h->d_counter.reserve(16));
+  if (h->cfg.output_level >= 3) {
+    FA_CUDA(h->d_cand.reserve(Fz * h->maxp * sizeof(uint32_t)));
+    FA_CUDA(h->d_ncand.reserve(Fz * sizeof(int)));
+    FA_CUDA(h->d_gsum.reserve(Fz * sizeof(double)));
+    const size_t T = (size_t)std::max<long long>(tb, 1);
+    FA_CUDA(h->d_trk_i.reserve(T * 3 * sizeof(int)));        // count, order, rank
+    FA_CUDA(h->d_trk_d.reserve(T * 3 * sizeof(double)));     // sum_e, sum_eb, mean
+    FA_CUDA(h->d_trk_slot.reserve(T));
+    const size_t P = Fz * h->maxp;
+    FA_CUDA(h->d_pt_i.reserve(P * 4 * sizeof(int)));         // track, ord, frame, binspan
+    FA_CUDA(h->d_pt_e.reserve(P * sizeof(double)));
+    FA_CUDA(h->d_rows.reserve((Fz + nz) * 2 * sizeof(int)));
+    FA_CUDA(h->d_rowlist.reserve(P * sizeof(int)));
+    FA_CUDA(h->d_segs.reserve((Fz + nz) * sizeof(fa_segment)));
+    FA_CUDA(h->d_syls.reserve((Fz + nz) * sizeof(fa_syllable)));
+    FA_CUDA(h->d_formants.reserve(Fz * 9 * sizeof(float)));
+    FA_CUDA(h->d_energy.reserve(Fz * 3 * sizeof(float)));
+    if (h->cfg.output_level == 5 || h->cfg.output_level == 13)
+      FA_CUDA(h->d_features.reserve((Fz + nz) * FA_N_FEATURES * sizeof(double)));
+    FA_CUDA(h->d_counts.reserve(nz * 6 * sizeof(int)));      // n_segs, n_stored, n_rows, n_syls, n_feat, overflow
+    FA_CUDA(h->d_off.reserve((nz + 1) * 4 * sizeof(long long)));
+    FA_CUDA(h->g_segs.reserve((Fz + nz) * sizeof(fa_segment)));
+    FA_CUDA(h->g_syls.reserve((Fz + nz) * sizeof(fa_syllable)));
+    FA_CUDA(h->g_formants.reserve(Fz * 9 * sizeof(float)));
+    FA_CUDA(h->g_energy.reserve(Fz * 3 * sizeof(float)));
+    if (h->cfg.output_level == 5 || h->cfg.output_level == 13)
+      FA_CUDA(h->g_features.reserve((Fz + nz) * FA_N_FEATURES * sizeof(double)));
+  }
+  h->uploaded = true;
+  h->ran = false;
+  h->downloaded = false;
+  return FA_OK;
+}
+
+int fa_run_resident(fa_handle* h) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  if (!h->uploaded) return fail(h, FA_ERR_NOT_RUN, "fa_run_resident before fa_upload");
+  cudaSetDevice(h->device);
+  cudaStream_t s = h->stream;
+  const fa_config& c = h->cfg;
+  const int n = (int)h->utts.size();
+  const long long F = h->total_frames;
+  const long long* meta = h->d_meta.as<long long>();
+  h->launches = 0;
+  FA_CUDA(cudaEventRecord(h->ev[0], s));
+
+  FaSpectrumParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.pcm = h->d_pcm.as<float>();
+  sp.utt_off = meta; sp.utt_len = meta + n; sp.frame_off = meta + 2 * n;
+  sp.n_utt = n; sp.hop = h->hop; sp.N = h->N; sp.M = h->M; sp.logM = h->logM; sp.B = h->B;
+  sp.win = h->d_win.as<float>(); sp.tw = h->d_tw.as<float2>(); sp.tw_stage = h->d_tws.as<float2>(); sp.ws = h->d_ws.as<float2>();
+  sp.bm_k0 = h->d_bmi.as<int>(); sp.bm_cnt = sp.bm_k0 + h->B; sp.bm_off = sp.bm_k0 + 2 * h->B;
+  sp.bm_w = h->d_bmw.as<float>(); sp.n_weights = h->n_weights;
+  sp.emph = h->d_emph.as<float>(); sp.use_emph = c.high_f_emph != 0.0; sp.power = c.spec_type == FA_SPEC_POWER;
+  sp.gain = fa_tab_gain(&c); sp.tau = (float)c.smoothing; sp.omt = (float)(1.0 - c.smoothing);
+  sp.inv2N = (float)(1.0 / (2.0 * (double)h->N)); sp.min_db = (float)c.min_db; sp.max_db = (float)c.max_db;
+  sp.clamp_db = c.clamp_db;
+  sp.spec_db = h->want_spec ? h->d_spec.as<float>() : nullptr;
+  sp.frames = h->d_frames.as<uint32_t>();
+  sp.work_counter = h->d_counter.as<int>();
+  FA_CUDA(fa_launch_spectrum(sp, s, &h->launches));
+  FA_CUDA(cudaEventRecord(h->ev[1], s));
+
+  if (c.output_level >= 3 && F > 0) {
+    FaPeaksParams pp;
+    pp.frames = h->d_frames.as<uint32_t>(); pp.B = h->B; pp.maxp = h->maxp; pp.n_frames = F;
+    pp.cand = h->d_cand.as<uint32_t>(); pp.ncand = h->d_ncand.as<int>(); pp.gsum = h->d_gsum.as<double>();
+    FA_CUDA(fa_launch_peaks(pp, s, &h->launches));
+  }
+  FA_CUDA(cudaEventRecord(h->ev[2], s));
+
+  if (c.output_level >= 3) {
+    const size_t T = (size_t)std::max<long long>(h->track_total, 1);
+    const size_t P = (size_t)std::max<long long>(F, 1) * h->maxp;
+    const size_t R = (size_t)std::max<long long>(F, 1) + n;
+    FaSegmentParams g;
+    memset(&g, 0, sizeof(g));
+    g.frames = h->d_frames.as<uint32_t>(); g.cand = h->d_cand.as<uint32_t>(); g.ncand = h->d_ncand.as<int>();
+    g.gsum = h->d_gsum.as<double>(); g.frame_off = meta + 2 * n; g.n_utt = n; g.B = h->B; g.maxp = h->maxp;
+    g.level = c.output_level;
+    g.max_voiced_bin = (int)fa_js_parse_int(0.7 * (double)h->B);
+    g.seg_min_frames = (int)fa_js_parse_int(c.min_seg_length_ms / c.window_step_ms);
+    g.auto_gate = c.auto_noise_gate;
+    g.seg_breaker = c.pause_length_ms > 2 * c.window_step_ms ? c.pause_length_ms / c.window_step_ms : 250 / c.window_step_ms;
+    if (c.auto_noise_gate) { g.y0 = 50; g.v0 = 2; }
+    else { g.y0 = fa_js_pow(10, c.voiced_max_db / 20); g.v0 = fa_js_pow(10, c.voiced_min_db / 20); }
+    g.track_base = const_cast<long long*>(meta + 3 * n + 1);
+    g.trk_count = h->d_trk_i.as<int>(); g.trk_order = g.trk_count + T; g.trk_rank = g.trk_order + T;
+    g.trk_sum_e = h->d_trk_d.as<double>(); g.trk_sum_eb = g.trk_sum_e + T; g.trk_mean = g.trk_sum_eb + T;
+    g.trk_slot = h->d_trk_slot.as<signed char>();
+    g.pt_track = h->d_pt_i.as<int>(); g.pt_ord = g.pt_track + P; g.pt_frame = g.pt_ord + P; g.pt_binspan = g.pt_frame + P;
+    g.pt_e = h->d_pt_e.as<double>();
+    g.row_count = h->d_rows.as<int>(); g.row_off = g.row_count + R; g.row_list = h->d_rowlist.as<int>();
+    g.segs = h->d_segs.as<fa_segment>(); g.syls = h->d_syls.as<fa_syllable>();
+    g.formants = h->d_formants.as<float>(); g.energy = h->d_energy.as<float>();
+    int* cnt = h->d_counts.as<int>();
+    g.n_segs = cnt; g.n_stored = cnt + n; g.n_rows = cnt + 2 * n; g.n_syls = cnt + 3 * n; g.overflow = cnt + 5 * n;
+    FA_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * 6 * (size_t)n, s));
+    FA_CUDA(fa_launch_segment(g, s, &h->launches));
+    FA_CUDA(cudaEventRecord(h->ev[3], s));
+
+    if (c.output_level == 5 || c.output_level == 13) {
+      FaFeatureParams fp;
+      fp.frame_off = meta + 2 * n; fp.n_utt = n; fp.level = c.output_level;
+      fp.segs = g.segs; fp.n_segs = g.n_segs; fp.syls = g.syls; fp.n_syls = g.n_syls; fp.formants = g.formants;
+      fp.features = h->d_features.as<double>(); fp.n_feat = cnt + 4 * n;
+      FA_CUDA(fa_launch_features(fp, s, &h->launches));
+    }
+    FA_CUDA(cudaEventRecord(h->ev[4], s));
+
+    FaGatherArgs ga;
+    ga.frame_off = meta + 2 * n; ga.n_utt = n; ga.n_segs = g.n_segs; ga.n_rows = g.n_rows; ga.n_syls = g.n_syls;
+    ga.n_feat = cnt + 4 * n; ga.off = h->d_off.as<long long>();
+    ga.segs = g.segs; ga.syls = g.syls; ga.formants = g.formants; ga.energy = g.energy;
+    ga.features = h->d_features.as<double>();
+    ga.d_segs = h->g_segs.as<fa_segment>(); ga.d_syls = h->g_syls.as<fa_syllable>();
+    ga.d_formants = h->g_formants.as<float>(); ga.d_energy = h->g_energy.as<float>();
+    ga.d_features = h->g_features.as<double>();
+    FA_CUDA(fa_launch_prefix(ga, s, &h->launches));
+    FA_CUDA(fa_launch_gather(ga, s, &h->launches));
+  } else {
+    FA_CUDA(cudaEventRecord(h->ev[3], s));
+    FA_CUDA(cudaEventRecord(h->ev[4], s));
+  }
+  FA_CUDA(cudaEventRecord(h->ev[5], s));
+  h->ran = true;
+  h->downloaded = false;
+  return FA_OK;
+}
+
+int fa_download(fa_handle* h) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  if (!h->ran) return fail(h, FA_ERR_NOT_RUN, "fa_download before a run");
+  cudaSetDevice(h->device);
+  cudaStream_t s = h->stream;
+  const int n = (int)h->utts.size();
+  for (int k = 0; k < 4; k++) h->tot[k] = 0;
+  if (h->cfg.output_level >= 3) {
+    FA_CUDA(h->h_counts.reserve(sizeof(int) * 6 * (size_t)n));
+    FA_CUDA(h->h_off.reserve(sizeof(long long) * 4 * ((size_t)n + 1)));
+    FA_CUDA(cudaMemcpyAsync(h->h_counts.p, h->d_counts.p, sizeof(int) * 6 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    FA_CUDA(cudaMemcpyAsync(h->h_off.p, h->d_off.p, sizeof(long long) * 4 * ((size_t)n + 1), cudaMemcpyDeviceToHost, s));
+    FA_CUDA(cudaStreamSynchronize(s));
+    const long long* off = h->h_off.as<long long>();
+    for (int k = 0; k < 4; k++) h->tot[k] = off[(size_t)k * (n + 1) + n];
+    FA_CUDA(h->h_segs.reserve(std::max<size_t>(16, h->tot[0] * sizeof(fa_segment))));
+    FA_CUDA(h->h_formants.reserve(std::max<size_t>(16, h->tot[1] * 9 * sizeof(float))));
+    FA_CUDA(h->h_energy.reserve(std::max<size_t>(16, h->tot[1] * 3 * sizeof(float))));
+    FA_CUDA(h->h_syls.reserve(std::max<size_t>(16, h->tot[2] * sizeof(fa_syllable))));
+    FA_CUDA(h->h_features.reserve(std::max<size_t>(16, h->tot[3] * FA_N_FEATURES * sizeof(double))));
+    if (h->tot[0]) FA_CUDA(cudaMemcpyAsync(h->h_segs.p, h->g_segs.p, h->tot[0] * sizeof(fa_segment), cudaMemcpyDeviceToHost, s));
+    if (h->tot[1]) {
+      FA_CUDA(cudaMemcpyAsync(h->h_formants.p, h->g_formants.p, h->tot[1] * 9 * sizeof(float), cudaMemcpyDeviceToHost, s));
+      FA_CUDA(cudaMemcpyAsync(h->h_energy.p, h->g_energy.p, h->tot[1] * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    if (h->tot[2]) FA_CUDA(cudaMemcpyAsync(h->h_syls.p, h->g_syls.p, h->tot[2] * sizeof(fa_syllable), cudaMemcpyDeviceToHost, s));
+    if (h->tot[3])
+      FA_CUDA(cudaMemcpyAsync(h->h_features.p, h->g_features.p, h->tot[3] * FA_N_FEATURES * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
+  FA_CUDA(cudaEventRecord(h->ev[6], s));
+  h->downloaded = true;
+  return FA_OK;
+}
+
+int fa_run(fa_handle* h) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  if (h->ran) return fail(h, FA_ERR_BUSY, "Error: Already playing");
+  cudaSetDevice(h->device);
+  FA_CUDA(cudaEventRecord(h->ev[7], h->stream));
+  int rc = fa_upload(h);
+  if (rc != FA_OK) return rc;
+  rc = fa_run_resident(h);
+  if (rc != FA_OK) return rc;
+  return fa_download(h);
+}
+
+int fa_sync(fa_handle* h) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  FA_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->ran) {
+    for (int i = 0; i < 4; i++) cudaEventElapsedTime(&h->stage_ms[i], h->ev[i], h->ev[i + 1]);
+    cudaEventElapsedTime(&h->stage_ms[4], h->ev[0], h->ev[5]);
+  }
+  return FA_OK;
+}
+
+int fa_stage_times(fa_handle* h, float ms[5]) {
+  if (!h || !ms) return FA_ERR_INVALID_ARG;
+  if (!h->ran) return fail(h, FA_ERR_NOT_RUN, "no run yet");
+  const int rc = fa_sync(h);
+  if (rc != FA_OK) return rc;
+  for (int i = 0; i < 5; i++) ms[i] = h->stage_ms[i];
+  return FA_OK;
+}
+
+int fa_launch_count(fa_handle* h) { return h ? h->launches : FA_ERR_INVALID_ARG; }
+int fa_num_utterances(const fa_handle* h) { return h ? (int)h->utts.size() : FA_ERR_INVALID_ARG; }
+
+static int need_results(fa_handle* h) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  if (!h->ran) return fail(h, FA_ERR_NOT_RUN, "results requested before fa_run");
+  cudaSetDevice(h->device);
+  if (!h->downloaded) {
+    const int rc = fa_download(h);
+    if (rc != FA_OK) return rc;
+  }
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return fail(h, FA_ERR_CUDA, "sync", e);
+  return FA_OK;
+}
+
+static void fill_counts(fa_handle* h, int i, fa_counts* c) {
+  const Utt& u = h->utts[i];
+  const int n = (int)h->utts.size();
+  memset(c, 0, sizeof(*c));
+  c->samples = u.n; c->sample_rate = h->sample_rate; c->hop = h->hop; c->frames = u.frames; c->bands = h->B;
+  if (h->cfg.output_level >= 3) {
+    const int* k = h->h_counts.as<int>();
+    c->segments = k[i]; c->stored_segments = k[n + i]; c->formant_rows = k[2 * n + i]; c->syllables = k[3 * n + i];
+    c->feature_rows = k[4 * n + i]; c->overflow = k[5 * n + i];
+  }
+}
+
+int fa_result_counts(fa_handle* h, int64_t utt_id, fa_counts* out) {
+  int rc = need_results(h);
+  if (rc != FA_OK) return rc;
+  if (!out) return FA_ERR_INVALID_ARG;
+  Utt* u = find_utt(h, utt_id);
+  if (!u) return fail(h, FA_ERR_UNKNOWN_UTT, "unknown utterance id");
+  fill_counts(h, (int)(u - h->utts.data()), out);
+  return out->overflow ? fail(h, FA_ERR_CAPACITY, "an internal table overflowed for this utterance") : FA_OK;
+}
+
+int fa_total_counts(fa_handle* h, fa_counts* out) {
+  int rc = need_results(h);
+  if (rc != FA_OK) return rc;
+  if (!out) return FA_ERR_INVALID_ARG;
+  memset(out, 0, sizeof(*out));
+  out->sample_rate = h->sample_rate; out->hop = h->hop; out->bands = h->B;
+  for (size_t i = 0; i < h->utts.size(); i++) {
+    fa_counts c;
+    fill_counts(h, (int)i, &c);
+    out->samples += c.samples; out->frames += c.frames; out->segments += c.segments;
+    out->stored_segments += c.stored_segments; out->formant_rows += c.formant_rows; out->syllables += c.syllables;
+    out->feature_rows += c.feature_rows; out->overflow += c.overflow;
+  }
+  return FA_OK;
+}
+
+// rows of utterance `utt_id` (or of the whole batch when utt_id < 0) from a device table with a fixed row size
+static int copy_rows_device(fa_handle* h, int64_t utt_id, const void* dev, size_t row_bytes, void* dst, size_t cap_rows) {
+  int rc = need_results(h);
+  if (rc != FA_OK) return rc;
+  long long r0 = 0, nr = h->total_frames;
+  if (utt_id >= 0) {
+    Utt* u = find_utt(h, utt_id);
+    if (!u) return fail(h, FA_ERR_UNKNOWN_UTT, "unknown utterance id");
+    r0 = u->row0; nr = u->frames;
+  }
+  if ((size_t)nr > cap_rows) return fail(h, FA_ERR_CAPACITY, "destination too small");
+  if (nr == 0) return 0;
+  if (!dst) return FA_ERR_INVALID_ARG;
+  FA_CUDA(cudaMemcpyAsync(dst, (const char*)dev + (size_t)r0 * row_bytes, (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, h->stream));
+  FA_CUDA(cudaStreamSynchronize(h->stream));
+  return (int)nr;
+}
+
+int fa_copy_spectrum(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  if (!h->want_spec) return fail(h, FA_ERR_INVALID_ARG, "spectrum not materialised (set want_spectrum or output_level <= 2)");
+  return copy_rows_device(h, utt_id, h->d_spec.p, (size_t)h->M * sizeof(float), dst, cap_rows);
+}
+
+int fa_copy_frames(fa_handle* h, int64_t utt_id, uint32_t* dst, size_t cap_rows) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  return copy_rows_device(h, utt_id, h->d_frames.p, (size_t)h->B * sizeof(uint32_t), dst, cap_rows);
+}
+
+// dense host tables: kind 0 segs, 1 rows, 2 syls, 3 feat
+static int copy_dense(fa_handle* h, int64_t utt_id, int kind, const void* host, size_t row_bytes, void* dst, size_t cap_rows) {
+  int rc = need_results(h);
+  if (rc != FA_OK) return rc;
+  if (h->cfg.output_level < 3) return 0;
+  const int n = (int)h->utts.size();
+  const long long* off = h->h_off.as<long long>() + (size_t)kind * (n + 1);
+  long long r0 = 0, nr = off[n];
+  if (utt_id >= 0) {
+    Utt* u = find_utt(h, utt_id);
+    if (!u) return fail(h, FA_ERR_UNKNOWN_UTT, "unknown utterance id");
+    const int i = (int)(u - h->utts.data());
+    if (h->h_counts.as<int>()[5 * n + i]) return fail(h, FA_ERR_CAPACITY, "an internal table overflowed for this utterance");
+    r0 = off[i]; nr = off[i + 1] - off[i];
+  }
+  if ((size_t)nr > cap_rows) return fail(h, FA_ERR_CAPACITY, "destination too small");
+  if (nr && !dst) return FA_ERR_INVALID_ARG;
+  if (nr) memcpy(dst, (const char*)host + (size_t)r0 * row_bytes, (size_t)nr * row_bytes);
+  return (int)nr;
+}
+
+int fa_copy_segments(fa_handle* h, int64_t utt_id, fa_segment* dst, size_t cap) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  return copy_dense(h, utt_id, 0, h->h_segs.p, sizeof(fa_segment), dst, cap);
+}
+int fa_copy_formants(fa_handle* h, int64_t utt_id, float* dst, size_t cap) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  return copy_dense(h, utt_id, 1, h->h_formants.p, 9 * sizeof(float), dst, cap);
+}
+int fa_copy_energy(fa_handle* h, int64_t utt_id, float* dst, size_t cap) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  return copy_dense(h, utt_id, 1, h->h_energy.p, 3 * sizeof(float), dst, cap);
+}
+int fa_copy_syllables(fa_handle* h, int64_t utt_id, fa_syllable* dst, size_t cap) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  return copy_dense(h, utt_id, 2, h->h_syls.p, sizeof(fa_syllable), dst, cap);
+}
+int fa_copy_features(fa_handle* h, int64_t utt_id, double* dst, size_t cap) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  return copy_dense(h, utt_id, 3, h->h_features.p, FA_N_FEATURES * sizeof(double), dst, cap);
+}
+
+int fa_copy_peak_candidates(fa_handle* h, int64_t utt_id, uint32_t* packed, int32_t* counts, size_t cap_rows,
+                            int32_t* max_per_frame) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  if (h->cfg.output_level < 3) return fail(h, FA_ERR_INVALID_ARG, "no peak scan below output_level 3");
+  if (max_per_frame) *max_per_frame = h->maxp;
+  int rc = copy_rows_device(h, utt_id, h->d_cand.p, (size_t)h->maxp * sizeof(uint32_t), packed, cap_rows);
+  if (rc < 0) return rc;
+  return copy_rows_device(h, utt_id, h->d_ncand.p, sizeof(int), counts, cap_rows);
+}
+
+}  // extern "C"

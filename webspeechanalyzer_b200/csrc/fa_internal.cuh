@@ -1,0 +1,104 @@
+// fa_internal.cuh -- shared declarations of libfa_b200.so (sm_100a only; no CPU path).
+//
+// Stage map; @B = byte offset in /root/reference/dist/main.js line 2:
+//   K1 fa_spectrum_*   S1 + S1b  AnalyserNode front end (replaces the un-vendored worklet @B6480) -> dB rows + uint32 band frames
+//   K2 fa_peaks        S2        candidate peak scan of D() @B25863 (v-independent part)
+//   K3 fa_segment      S2b/S3/S3b/S3c  D()/C()/O() @B25717/@B28506/@B27088, accumulate_fm @B35952, straighten @B35074, sep_syllables @B34757
+//   K4 fa_features     S4        formant_features @B32369 + stats (src/stats.js:29-64)
+//   K5 fa_compact      gathers the per-utterance tables into dense arrays for one D2H copy
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fa_b200.h"
+
+#define FA_MAX_BANDS 256
+
+struct FaSpectrumParams {
+  const float* pcm;              // concatenated utterances, each start 16-byte aligned, padded tail
+  const long long* utt_off;      // [n_utt] first sample of utterance u
+  const long long* utt_len;      // [n_utt] samples
+  const long long* frame_off;    // [n_utt + 1] first frame row of utterance u
+  int n_utt;
+  int hop, N, M, logM, B;
+  const float* win;              // [N]
+  const float2* tw;              // [M/2]   W_M^j
+  const float2* tw_stage;        // [M-1]   stage-major: stage s (1-based) at offset 2^(s-1)-1, entries W_{2^s}^j
+  const float2* ws;              // [M]     W_{2M}^k (mirror rule above M/2)
+  const int* bm_k0;              // [B]
+  const int* bm_cnt;             // [B]
+  const int* bm_off;             // [B+1]
+  const float* bm_w;             // [n_weights]
+  int n_weights;
+  const float* emph;             // [B]
+  int use_emph, power;
+  float gain, tau, omt, inv2N, min_db, max_db;
+  int clamp_db;
+  float* spec_db;                // [F_total][M] or nullptr
+  uint32_t* frames;              // [F_total][B] or nullptr
+  int* work_counter;             // dynamic utterance queue
+};
+
+struct FaPeaksParams {
+  const uint32_t* frames;        // [F_total][B]
+  int B, maxp;
+  long long n_frames;
+  uint32_t* cand;                // [F_total][maxp] packed lo | hi<<8 | pk<<16 | last<<24
+  int* ncand;                    // [F_total]
+  double* gsum;                  // [F_total] sum e[1..B-1]
+};
+
+// per-utterance scan state that survives across time chunks (reserved for the stream stitcher)
+struct FaSegmentParams {
+  const uint32_t* frames;
+  const uint32_t* cand;
+  const int* ncand;
+  const double* gsum;
+  const long long* frame_off;    // [n_utt + 1]
+  int n_utt, B, maxp, level;
+  // reset_segmentation @B25053
+  int max_voiced_bin, seg_min_frames, auto_gate;
+  double seg_breaker, y0, v0;
+  // workspaces (per utterance u: base index = frame_off[u] * K + const * u)
+  int track_cap_mul, track_cap_add;   // tracks capacity of utterance u = F_u * mul + add
+  long long* track_base;              // [n_utt + 1] prefix of capacities
+  int* trk_count; double* trk_sum_e; double* trk_sum_eb; double* trk_mean; int* trk_order; int* trk_rank; signed char* trk_slot;
+  // point pool: capacity F_u * maxp, base = frame_off[u] * maxp
+  int* pt_track; int* pt_ord; int* pt_frame; int* pt_binspan; double* pt_e;
+  int* row_count; int* row_off;       // [F_total + n_utt] scratch (per utterance F_u + 1)
+  int* row_list;                      // [F_total * maxp]
+  // outputs (per utterance tables at base frame_off[u] + u, capacity F_u + 1)
+  fa_segment* segs; int* n_segs; int* n_stored;
+  float* formants;                    // [F_total][9]   rows of utterance u start at frame_off[u]
+  float* energy;                      // [F_total][3]
+  int* n_rows;                        // [n_utt]
+  fa_syllable* syls; int* n_syls;
+  int* overflow;                      // [n_utt]
+};
+
+struct FaFeatureParams {
+  const long long* frame_off;
+  int n_utt, level;
+  const fa_segment* segs; const int* n_segs;
+  const fa_syllable* syls; const int* n_syls;
+  const float* formants;
+  double* features;                   // [(F_total + n_utt)][53] per-utterance rows at base frame_off[u] + u
+  int* n_feat;                        // [n_utt]
+};
+
+struct FaGatherArgs {
+  const long long* frame_off;
+  int n_utt;
+  const int *n_segs, *n_rows, *n_syls, *n_feat;
+  long long* off;  // [4][n_utt + 1] exclusive prefixes: segs, rows, syls, feat
+  const fa_segment* segs; const fa_syllable* syls; const float* formants; const float* energy; const double* features;
+  fa_segment* d_segs; fa_syllable* d_syls; float* d_formants; float* d_energy; double* d_features;
+};
+
+cudaError_t fa_launch_spectrum(const FaSpectrumParams& p, cudaStream_t s, int* launches);
+cudaError_t fa_launch_peaks(const FaPeaksParams& p, cudaStream_t s, int* launches);
+cudaError_t fa_launch_segment(const FaSegmentParams& p, cudaStream_t s, int* launches);
+cudaError_t fa_launch_features(const FaFeatureParams& p, cudaStream_t s, int* launches);
+cudaError_t fa_launch_prefix(const FaGatherArgs& a, cudaStream_t s, int* launches);
+cudaError_t fa_launch_gather(const FaGatherArgs& a, cudaStream_t s, int* launches);

@@ -1,0 +1,154 @@
+"""Batch engine: a thin object wrapper over the C-ABI handle (one handle per GPU, one batch at a time)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _capi
+from ._capi import FaError
+from ._ctypes_defs import FaConfig, FaCounts, N_FEATURES
+
+SEG_DTYPE = np.dtype([("start", "<i4"), ("len", "<i4"), ("stored", "<i4"), ("n_syllables", "<i4"),
+                      ("first_syllable", "<i4"), ("row_offset", "<i4"), ("ymax", "<f8"), ("vmin", "<f8"),
+                      ("cs_ratio", "<f8")])
+SYL_DTYPE = np.dtype([("stored_seg", "<i4"), ("start", "<i4"), ("len", "<i4"), ("reserved", "<i4")])
+
+
+@dataclass
+class UtteranceResult:
+    counts: dict
+    segments: np.ndarray      # SEG_DTYPE, seg_ci order
+    formants: np.ndarray      # [rows, 9] float32
+    energy: np.ndarray        # [rows, 3] float32
+    syllables: np.ndarray     # SYL_DTYPE
+    features: np.ndarray      # [rows, 53] float64
+
+    @property
+    def seg_ci(self):
+        return [(int(s["start"]), int(s["len"])) for s in self.segments]
+
+
+def synth_speech(n_samples: int, sample_rate: int, seed: int, utt_index: int) -> np.ndarray:
+    """Synthetic glottal-pulse speech (csrc/fa_synth.cpp); host code, needs no GPU."""
+    out = np.empty(n_samples, np.float32)
+    rc = _capi.lib().fa_synth_speech(out.ctypes.data, n_samples, sample_rate, seed, utt_index)
+    if rc != 0:
+        raise FaError(rc, "fa_synth_speech")
+    return out
+
+
+class Engine:
+    """One GPU, one stream.  submit() utterances, run(), then fetch per-utterance results."""
+
+    def __init__(self, cfg: FaConfig, device: int = 0):
+        self._lib = _capi.lib()
+        self.cfg = cfg.copy()
+        self._h = C.c_void_p()
+        rc = self._lib.fa_create(C.byref(self.cfg), device, C.byref(self._h))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise FaError(rc, self._lib.fa_status_string(rc).decode())
+        self.device = device
+
+    # -- lifetime --
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.fa_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int) -> int:
+        if rc < 0:
+            raise FaError(rc, (self._lib.fa_last_error(self._h) or b"").decode() or
+                          self._lib.fa_status_string(rc).decode())
+        return rc
+
+    # -- batch --
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._check(self._lib.fa_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def reset(self):
+        self._check(self._lib.fa_reset(self._h))
+
+    def submit(self, utt_id: int, pcm: np.ndarray, sample_rate: int) -> int:
+        if pcm.dtype == np.int16:
+            pcm = np.ascontiguousarray(pcm)
+            return self._check(self._lib.fa_submit_pcm_i16(self._h, utt_id, pcm.ctypes.data, pcm.size, sample_rate))
+        pcm = np.ascontiguousarray(pcm, np.float32)
+        return self._check(self._lib.fa_submit_pcm(self._h, utt_id, pcm.ctypes.data, pcm.size, sample_rate))
+
+    def run(self):
+        self._check(self._lib.fa_run(self._h))
+
+    def sync(self):
+        self._check(self._lib.fa_sync(self._h))
+
+    def upload(self):
+        self._check(self._lib.fa_upload(self._h))
+
+    def run_resident(self):
+        self._check(self._lib.fa_run_resident(self._h))
+
+    def download(self):
+        self._check(self._lib.fa_download(self._h))
+
+    def stage_times(self):
+        ms = (C.c_float * 5)()
+        self._check(self._lib.fa_stage_times(self._h, ms))
+        return dict(zip(("spectrum", "peaks", "segment", "features", "total"), [float(x) for x in ms]))
+
+    @property
+    def launches(self) -> int:
+        return self._lib.fa_launch_count(self._h)
+
+    # -- results --
+    def counts(self, utt_id: int | None = None) -> dict:
+        c = FaCounts()
+        if utt_id is None:
+            self._check(self._lib.fa_total_counts(self._h, C.byref(c)))
+        else:
+            self._check(self._lib.fa_result_counts(self._h, utt_id, C.byref(c)))
+        return {k: getattr(c, k) for k, _ in FaCounts._fields_}
+
+    def _rows(self, fn, utt_id, nrows, shape_tail, dtype):
+        out = np.empty((nrows,) + shape_tail, dtype)
+        n = self._check(fn(self._h, -1 if utt_id is None else utt_id, out.ctypes.data, nrows))
+        return out[:n]
+
+    def spectrum(self, utt_id: int | None = None) -> np.ndarray:
+        c = self.counts(utt_id)
+        return self._rows(self._lib.fa_copy_spectrum, utt_id, c["frames"], (self.cfg.fft_size // 2,), np.float32)
+
+    def frames(self, utt_id: int | None = None) -> np.ndarray:
+        c = self.counts(utt_id)
+        return self._rows(self._lib.fa_copy_frames, utt_id, c["frames"], (c["bands"],), np.uint32)
+
+    def peak_candidates(self, utt_id: int):
+        c = self.counts(utt_id)
+        maxp = C.c_int32(0)
+        B = c["bands"]
+        packed = np.zeros((c["frames"], B // 2 + 4), np.uint32)
+        cnt = np.zeros(c["frames"], np.int32)
+        self._check(self._lib.fa_copy_peak_candidates(self._h, utt_id, packed.ctypes.data, cnt.ctypes.data, c["frames"],
+                                                      C.byref(maxp)))
+        assert maxp.value == packed.shape[1]
+        return packed, cnt
+
+    def result(self, utt_id: int | None = None) -> UtteranceResult:
+        c = self.counts(utt_id)
+        L = self._lib
+        segs = self._rows(L.fa_copy_segments, utt_id, c["segments"], (), SEG_DTYPE)
+        fm = self._rows(L.fa_copy_formants, utt_id, c["formant_rows"], (9,), np.float32)
+        en = self._rows(L.fa_copy_energy, utt_id, c["formant_rows"], (3,), np.float32)
+        sy = self._rows(L.fa_copy_syllables, utt_id, c["syllables"], (), SYL_DTYPE)
+        ft = self._rows(L.fa_copy_features, utt_id, c["feature_rows"], (N_FEATURES,), np.float64)
+        return UtteranceResult(c, segs, fm, en, sy, ft)
