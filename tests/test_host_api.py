@@ -1,0 +1,127 @@
+"""Host-side mirror of the formantanalyzer API: configure() truthiness rules, string rejections, WAV decoding,
+toFixed(3), and the callback shapes / order of P() checked against the literal transliteration."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from oracle.literal.refmodules import Segmentor
+from webspeechanalyzer_b200 import FaConfig, api, synth_speech, wav
+from webspeechanalyzer_b200.engine import UtteranceResult
+
+
+@pytest.fixture(autouse=True)
+def _fresh():
+    api.reset_defaults()
+    yield
+    api.reset_defaults()
+
+
+def test_configure_truthiness_rules():
+    api.configure({"output_level": 0, "window_step": 0, "f_min": 0, "high_f_emph": 0, "auto_noise_gate": False,
+                   "voiced_min_dB": 0, "spec_type": 3})
+    s = api._settings
+    assert s["output_level"] == 4 and s["window_step"] == 25          # falsy values cannot be set (@B3292)
+    assert s["f_min"] == 0 and s["auto_noise_gate"] is False and s["voiced_min_dB"] == 0 and s["spec_type"] == 3
+    api.configure({"output_level": 13, "window_step": 15, "fftSize": 1024, "smoothingTimeConstant": 0})
+    c = api._fa_config()
+    assert (c.output_level, c.window_step_ms, c.fft_size, c.smoothing, c.spec_type, c.bands) == (13, 15.0, 1024, 0.0, 3, 256)
+
+
+def test_rejections_are_the_reference_strings():
+    assert str(api.LaunchAudioNodes(2, object()).exception()) == "Invalid audio source"
+    assert str(api.LaunchAudioNodes(3).exception()) == "Invalid audio source"
+    assert str(api.LaunchAudioNodes(1, None).exception()) == "Invalid audio source"
+    assert str(api.LaunchAudioNodes(1, b"not a wav").exception()) == "Unable to decode audio data"
+    api._state["playing"] = True
+    assert str(api.LaunchAudioNodes(4, {"pcm": np.zeros(10, np.float32), "sampleRate": 16000}).exception()) == "Error: Already playing"
+    api._state["playing"] = False
+    api.StopAudioNodes("not playing: no effect")
+    assert api._state["stop"] is None
+
+
+def test_wav_roundtrip_and_formats():
+    p = synth_speech(8000, 16000, 1, 0)
+    x, sr = wav.decode_wav(wav.encode_wav_pcm16(p, 16000))
+    assert sr == 16000 and x.dtype == np.float32 and np.abs(x - p).max() <= 0.5 / 32768 + 1e-7
+    import struct
+    raw = p.astype("<f4").tobytes()
+    f32 = b"RIFF" + struct.pack("<I", 36 + len(raw)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 3, 1, 16000, 64000, 4, 32) \
+        + b"data" + struct.pack("<I", len(raw)) + raw
+    y, _ = wav.decode_wav(f32)
+    assert np.array_equal(y, p)
+    st = np.stack([p, -p], axis=1).astype("<f4").tobytes()
+    f32s = b"RIFF" + struct.pack("<I", 36 + len(st)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 3, 2, 16000, 128000, 8, 32) \
+        + b"data" + struct.pack("<I", len(st)) + st
+    z, _ = wav.decode_wav(f32s)
+    assert np.abs(z).max() == 0.0
+
+
+def test_to_fixed3_matches_js():
+    assert api.to_fixed3(0.0625) == "0.063" and api.to_fixed3(1.305) == "1.305" and api.to_fixed3(0.015 * 87) == "1.305"
+
+
+def as_result(an) -> UtteranceResult:
+    return UtteranceResult({}, an.segments, an.formants, an.energy, an.syllables, an.features)
+
+
+@pytest.mark.parametrize("level,step", [(13, 15.0), (5, 25.0), (4, 25.0), (10, 15.0)])
+def test_callback_shapes_and_order_equal_literal_P(level, step):
+    sr = 16000
+    cfg = FaConfig.default(output_level=level, window_step_ms=step)
+    pcm = np.concatenate([synth_speech(4 * sr, sr, 21, u) for u in range(3)])
+    fe, an = oracle.analyze_pcm(cfg, pcm, sr)
+    S = Segmentor(level, cfg.bands, 200, step, 200, 50, True, 100, 10, None, True, ["lab"])
+    for f in fe["frames"]:
+        S.spectrum_push(f)
+    S.segment_truncate()
+    calls = api.segment_callbacks(level, step, ["lab"], as_result(an))
+    assert len(calls) == len(S.events) > 0
+    for mine, ref in zip(calls, S.events):
+        assert mine[0] == ref[0] and mine[1] == ref[1]
+        if level in (13, 10):
+            assert mine[2] == ref[2]                                   # toFixed(3) strings
+            assert all(isinstance(t, str) for pair in mine[2] for t in pair)
+        else:
+            assert mine[2] == ref[2]                                   # numbers: start*step, (len+1)*step
+        if level == 13:
+            assert np.array_equal(np.array(mine[3]), np.array(ref[3]), equal_nan=True) and len(mine[3][0]) == 53
+        elif level == 5:
+            assert np.array_equal(np.array(mine[3]), np.array(ref[3]), equal_nan=True) and len(mine[3]) == 53
+        elif level == 4:
+            assert np.array_equal(np.stack(mine[3]), np.stack(ref[3])) and mine[3][0].dtype == np.float32
+        elif level == 10:
+            assert len(mine[3]) == len(ref[3])
+            for a, b in zip(mine[3], ref[3]):
+                assert np.array_equal(np.stack(a), np.stack(b))
+
+
+def test_dropped_segment_misaligns_times_like_the_reference():
+    """Quirk 15: straighten_formants throws when a track point's frame index >= len; seg_ci keeps the entry but the
+    stores do not, so later callbacks pair store e with seg_ci[e]."""
+    B = 128
+    bins = np.arange(B)
+
+    def voiced(c, amps):
+        e = np.zeros(B)
+        for a, cc in zip(amps, c):
+            e += a * np.exp(-0.5 * ((bins - cc) / 1.5) ** 2)
+        return np.rint(e).astype(np.uint32)
+
+    v = voiced([12, 30, 50, 70, 85], [8000, 40000, 8000, 8000, 8000])
+    z = np.zeros(B, np.uint32)
+    # voiced, pause, voiced, voiced, then a long pause -> len 3 but a track point sits at frame 3
+    frames = [v, z, v, v] + [z] * 10 + [v] * 12 + [z] * 10
+    cfg = FaConfig.default(output_level=5)
+    an = oracle.analyze_frames(cfg, np.stack(frames))
+    S = Segmentor(5, B, 200, 25.0, 200, 50, True, 100, 10, None, True, [])
+    for f in frames:
+        S.spectrum_push(f)
+    S.segment_truncate()
+    assert [tuple(x) for x in S.u] == an.seg_ci
+    stored = [int(s["stored"]) for s in an.segments]
+    assert stored == [-1, 0] and an.seg_ci == [(8, 3), (22, 12)]   # the drop happened
+    calls = api.segment_callbacks(5, 25.0, [], as_result(an))
+    assert len(calls) == len(S.events) == 1
+    # store 0 belongs to seg_ci[1] but is stamped with seg_ci[0]'s time, exactly like the reference
+    assert calls[0][2] == S.events[0][2] == [8 * 0.025, (3 + 1) * 0.025]
+    assert calls[0][3][0] == 12.0

@@ -1,0 +1,233 @@
+"""Host-side mirror of the formantanalyzer public API (the drop-in boundary).
+
+    reference (inner module 1 of /root/reference/dist/main.js line 2)           here
+    configure(cfg)                                   @B3292                      configure(cfg)
+    LaunchAudioNodes(context_source, source_obj, callback, file_labels=[],
+                     offline=false, test_play=true, play_offset, play_duration)  LaunchAudioNodes(...)  -> Future(True)
+                                                     @B4469
+    StopAudioNodes(reason)                           @B5699                      StopAudioNodes(reason)
+    set_predicted_label_for_segment(si, idx, label)  (module 2 `T` -> set_segments_label @B31782-)  same name
+
+The reference's host language is JavaScript; `node` is not present in this image, so the tested host shim
+is this Python module over the C-ABI (ctypes), and the N-API addon that binds the same C-ABI for Node lives
+in webspeechanalyzer_b200/node/ (compile-checked only).  Same names, argument order, callback
+shapes per output level (P() @B28869), string rejections and single-flight rule; callbacks are suppressed
+when test_play is true (the reference's default, quirk 13).
+
+Extensions (documented in INTEGRATION.md): context_source 4 = {"pcm": float32 array, "sampleRate": sr};
+configure() accepts fftSize, smoothingTimeConstant, minDecibels, maxDecibels, mag_scale, clamp_dB;
+levels 1-2 (canvas only in the reference) call back once with the dB spectrum.
+"""
+from __future__ import annotations
+
+import math
+from concurrent.futures import Future
+from decimal import Decimal, ROUND_HALF_UP
+
+import numpy as np
+
+from . import wav
+from ._ctypes_defs import FaConfig
+from .engine import Engine
+
+__all__ = ["configure", "LaunchAudioNodes", "StopAudioNodes", "set_predicted_label_for_segment", "LaunchError"]
+
+
+class LaunchError(Exception):
+    """Carries the string the reference's promise would have been rejected with."""
+
+
+def _defaults() -> dict:
+    # /root/reference/dist/main.js:2@B2972
+    return dict(plot_enable=False, spec_type=1, output_level=4, plot_len=200, f_min=50, f_max=4000, N_fft_bins=256,
+                N_mel_bins=128, window_width=25, window_step=25, pause_length=200, min_seg_length=50,
+                auto_noise_gate=True, voiced_max_dB=100, voiced_min_dB=10, plot_lag=1, pre_norm_gain=1000,
+                high_f_emph=0, plot_canvas=None, canvas_width=200, canvas_height=100,
+                # extension fields (AnalyserNode front end)
+                fftSize=2048, smoothingTimeConstant=0.8, minDecibels=-100, maxDecibels=-30, mag_scale=0, clamp_dB=True,
+                device=0)
+
+
+_settings = _defaults()
+_state = {"playing": False, "stop": None, "engine": None, "engine_key": None, "labels": []}
+
+
+def reset_defaults():
+    """Test helper: module state back to the formantanalyzer defaults."""
+    global _settings
+    _settings = _defaults()
+    _state.update(playing=False, stop=None, labels=[])
+
+
+def configure(cfg: dict) -> None:
+    """configure() @B3292: `x && (a.x = x)` for the truthy-tested fields, `null !== x` for the others."""
+    a = _settings
+    truthy = ("output_level", "f_max", "N_fft_bins", "N_mel_bins", "window_width", "window_step", "pre_norm_gain",
+              "pause_length", "min_seg_length", "voiced_max_dB")
+    not_null = ("spec_type", "f_min", "high_f_emph", "auto_noise_gate", "voiced_min_dB")
+    for k in truthy:
+        if cfg.get(k):
+            a[k] = cfg[k]
+    for k in not_null:
+        if k in cfg and cfg[k] is not None:
+            a[k] = cfg[k]
+    if cfg.get("plot_enable") and cfg.get("plot_canvas"):
+        # plotting is out of scope (canvas UI); remember the fields the segmentor depends on
+        a["plot_enable"] = True
+        if cfg.get("plot_len"):
+            a["plot_len"] = cfg["plot_len"]
+    else:
+        a["plot_enable"] = False
+    for k in ("fftSize", "smoothingTimeConstant", "minDecibels", "maxDecibels", "mag_scale", "clamp_dB", "device"):
+        if k in cfg and cfg[k] is not None:
+            a[k] = cfg[k]
+
+
+def _fa_config() -> FaConfig:
+    a = _settings
+    return FaConfig.default(
+        spec_type=int(a["spec_type"]), output_level=int(a["output_level"]), plot_len=int(a["plot_len"]),
+        n_fft_bins=int(a["N_fft_bins"]), n_mel_bins=int(a["N_mel_bins"]), auto_noise_gate=1 if a["auto_noise_gate"] else 0,
+        f_min=float(a["f_min"]), f_max=float(a["f_max"]), window_width_ms=float(a["window_width"]),
+        window_step_ms=float(a["window_step"]), pause_length_ms=float(a["pause_length"]),
+        min_seg_length_ms=float(a["min_seg_length"]), voiced_max_db=float(a["voiced_max_dB"]),
+        voiced_min_db=float(a["voiced_min_dB"]), pre_norm_gain=float(a["pre_norm_gain"]),
+        high_f_emph=float(a["high_f_emph"]), fft_size=int(a["fftSize"]), clamp_db=1 if a["clamp_dB"] else 0,
+        smoothing=float(a["smoothingTimeConstant"]), min_db=float(a["minDecibels"]), max_db=float(a["maxDecibels"]),
+        mag_scale=float(a["mag_scale"]))
+
+
+def to_fixed3(x: float) -> str:
+    """Number.prototype.toFixed(3) (get_syls_timestamps @B31114): exact decimal value, ties up."""
+    return str(Decimal(float(x)).quantize(Decimal("0.001"), rounding=ROUND_HALF_UP))
+
+
+def segment_callbacks(level: int, step_ms: float, labels: list, res) -> list[tuple]:
+    """P() @B28869 on the tables of one utterance: the argument tuples of every callback, in firing order.
+
+    The store index `e` also indexes seg_ci for the time stamps (get_seg_timestamps @B31504 /
+    get_syls_timestamps @B31114) -- after a dropped segment the reference pairs store e with seg_ci[e],
+    not with the segment that produced it; reproduced here.
+    """
+    step = step_ms / 1e3
+    segs = res.segments
+    stored = [s for s in segs if s["stored"] >= 0]
+    out = []
+    for e, s in enumerate(stored):
+        ci = segs[e]
+        rows = res.formants[s["row_offset"]: s["row_offset"] + s["len"]]
+        if level in (13, 10):
+            syl = res.syllables[s["first_syllable"]: s["first_syllable"] + s["n_syllables"]]
+            if len(syl) == 0:
+                continue
+            times = [[to_fixed3((int(ci["start"]) + int(y["start"])) * step), to_fixed3((int(y["len"]) + 1) * step)] for y in syl]
+            if level == 13:
+                # feature rows of an utterance are in syllable order
+                f0 = int(s["first_syllable"])
+                payload = [list(map(float, r)) for r in res.features[f0: f0 + len(syl)]]
+            else:
+                payload = [[np.array(r, np.float32) for r in rows[int(y["start"]): int(y["start"]) + int(y["len"])]] for y in syl]
+            out.append((e, labels, times, payload))
+        elif level == 5:
+            out.append((e, labels, [int(ci["start"]) * step, (int(ci["len"]) + 1) * step], list(map(float, res.features[e]))))
+        elif level == 4:
+            if len(rows) == 0:
+                continue
+            out.append((e, labels, [int(ci["start"]) * step, (int(ci["len"]) + 1) * step], [np.array(r, np.float32) for r in rows]))
+    return out
+
+
+def _engine(cfg: FaConfig, device: int) -> Engine:
+    key = (bytes(cfg), device)
+    if _state["engine"] is None or _state["engine_key"] != key:
+        if _state["engine"] is not None:
+            _state["engine"].close()
+        _state["engine"] = Engine(cfg, device)
+        _state["engine_key"] = key
+    return _state["engine"]
+
+
+def LaunchAudioNodes(context_source, source_obj=None, callback=None, file_labels=None, offline=False, test_play=True,
+                     play_offset=None, play_duration=None) -> Future:
+    fut: Future = Future()
+    file_labels = [] if file_labels is None else file_labels
+
+    def reject(msg: str):
+        fut.set_exception(LaunchError(msg))
+        return fut
+
+    a = _settings
+    if _state["playing"]:
+        return reject("Error: Already playing")
+    if not (a["N_mel_bins"] or a["N_fft_bins"]):
+        return reject("Invalid reset_nodes config")
+    bands = a["N_mel_bins"] if a["spec_type"] == 1 else a["N_fft_bins"]
+    if not bands:
+        return reject("reset_segmentor failed: Invalid spec_bands")
+    if not a["output_level"]:
+        return reject("Invalid reset_plot config")
+    try:
+        if context_source == 1 and source_obj is not None:
+            pcm, sr = wav.decode_wav(source_obj)
+        elif context_source == 4 and source_obj is not None:
+            pcm, sr = np.asarray(source_obj["pcm"], np.float32), int(source_obj["sampleRate"])
+        else:
+            # 2 (<audio> element) and 3 (microphone) need a browser audio graph
+            return reject("Invalid audio source")
+    except wav.WavError as e:
+        return reject(str(e))
+    if play_offset or play_duration:
+        o = int(round((play_offset or 0) * sr))
+        n = pcm.size - o if not play_duration else int(round(play_duration * sr))
+        pcm = pcm[o: o + max(n, 0)]
+    _state["playing"] = True
+    _state["labels"] = []
+    try:
+        cfg = _fa_config()
+        eng = _engine(cfg, int(a["device"]))
+        eng.reset()
+        eng.submit(0, pcm, sr)
+        eng.run()
+        eng.sync()
+        level = int(a["output_level"])
+        if level <= 2:
+            if not test_play and callback:
+                sp = eng.spectrum(0)
+                callback(0, file_labels, [0.0, sp.shape[0] * a["window_step"] / 1e3], sp)
+        else:
+            res = eng.result(0)
+            calls = segment_callbacks(level, float(a["window_step"]), file_labels, res)
+            _state["labels"] = [list(file_labels) for _ in calls]
+            if not test_play and callback:
+                for args in calls:
+                    if _state["stop"] is not None:
+                        break
+                    callback(*args)
+        fut.set_result(True)
+    except Exception as e:  # noqa: BLE001  (the reference rejects with the error)
+        fut.set_exception(LaunchError(str(e)))
+    finally:
+        _state["playing"] = False
+        _state["stop"] = None
+    return fut
+
+
+def StopAudioNodes(reason: str = "no reason") -> None:
+    """disconnect_nodes @B21559: only has an effect while playing."""
+    if _state["playing"]:
+        _state["stop"] = reason
+
+
+def set_predicted_label_for_segment(seg_index: int, label_index: int, predicted_label) -> None:
+    """set_segments_label (module 3 `G`): pads the segment's label list with -1 up to label_index, then sets it."""
+    lab = _state["labels"][seg_index]
+    while len(lab) < label_index:
+        lab.append(-1)
+    if len(lab) == label_index:
+        lab.append(predicted_label)
+    else:
+        lab[label_index] = predicted_label
+
+
+def get_segment_labels(seg_index: int):
+    return _state["labels"][seg_index]
