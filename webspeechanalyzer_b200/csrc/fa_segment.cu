@@ -29,13 +29,21 @@ constexpr int PCAP = 136;  // accepted peaks per frame (>= maxp = B/2 + 4)
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int BIG = 0x7fffffff;
 
+constexpr int CMAX = 10;   // candidate peaks per live track: a +-8 bin window holds <= 9 peaks (>= 2 bins apart)
+
 struct WarpShared {
   uint32_t e[FA_MAX_BANDS];
+  unsigned long long P[FA_MAX_BANDS];      // inclusive prefix sums of e (exact)
+  uint32_t pmask[FA_MAX_BANDS / 32 + 1];   // bit b: an accepted peak has pk == b
+  unsigned char pidx[FA_MAX_BANDS];        // its index in the accepted list
   unsigned char plo[PCAP], phi[PCAP], ppk[PCAP];
   int owner[PCAP];
+  unsigned long long bestbits[PCAP];       // best score per peak (bit pattern of a positive double)
   int a_id[ACAP], a_last_frame[ACAP], a_last_bin[ACAP], a_npts[ACAP], a_b2[ACAP], a_b3[ACAP];
   uint32_t a_last_amp[ACAP];
   double a_vel[ACAP], a_sum_e[ACAP], a_sum_eb[ACAP];
+  double cand_sc[CMAX][ACAP];              // [k][slot]: lane-consecutive slots -> conflict free
+  unsigned char cand_o[CMAX][ACAP];
 };
 
 struct ScanState {
@@ -161,98 +169,145 @@ __device__ __noinline__ void accumulate_fm(const FaSegmentParams& p, WarpShared&
     }
     st.n_act = n_new;
   }
-  // (1) best live track per peak: lane per track, warp arg-max (ties -> earlier track)
-  for (int o = 0; o < n_peaks; o++) {
-    const int pk = S.ppk[o];
-    const double amp_new = (double)S.e[pk];
-    double best = 0;
-    int best_r = BIG;
-    for (int r = lane; r < st.n_act; r += 32) {
+  // per-frame tables: peak bitmask + index, exact prefix sums of the frame
+  const int B = p.B;
+  {
+    const int nw = (B + 31) >> 5;
+    if (lane <= nw) S.pmask[lane] = 0u;
+    const int C = (B + 31) >> 5;            // bins per lane
+    const int b0 = lane * C, b1 = min(b0 + C, B);
+    unsigned long long loc = 0;
+    for (int b = b0; b < b1; b++) loc += S.e[b];
+    unsigned long long incl = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += t;
+    }
+    unsigned long long run = incl - loc;
+    for (int b = b0; b < b1; b++) { run += S.e[b]; S.P[b] = run; }
+    __syncwarp();
+    for (int o = lane; o < n_peaks; o += 32) {
+      const int pk = S.ppk[o];
+      atomicOr(&S.pmask[pk >> 5], 1u << (pk & 31));
+      S.pidx[pk] = (unsigned char)o;
+      S.owner[o] = BIG;
+      S.bestbits[o] = 0ull;
+    }
+    __syncwarp();
+  }
+  // (1) score every (live track, peak within its window): lane per track.  best[o] = max score via
+  //     shared-memory atomicMax on the bit pattern; ties go to the earlier track via atomicMin on the slot.
+  int my_cnt[ACAP / 32];
+#pragma unroll
+  for (int ps = 0; ps < ACAP / 32; ps++) {
+    my_cnt[ps] = 0;
+    const int r = ps * 32 + lane;
+    if (r < st.n_act) {
       const int gap = n_label - S.a_last_frame[r];
       if (gap >= 0 && gap < 4) {
         const int lb = S.a_last_bin[r];
-        const int dist = abs(lb - pk);
         const int lim = gap == 0 ? 3 : gap == 1 ? 4 : gap == 2 ? 6 : 9;  // DIST @B32325
-        if (dist < lim) {
-          const double sc = fm_score(gap, (double)dist, S.a_npts[r], lb, pk, (double)S.a_last_amp[r], amp_new, S.a_vel[r]);
-          if (sc > 1 && sc > best) { best = sc; best_r = r; }
+        const int wlo = max(lb - lim + 1, 0), whi = min(lb + lim - 1, B - 1);
+        const int word = wlo >> 5, sh = wlo & 31;
+        const unsigned long long two = (unsigned long long)S.pmask[word] | ((unsigned long long)S.pmask[word + 1] << 32);
+        unsigned bits = (unsigned)(two >> sh) & ((2u << (whi - wlo)) - 1u);
+        const double amp_old = (double)S.a_last_amp[r], vel = S.a_vel[r];
+        const int np = S.a_npts[r];
+        int cnt = 0;
+        while (bits) {
+          const int j = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const int bin = wlo + j;
+          const double sc = fm_score(gap, (double)abs(lb - bin), np, lb, bin, amp_old, (double)S.e[bin], vel);
+          if (sc > 1) {
+            const int o = S.pidx[bin];
+            if (cnt < CMAX) {
+              S.cand_sc[cnt][r] = sc;
+              S.cand_o[cnt][r] = (unsigned char)o;
+            }
+            cnt++;
+            atomicMax(&S.bestbits[o], (unsigned long long)__double_as_longlong(sc));
+          }
+        }
+        my_cnt[ps] = cnt;
+      }
+    }
+  }
+  {
+    bool ovf = false;
+#pragma unroll
+    for (int ps = 0; ps < ACAP / 32; ps++) ovf |= my_cnt[ps] > CMAX;
+    if (__any_sync(FULL, ovf)) { st.overflow = 1; return; }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int ps = 0; ps < ACAP / 32; ps++) {
+    const int r = ps * 32 + lane;
+    for (int k = 0; k < my_cnt[ps]; k++) {
+      const int o = S.cand_o[k][r];
+      if ((unsigned long long)__double_as_longlong(S.cand_sc[k][r]) == S.bestbits[o]) atomicMin(&S.owner[o], r);
+    }
+  }
+  __syncwarp();
+  // (2) every owning track absorbs its (merged) peaks: lane per track, its owned peaks are among its candidates
+  unsigned long long moved = 0;
+#pragma unroll
+  for (int ps = 0; ps < ACAP / 32; ps++) {
+    const int r = ps * 32 + lane;
+    int first = -1, lo = 0, hi = 0, o_bin = 0;
+    uint32_t bamp = 0;
+    for (int k = 0; k < my_cnt[ps]; k++) {
+      const int o = S.cand_o[k][r];
+      if (S.owner[o] == r) {
+        const int pk = S.ppk[o];
+        const uint32_t a = S.e[pk];
+        if (first < 0) { first = o; lo = S.plo[o]; hi = S.phi[o]; o_bin = pk; bamp = a; }
+        else {
+          lo = min(lo, (int)S.plo[o]);
+          hi = max(hi, (int)S.phi[o]);
+          if (a > bamp) { bamp = a; o_bin = pk; }
         }
       }
     }
-#pragma unroll
-    for (int off = 16; off; off >>= 1) {
-      const double ob = __shfl_xor_sync(FULL, best, off);
-      const int orr = __shfl_xor_sync(FULL, best_r, off);
-      if (orr != BIG && (best_r == BIG || ob > best || (ob == best && orr < best_r))) { best = ob; best_r = orr; }
+    bool upd = false;
+    uint32_t amp0 = 0;
+    if (first >= 0) {
+      amp0 = S.e[S.ppk[first]];
+      upd = (double)amp0 > vmin;
     }
-    if (lane == 0) S.owner[o] = best_r == BIG ? -1 : best_r;
-  }
-  __syncwarp();
-  // (2) every owning track, in creation order, absorbs its (merged) peaks
-  int cur = 0;
-  for (;;) {
-    int mn = BIG;
-    for (int o = lane; o < n_peaks; o += 32) {
-      const int ow = S.owner[o];
-      if (ow >= cur && ow < mn) mn = ow;
-    }
-    mn = warp_min_i(mn);
-    if (mn == BIG) break;
-    const int r = mn;
-    cur = r + 1;
-    int first = BIG, lo = BIG, hi = -1, bidx = BIG;
-    uint32_t bamp = 0;
-    for (int o = lane; o < n_peaks; o += 32) {
-      if (S.owner[o] == r) {
-        first = min(first, o);
-        lo = min(lo, (int)S.plo[o]);
-        hi = max(hi, (int)S.phi[o]);
-        const uint32_t a = S.e[S.ppk[o]];
-        if (bidx == BIG || a > bamp) { bamp = a; bidx = o; }
-      }
-    }
-    first = warp_min_i(first);
-    lo = warp_min_i(lo);
-    hi = warp_max_i(hi);
-#pragma unroll
-    for (int off = 16; off; off >>= 1) {
-      const uint32_t oa = __shfl_xor_sync(FULL, bamp, off);
-      const int oi = __shfl_xor_sync(FULL, bidx, off);
-      if (oi != BIG && (bidx == BIG || oa > bamp || (oa == bamp && oi < bidx))) { bamp = oa; bidx = oi; }
-    }
-    const uint32_t amp0 = S.e[S.ppk[first]];
-    if ((double)amp0 > vmin) {
-      const int o_bin = S.ppk[bidx];
-      unsigned long long acc = 0;
-      for (int b = lo + lane; b <= hi; b += 32) acc += S.e[b];
-      const double E = (double)warp_sum_u64(acc);
+    const unsigned um = __ballot_sync(FULL, upd);
+    if (upd) {
+      const unsigned long long Ei = S.P[hi] - (lo > 0 ? S.P[lo - 1] : 0ull);
+      const double E = (double)Ei;
+      moved += Ei;
       const int h = S.a_npts[r];
       const int b1 = S.a_last_bin[r], b2 = S.a_b2[r], b3 = S.a_b3[r];
       double vel = S.a_vel[r];
       if (h >= 3) vel = (double)(o_bin - b1 + (b2 - b1) + (b3 - b2)) / 3;
       else if (h == 2) vel = (double)(o_bin - b1 + (b2 - b1)) / 2;
       else if (h == 1) vel = (double)(o_bin - b1);
-      __syncwarp();
-      if (lane == 0) {
-        S.a_vel[r] = vel; S.a_last_frame[r] = n_label; S.a_b3[r] = b2; S.a_b2[r] = b1; S.a_last_bin[r] = o_bin;
-        S.a_last_amp[r] = amp0; S.a_npts[r] = h + 1; S.a_sum_e[r] += E; S.a_sum_eb[r] += E * (double)o_bin;
-        const long long q = bs.pb + st.n_pts;
-        p.pt_track[q] = S.a_id[r]; p.pt_ord[q] = h; p.pt_frame[q] = n_label;
-        p.pt_binspan[q] = o_bin | ((hi - lo + 1) << 16); p.pt_e[q] = E;
-      }
-      st.n_pts++;
-      st.s_energy -= E;
-      st.c_energy += E;
-      __syncwarp();
+      S.a_vel[r] = vel; S.a_last_frame[r] = n_label; S.a_b3[r] = b2; S.a_b2[r] = b1; S.a_last_bin[r] = o_bin;
+      S.a_last_amp[r] = amp0; S.a_npts[r] = h + 1; S.a_sum_e[r] += E; S.a_sum_eb[r] += E * (double)o_bin;
+      const long long q = bs.pb + st.n_pts + __popc(um & ((1u << lane) - 1));
+      p.pt_track[q] = S.a_id[r]; p.pt_ord[q] = h; p.pt_frame[q] = n_label;
+      p.pt_binspan[q] = o_bin | ((hi - lo + 1) << 16); p.pt_e[q] = E;
     }
+    st.n_pts += __popc(um);
   }
+  {
+    const double mv = (double)warp_sum_u64(moved);  // exact integers: one subtraction == the reference's sequence
+    st.s_energy -= mv;
+    st.c_energy += mv;
+  }
+  __syncwarp();
   // (3) un-owned peaks above the gate start new tracks, in peak order
   for (int o0 = 0; o0 < n_peaks; o0 += 32) {
     const int o = o0 + lane;
     const bool valid = o < n_peaks;
     const int pk = valid ? S.ppk[o] : 0;
     const uint32_t amp = valid ? S.e[pk] : 0;
-    const bool mk = valid && S.owner[o] == -1 && (double)amp > vmin;
+    const bool mk = valid && S.owner[o] == BIG && (double)amp > vmin;
     const unsigned m = __ballot_sync(FULL, mk);
     const int cnt = __popc(m);
     if (st.n_act + cnt > ACAP || st.n_tr + cnt > bs.tcap) { st.overflow = 1; return; }
@@ -260,9 +315,7 @@ __device__ __noinline__ void accumulate_fm(const FaSegmentParams& p, WarpShared&
       const int pos = __popc(m & ((1u << lane) - 1));
       const int slot = st.n_act + pos, id = st.n_tr + pos;
       const int lo = S.plo[o], hi = S.phi[o];
-      unsigned long long acc = 0;
-      for (int b = lo; b <= hi; b++) acc += S.e[b];
-      const double E = (double)acc;
+      const double E = (double)(S.P[hi] - (lo > 0 ? S.P[lo - 1] : 0ull));
       S.a_id[slot] = id; S.a_last_frame[slot] = n_label; S.a_last_bin[slot] = pk; S.a_last_amp[slot] = amp;
       S.a_vel[slot] = 0; S.a_npts[slot] = 1; S.a_b2[slot] = 0; S.a_b3[slot] = 0; S.a_sum_e[slot] = E;
       S.a_sum_eb[slot] = E * (double)pk;
@@ -469,7 +522,8 @@ __device__ __noinline__ int finalize_segment(const FaSegmentParams& p, WarpShare
 }
 
 __global__ void __launch_bounds__(kWarps * 32) fa_segment_kernel(const FaSegmentParams p) {
-  __shared__ WarpShared sh[kWarps];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WarpShared* sh = reinterpret_cast<WarpShared*>(smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int u = blockIdx.x * kWarps + wib;
   if (u >= p.n_utt) return;
@@ -599,7 +653,10 @@ __global__ void __launch_bounds__(kWarps * 32) fa_segment_kernel(const FaSegment
 cudaError_t fa_launch_segment(const FaSegmentParams& p, cudaStream_t s, int* launches) {
   if (p.n_utt <= 0) return cudaSuccess;
   const int grid = (p.n_utt + kWarps - 1) / kWarps;
-  fa_segment_kernel<<<grid, kWarps * 32, 0, s>>>(p);
+  const int bytes = (int)sizeof(WarpShared) * kWarps;
+  cudaError_t e = cudaFuncSetAttribute(fa_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  fa_segment_kernel<<<grid, kWarps * 32, bytes, s>>>(p);
   if (launches) (*launches)++;
   return cudaGetLastError();
 }
