@@ -360,7 +360,7 @@ int fa_upload(fa_handle* h) {
   FA_CUDA(cudaMemcpyAsync(h->d_pcm.p, h->h_pcm.p, (size_t)(h->staged + 16) * sizeof(float), cudaMemcpyHostToDevice, s));
   // outputs / workspaces
   const size_t Fz = (size_t)std::max<long long>(F, 1), nz = (size_t)n;
-  if (h->want_spec) FA_CUDA(h->d_spec.reserve(Fz * h->M * sizeof(float)));
+  if (h->want_spec || h->N == 2048) FA_CUDA(h->d_spec.reserve(Fz * h->M * sizeof(float)));  // also the K1a -> K1b magnitude rows
   FA_CUDA(h->d_frames.reserve(Fz * h->B * sizeof(uint32_t)));
   FA_CUDA(h->d_counter.reserve(16));
   if (h->cfg.output_level >= 3) {
@@ -421,7 +421,10 @@ int fa_run_resident(fa_handle* h) {
   sp.gain = fa_tab_gain(&c); sp.tau = (float)c.smoothing; sp.omt = (float)(1.0 - c.smoothing);
   sp.inv2N = (float)(1.0 / (2.0 * (double)h->N)); sp.min_db = (float)c.min_db; sp.max_db = (float)c.max_db;
   sp.clamp_db = c.clamp_db;
-  sp.spec_db = h->want_spec ? h->d_spec.as<float>() : nullptr;
+  sp.scratch_mag = h->N == 2048;
+  sp.write_db = h->want_spec;
+  sp.n_rows = F;
+  sp.spec_db = (h->want_spec || sp.scratch_mag) ? h->d_spec.as<float>() : nullptr;
   sp.frames = h->d_frames.as<uint32_t>();
   sp.work_counter = h->d_counter.as<int>();
   FA_CUDA(fa_launch_spectrum(sp, s, &h->launches));

@@ -35,7 +35,11 @@ struct FaSpectrumParams {
   int use_emph, power;
   float gain, tau, omt, inv2N, min_db, max_db;
   int clamp_db;
-  float* spec_db;                // [F_total][M] or nullptr
+  float* spec_db;                // [F_total][M]: |X|/N rows from K1a, converted to dB in place by K1b (fast path);
+                                 // generic path: dB rows or nullptr
+  int scratch_mag;               // 1: spec_db is allocated and may be used as the K1a -> K1b magnitude buffer
+  int write_db;                  // 1: the caller wants the dB rows
+  long long n_rows;              // total frames of the batch
   uint32_t* frames;              // [F_total][B] or nullptr
   int* work_counter;             // dynamic utterance queue
 };
