@@ -144,6 +144,14 @@ FA_API const char* fa_last_error(const fa_handle* h);
 /* Use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the handle's own. */
 FA_API int fa_set_stream(fa_handle* h, void* cuda_stream);
 
+/* Number of sub-batches a run is split into (each on its own forked stream so that H2D, the kernels of different
+ * sub-batches and the spectrum D2H overlap): 0 = automatic, 1 = serial (per-stage timings are only defined then). */
+FA_API int fa_set_pipeline(fa_handle* h, int n_sub_batches);
+
+/* Caller-owned destination (ideally page-locked) for the dB spectrum rows of the whole batch, in submission order:
+ * fa_run streams the rows into it as sub-batches finish; valid after fa_sync.  NULL removes the sink. */
+FA_API int fa_set_spectrum_sink(fa_handle* h, float* dst, size_t cap_rows);
+
 /* Drop all submitted utterances and results (StopAudioNodes / a new batch). */
 FA_API int fa_reset(fa_handle* h);
 
@@ -151,6 +159,12 @@ FA_API int fa_reset(fa_handle* h);
  * pinned staging buffer.  All utterances of one batch share sample_rate.  Returns its index. */
 FA_API int fa_submit_pcm(fa_handle* h, int64_t utt_id, const float* pcm, size_t n_samples, int sample_rate);
 FA_API int fa_submit_pcm_i16(fa_handle* h, int64_t utt_id, const int16_t* pcm, size_t n_samples, int sample_rate);
+/* A whole batch in ONE caller buffer: utterance i is pcm[offsets[i] .. offsets[i+1]) and gets id first_utt_id + i.
+ * If `pcm` is page-locked host memory (cudaHostAlloc / cudaHostRegister) the batch is NOT copied: the H2D transfer
+ * reads the caller's buffer directly, which must then stay valid and unchanged until fa_sync.  Otherwise it is
+ * staged like fa_submit_pcm.  Returns the index of the first utterance. */
+FA_API int fa_submit_pcm_batch(fa_handle* h, int64_t first_utt_id, const float* pcm, const int64_t* offsets, int n_utt,
+                               int sample_rate);
 
 /* Asynchronously: H2D copy of the staged PCM, stages 1-4 on the handle's stream, D2H of the result
  * tables.  fa_sync waits for it. */

@@ -63,11 +63,23 @@ struct HostBuf {  // pinned
 
 struct Utt {
   int64_t id;
-  long long off;     // first sample in the staging buffer (multiple of 4)
+  int region;        // 0 = the handle's pinned staging buffer, > 0 = a caller-owned buffer (zero copy)
+  long long off;     // first sample inside its region
   long long n;       // samples
   long long row0;    // first frame row
   int frames;
 };
+
+// A contiguous run of PCM on the host that maps to a contiguous run in d_pcm.
+struct Region {
+  const float* host;   // nullptr for region 0 (resolved at upload: the staging buffer may move while it grows)
+  long long n;         // floats
+  long long dev_off;   // first float in d_pcm (multiple of 4)
+};
+
+struct SubBatch { int u0, u1; long long r0, r1; };
+
+constexpr int kMaxSub = 8;
 
 }  // namespace
 
@@ -80,8 +92,18 @@ struct fa_handle {
   bool tables_ready = false;
   int tables_sr = 0;
   std::vector<Utt> utts;
+  std::vector<Region> regions;
+  std::vector<long long> abs_off;  // device offset of every utterance (filled by prepare)
   std::unordered_map<int64_t, int> index;
   long long staged = 0;        // floats used in h_pcm
+  long long dev_floats = 0;    // floats of d_pcm in use
+  int pipeline = 0;            // sub-batches: 0 = auto, 1 = serial
+  float* spec_sink = nullptr;  // caller-owned destination of the dB rows (filled during fa_run)
+  size_t spec_sink_rows = 0;
+  cudaStream_t sub_stream[kMaxSub] = {};
+  cudaEvent_t sub_done[kMaxSub] = {};
+  cudaEvent_t fork_ev = nullptr;
+  bool prepared = false;
   long long total_frames = 0;
   HostBuf h_pcm, h_meta, h_counts, h_off, h_segs, h_syls, h_formants, h_energy, h_features;
   DevBuf d_pcm, d_meta, d_spec, d_frames, d_cand, d_ncand, d_gsum, d_counter;
@@ -242,7 +264,13 @@ int fa_create(const fa_config* cfg, int device, fa_handle** out) {
   }
   h->stream = h->own_stream;
   for (auto& e : h->ev) cudaEventCreate(&e);
+  for (int i = 0; i < kMaxSub; i++) {
+    cudaStreamCreateWithFlags(&h->sub_stream[i], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->sub_done[i], cudaEventDisableTiming);
+  }
+  cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming);
   h->want_spec = cfg->want_spectrum || cfg->output_level <= 2;
+  h->regions.push_back(Region{nullptr, 0, 0});
   *out = h;
   return FA_OK;
 }
@@ -251,6 +279,7 @@ int fa_destroy(fa_handle* h) {
   if (!h) return FA_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  for (int i = 0; i < kMaxSub; i++) if (h->sub_stream[i]) cudaStreamSynchronize(h->sub_stream[i]);
   for (DevBuf* b : {&h->d_pcm, &h->d_meta, &h->d_spec, &h->d_frames, &h->d_cand, &h->d_ncand, &h->d_gsum, &h->d_counter,
                     &h->d_win, &h->d_tw, &h->d_tws, &h->d_ws, &h->d_bmi, &h->d_bmw, &h->d_emph, &h->d_trkbase, &h->d_trk_i,
                     &h->d_trk_d, &h->d_trk_slot, &h->d_pt_i, &h->d_pt_e, &h->d_rows, &h->d_rowlist, &h->d_segs, &h->d_syls,
@@ -261,6 +290,11 @@ int fa_destroy(fa_handle* h) {
                      &h->h_features})
     b->release();
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (int i = 0; i < kMaxSub; i++) {
+    if (h->sub_done[i]) cudaEventDestroy(h->sub_done[i]);
+    if (h->sub_stream[i]) cudaStreamDestroy(h->sub_stream[i]);
+  }
+  if (h->fork_ev) cudaEventDestroy(h->fork_ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return FA_OK;
@@ -276,39 +310,68 @@ int fa_set_stream(fa_handle* h, void* s) {
   return FA_OK;
 }
 
+int fa_set_pipeline(fa_handle* h, int n_sub) {
+  if (!h || n_sub < 0 || n_sub > kMaxSub) return FA_ERR_INVALID_ARG;
+  h->pipeline = n_sub;
+  return FA_OK;
+}
+
+int fa_set_spectrum_sink(fa_handle* h, float* dst, size_t cap_rows) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  if (dst && !h->want_spec) return fail(h, FA_ERR_INVALID_ARG, "spectrum not materialised (set want_spectrum or output_level <= 2)");
+  h->spec_sink = dst;
+  h->spec_sink_rows = dst ? cap_rows : 0;
+  return FA_OK;
+}
+
 int fa_reset(fa_handle* h) {
   if (!h) return FA_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   h->utts.clear();
   h->index.clear();
+  h->regions.clear();
+  h->regions.push_back(Region{nullptr, 0, 0});
   h->staged = 0;
   h->total_frames = 0;
-  h->uploaded = h->ran = h->downloaded = false;
+  h->uploaded = h->ran = h->downloaded = h->prepared = false;
   return FA_OK;
 }
 
-static int submit_common(fa_handle* h, int64_t utt_id, size_t n, int sr, float** dst) {
-  if (!h || sr <= 0) return fail(h, FA_ERR_INVALID_ARG, "Invalid audio source");
+static int add_utt(fa_handle* h, int64_t utt_id, int region, long long off, size_t n, int sr) {
   if (h->index.count(utt_id)) return fail(h, FA_ERR_INVALID_ARG, "duplicate utterance id");
-  cudaSetDevice(h->device);
-  if (h->utts.empty()) h->sample_rate = sr;
-  else if (sr != h->sample_rate) return fail(h, FA_ERR_INVALID_ARG, "all utterances of a batch must share the sample rate");
-  if (h->uploaded || h->ran) return fail(h, FA_ERR_BUSY, "Error: Already playing");
-  const long long off = h->staged;
-  const long long padded = ((long long)n + 3) & ~3ll;
-  FA_CUDA(h->h_pcm.reserve((size_t)(off + padded + 16) * sizeof(float), (size_t)off * sizeof(float)));
   Utt u;
-  u.id = utt_id; u.off = off; u.n = (long long)n;
+  u.id = utt_id; u.region = region; u.off = off; u.n = (long long)n;
   u.frames = (int)(n / (size_t)fa_tab_hop(sr, h->cfg.window_step_ms));
   u.row0 = h->total_frames;
   h->index[utt_id] = (int)h->utts.size();
   h->utts.push_back(u);
-  h->staged = off + padded;
   h->total_frames += u.frames;
+  return (int)h->utts.size() - 1;
+}
+
+static int submit_check(fa_handle* h, int sr) {
+  if (!h || sr <= 0) return fail(h, FA_ERR_INVALID_ARG, "Invalid audio source");
+  cudaSetDevice(h->device);
+  if (h->uploaded || h->ran) return fail(h, FA_ERR_BUSY, "Error: Already playing");
+  if (h->utts.empty()) h->sample_rate = sr;
+  else if (sr != h->sample_rate) return fail(h, FA_ERR_INVALID_ARG, "all utterances of a batch must share the sample rate");
+  return FA_OK;
+}
+
+static int submit_common(fa_handle* h, int64_t utt_id, size_t n, int sr, float** dst) {
+  int rc = submit_check(h, sr);
+  if (rc != FA_OK) return rc;
+  if (h->index.count(utt_id)) return fail(h, FA_ERR_INVALID_ARG, "duplicate utterance id");
+  const long long off = h->staged;
+  const long long padded = ((long long)n + 3) & ~3ll;
+  FA_CUDA(h->h_pcm.reserve((size_t)(off + padded + 16) * sizeof(float), (size_t)off * sizeof(float)));
+  rc = add_utt(h, utt_id, 0, off, n, sr);
+  if (rc < 0) return rc;
+  h->staged = off + padded;
   *dst = h->h_pcm.as<float>() + off;
   for (long long i = (long long)n; i < padded; i++) (*dst)[i] = 0.f;
-  return (int)h->utts.size() - 1;
+  return rc;
 }
 
 int fa_submit_pcm(fa_handle* h, int64_t utt_id, const float* pcm, size_t n, int sr) {
@@ -329,9 +392,41 @@ int fa_submit_pcm_i16(fa_handle* h, int64_t utt_id, const int16_t* pcm, size_t n
   return rc;
 }
 
-int fa_upload(fa_handle* h) {
-  if (!h) return FA_ERR_INVALID_ARG;
-  cudaSetDevice(h->device);
+int fa_submit_pcm_batch(fa_handle* h, int64_t first_utt_id, const float* pcm, const int64_t* offsets, int n_utt, int sr) {
+  int rc = submit_check(h, sr);
+  if (rc != FA_OK) return rc;
+  if (!pcm || !offsets || n_utt <= 0) return fail(h, FA_ERR_INVALID_ARG, "Invalid audio source");
+  for (int i = 0; i < n_utt; i++)
+    if (offsets[i + 1] < offsets[i] || offsets[0] < 0) return fail(h, FA_ERR_INVALID_ARG, "offsets must be non-decreasing");
+  for (int i = 0; i < n_utt; i++)
+    if (h->index.count(first_utt_id + i)) return fail(h, FA_ERR_INVALID_ARG, "duplicate utterance id");
+  cudaPointerAttributes attr;
+  const bool pinned = cudaPointerGetAttributes(&attr, pcm) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();  // an unregistered pointer is not an error for us
+  const int first = (int)h->utts.size();
+  if (pinned) {
+    // zero copy: the H2D transfer reads the caller's buffer, which must stay valid until fa_sync
+    Region r;
+    r.host = pcm + offsets[0];
+    r.n = offsets[n_utt] - offsets[0];
+    r.dev_off = 0;
+    h->regions.push_back(r);
+    const int ri = (int)h->regions.size() - 1;
+    for (int i = 0; i < n_utt; i++) {
+      rc = add_utt(h, first_utt_id + i, ri, offsets[i] - offsets[0], (size_t)(offsets[i + 1] - offsets[i]), sr);
+      if (rc < 0) return rc;
+    }
+  } else {
+    for (int i = 0; i < n_utt; i++) {
+      rc = fa_submit_pcm(h, first_utt_id + i, pcm + offsets[i], (size_t)(offsets[i + 1] - offsets[i]), sr);
+      if (rc < 0) return rc;
+    }
+  }
+  return first;
+}
+
+// allocate everything a run needs and upload the small tables / metadata (not the PCM)
+static int prepare(fa_handle* h) {
   if (h->utts.empty()) return fail(h, FA_ERR_INVALID_ARG, "Invalid audio source");
   if (!h->tables_ready || h->tables_sr != h->sample_rate) {
     const int rc = build_tables(h, h->sample_rate);
@@ -340,29 +435,38 @@ int fa_upload(fa_handle* h) {
   const int n = (int)h->utts.size();
   const long long F = h->total_frames;
   cudaStream_t s = h->stream;
+  // device layout of the PCM: [staging | caller buffers ...], each region 16-byte aligned
+  long long dev = 0;
+  h->regions[0].n = h->staged;
+  for (auto& r : h->regions) {
+    r.dev_off = dev;
+    dev += (r.n + 3) & ~3ll;
+  }
+  h->dev_floats = dev;
+  h->abs_off.resize(n);
   // meta: utt_off[n], utt_len[n], frame_off[n+1], track_base[n+1]
   FA_CUDA(h->h_meta.reserve(sizeof(long long) * (4 * (size_t)n + 2)));
   long long* m = h->h_meta.as<long long>();
   long long tb = 0;
   for (int i = 0; i < n; i++) {
-    m[i] = h->utts[i].off;
-    m[n + i] = h->utts[i].n;
-    m[2 * n + i] = h->utts[i].row0;
+    const Utt& u = h->utts[i];
+    h->abs_off[i] = h->regions[u.region].dev_off + u.off;
+    m[i] = h->abs_off[i];
+    m[n + i] = u.n;
+    m[2 * n + i] = u.row0;
     m[3 * n + 1 + i] = tb;
-    tb += (long long)h->utts[i].frames * 16 + 64;
+    tb += (long long)u.frames * 16 + 64;
   }
   m[2 * n + n] = F;
   m[3 * n + 1 + n] = tb;
   h->track_total = tb;
   FA_CUDA(h->d_meta.reserve(sizeof(long long) * (4 * (size_t)n + 2)));
   FA_CUDA(cudaMemcpyAsync(h->d_meta.p, m, sizeof(long long) * (4 * (size_t)n + 2), cudaMemcpyHostToDevice, s));
-  FA_CUDA(h->d_pcm.reserve((size_t)(h->staged + 16) * sizeof(float)));
-  FA_CUDA(cudaMemcpyAsync(h->d_pcm.p, h->h_pcm.p, (size_t)(h->staged + 16) * sizeof(float), cudaMemcpyHostToDevice, s));
-  // outputs / workspaces
+  FA_CUDA(h->d_pcm.reserve((size_t)(dev + 16) * sizeof(float)));
   const size_t Fz = (size_t)std::max<long long>(F, 1), nz = (size_t)n;
   if (h->want_spec || h->N == 2048) FA_CUDA(h->d_spec.reserve(Fz * h->M * sizeof(float)));  // also the K1a -> K1b magnitude rows
   FA_CUDA(h->d_frames.reserve(Fz * h->B * sizeof(uint32_t)));
-  FA_CUDA(h->d_counter.reserve(16));
+  FA_CUDA(h->d_counter.reserve(16 * sizeof(int)));
   if (h->cfg.output_level >= 3) {
     FA_CUDA(h->d_cand.reserve(Fz * h->maxp * sizeof(uint32_t)));
     FA_CUDA(h->d_ncand.reserve(Fz * sizeof(int)));
@@ -391,29 +495,72 @@ int fa_upload(fa_handle* h) {
     if (h->cfg.output_level == 5 || h->cfg.output_level == 13)
       FA_CUDA(h->g_features.reserve((Fz + nz) * FA_N_FEATURES * sizeof(double)));
   }
-  h->uploaded = true;
-  h->ran = false;
-  h->downloaded = false;
+  h->prepared = true;
   return FA_OK;
 }
 
-int fa_run_resident(fa_handle* h) {
-  if (!h) return FA_ERR_INVALID_ARG;
-  if (!h->uploaded) return fail(h, FA_ERR_NOT_RUN, "fa_run_resident before fa_upload");
-  cudaSetDevice(h->device);
-  cudaStream_t s = h->stream;
+// split the batch into sub-batches of whole utterances with about equal frame counts
+static std::vector<SubBatch> plan(const fa_handle* h) {
+  const int n = (int)h->utts.size();
+  int S = h->pipeline;
+  if (S == 0) S = std::min(kMaxSub, std::max(1, n / 96));
+  S = std::max(1, std::min(S, n));
+  std::vector<SubBatch> out;
+  const long long F = h->total_frames;
+  int u = 0;
+  for (int b = 0; b < S; b++) {
+    SubBatch sb;
+    sb.u0 = u;
+    const long long target = F * (b + 1) / S;
+    if (b == S - 1) u = n;
+    else {
+      while (u < n && h->utts[u].row0 + h->utts[u].frames <= target) u++;
+      if (u == sb.u0 && u < n) u++;
+    }
+    sb.u1 = u;
+    sb.r0 = sb.u0 < n ? h->utts[sb.u0].row0 : F;
+    sb.r1 = sb.u1 < n ? h->utts[sb.u1].row0 : F;
+    if (sb.u1 > sb.u0) out.push_back(sb);
+    if (u >= n) break;
+  }
+  return out;
+}
+
+// H2D of the PCM of utterances [u0, u1): contiguous runs per region
+static int copy_pcm_range(fa_handle* h, int u0, int u1, cudaStream_t s) {
+  int i = u0;
+  while (i < u1) {
+    const int reg = h->utts[i].region;
+    long long lo = h->utts[i].off, hi = lo + ((h->utts[i].n + 3) & ~3ll);
+    int j = i + 1;
+    while (j < u1 && h->utts[j].region == reg && h->utts[j].off >= lo) {
+      hi = std::max(hi, h->utts[j].off + ((h->utts[j].n + 3) & ~3ll));
+      j++;
+    }
+    const Region& r = h->regions[reg];
+    const float* host = reg == 0 ? h->h_pcm.as<float>() : r.host;
+    hi = std::min(hi, reg == 0 ? h->staged : r.n);
+    if (hi > lo)
+      FA_CUDA(cudaMemcpyAsync(h->d_pcm.as<float>() + r.dev_off + lo, host + lo, (size_t)(hi - lo) * sizeof(float),
+                              cudaMemcpyHostToDevice, s));
+    i = j;
+  }
+  return FA_OK;
+}
+
+// stages 1-4 of one sub-batch on stream s
+static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s, cudaEvent_t* ev /* 5 or null */) {
   const fa_config& c = h->cfg;
   const int n = (int)h->utts.size();
   const long long F = h->total_frames;
   const long long* meta = h->d_meta.as<long long>();
-  h->launches = 0;
-  FA_CUDA(cudaEventRecord(h->ev[0], s));
-
+  if (ev) FA_CUDA(cudaEventRecord(ev[0], s));
   FaSpectrumParams sp;
   memset(&sp, 0, sizeof(sp));
   sp.pcm = h->d_pcm.as<float>();
   sp.utt_off = meta; sp.utt_len = meta + n; sp.frame_off = meta + 2 * n;
-  sp.n_utt = n; sp.hop = h->hop; sp.N = h->N; sp.M = h->M; sp.logM = h->logM; sp.B = h->B;
+  sp.n_utt = n; sp.utt_begin = sb.u0; sp.utt_count = sb.u1 - sb.u0; sp.row_begin = sb.r0;
+  sp.hop = h->hop; sp.N = h->N; sp.M = h->M; sp.logM = h->logM; sp.B = h->B;
   sp.win = h->d_win.as<float>(); sp.tw = h->d_tw.as<float2>(); sp.tw_stage = h->d_tws.as<float2>(); sp.ws = h->d_ws.as<float2>();
   sp.bm_k0 = h->d_bmi.as<int>(); sp.bm_cnt = sp.bm_k0 + h->B; sp.bm_off = sp.bm_k0 + 2 * h->B;
   sp.bm_w = h->d_bmw.as<float>(); sp.n_weights = h->n_weights;
@@ -423,21 +570,19 @@ int fa_run_resident(fa_handle* h) {
   sp.clamp_db = c.clamp_db;
   sp.scratch_mag = h->N == 2048;
   sp.write_db = h->want_spec;
-  sp.n_rows = F;
+  sp.n_rows = sb.r1 - sb.r0;
   sp.spec_db = (h->want_spec || sp.scratch_mag) ? h->d_spec.as<float>() : nullptr;
   sp.frames = h->d_frames.as<uint32_t>();
-  sp.work_counter = h->d_counter.as<int>();
+  sp.work_counter = h->d_counter.as<int>() + slot;
   FA_CUDA(fa_launch_spectrum(sp, s, &h->launches));
-  FA_CUDA(cudaEventRecord(h->ev[1], s));
-
-  if (c.output_level >= 3 && F > 0) {
+  if (ev) FA_CUDA(cudaEventRecord(ev[1], s));
+  if (c.output_level >= 3 && sb.r1 > sb.r0) {
     FaPeaksParams pp;
-    pp.frames = h->d_frames.as<uint32_t>(); pp.B = h->B; pp.maxp = h->maxp; pp.n_frames = F;
+    pp.frames = h->d_frames.as<uint32_t>(); pp.B = h->B; pp.maxp = h->maxp; pp.n_frames = sb.r1 - sb.r0; pp.row_begin = sb.r0;
     pp.cand = h->d_cand.as<uint32_t>(); pp.ncand = h->d_ncand.as<int>(); pp.gsum = h->d_gsum.as<double>();
     FA_CUDA(fa_launch_peaks(pp, s, &h->launches));
   }
-  FA_CUDA(cudaEventRecord(h->ev[2], s));
-
+  if (ev) FA_CUDA(cudaEventRecord(ev[2], s));
   if (c.output_level >= 3) {
     const size_t T = (size_t)std::max<long long>(h->track_total, 1);
     const size_t P = (size_t)std::max<long long>(F, 1) * h->maxp;
@@ -446,6 +591,7 @@ int fa_run_resident(fa_handle* h) {
     memset(&g, 0, sizeof(g));
     g.frames = h->d_frames.as<uint32_t>(); g.cand = h->d_cand.as<uint32_t>(); g.ncand = h->d_ncand.as<int>();
     g.gsum = h->d_gsum.as<double>(); g.frame_off = meta + 2 * n; g.n_utt = n; g.B = h->B; g.maxp = h->maxp;
+    g.utt_begin = sb.u0; g.utt_count = sb.u1 - sb.u0;
     g.level = c.output_level;
     g.max_voiced_bin = (int)fa_js_parse_int(0.7 * (double)h->B);
     g.seg_min_frames = (int)fa_js_parse_int(c.min_seg_length_ms / c.window_step_ms);
@@ -464,37 +610,98 @@ int fa_run_resident(fa_handle* h) {
     g.formants = h->d_formants.as<float>(); g.energy = h->d_energy.as<float>();
     int* cnt = h->d_counts.as<int>();
     g.n_segs = cnt; g.n_stored = cnt + n; g.n_rows = cnt + 2 * n; g.n_syls = cnt + 3 * n; g.overflow = cnt + 5 * n;
-    FA_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * 6 * (size_t)n, s));
     FA_CUDA(fa_launch_segment(g, s, &h->launches));
-    FA_CUDA(cudaEventRecord(h->ev[3], s));
-
+    if (ev) FA_CUDA(cudaEventRecord(ev[3], s));
     if (c.output_level == 5 || c.output_level == 13) {
       FaFeatureParams fp;
       fp.frame_off = meta + 2 * n; fp.n_utt = n; fp.level = c.output_level;
+      fp.utt_begin = sb.u0; fp.utt_count = sb.u1 - sb.u0;
       fp.segs = g.segs; fp.n_segs = g.n_segs; fp.syls = g.syls; fp.n_syls = g.n_syls; fp.formants = g.formants;
       fp.features = h->d_features.as<double>(); fp.n_feat = cnt + 4 * n;
       FA_CUDA(fa_launch_features(fp, s, &h->launches));
     }
-    FA_CUDA(cudaEventRecord(h->ev[4], s));
+    if (ev) FA_CUDA(cudaEventRecord(ev[4], s));
+  } else if (ev) {
+    FA_CUDA(cudaEventRecord(ev[3], s));
+    FA_CUDA(cudaEventRecord(ev[4], s));
+  }
+  return FA_OK;
+}
 
+// the whole device side of a run: fork into sub-batch streams, (optional) H2D + kernels + (optional) spectrum
+// sink D2H per sub-batch, join, then the dense gather
+static int run_device(fa_handle* h, bool with_h2d, bool with_sink) {
+  cudaStream_t s = h->stream;
+  const fa_config& c = h->cfg;
+  const int n = (int)h->utts.size();
+  const long long* meta = h->d_meta.as<long long>();
+  h->launches = 0;
+  if (c.output_level >= 3) FA_CUDA(cudaMemsetAsync(h->d_counts.p, 0, sizeof(int) * 6 * (size_t)n, s));
+  FA_CUDA(cudaEventRecord(h->ev[0], s));
+  const std::vector<SubBatch> subs = plan(h);
+  const bool sink = with_sink && h->spec_sink && h->want_spec;
+  if (sink && (size_t)h->total_frames > h->spec_sink_rows) return fail(h, FA_ERR_CAPACITY, "spectrum sink too small");
+  if (subs.size() <= 1) {
+    SubBatch all{0, n, 0, h->total_frames};
+    if (with_h2d) { const int rc = copy_pcm_range(h, 0, n, s); if (rc != FA_OK) return rc; }
+    const int rc = launch_sub(h, all, 0, s, h->ev);
+    if (rc != FA_OK) return rc;
+    if (sink && h->total_frames)
+      FA_CUDA(cudaMemcpyAsync(h->spec_sink, h->d_spec.p, (size_t)h->total_frames * h->M * sizeof(float), cudaMemcpyDeviceToHost, s));
+  } else {
+    FA_CUDA(cudaEventRecord(h->fork_ev, s));
+    for (size_t b = 0; b < subs.size(); b++) {
+      cudaStream_t ss = h->sub_stream[b];
+      FA_CUDA(cudaStreamWaitEvent(ss, h->fork_ev, 0));
+      if (with_h2d) { const int rc = copy_pcm_range(h, subs[b].u0, subs[b].u1, ss); if (rc != FA_OK) return rc; }
+      const int rc = launch_sub(h, subs[b], (int)b, ss, nullptr);
+      if (rc != FA_OK) return rc;
+      if (sink && subs[b].r1 > subs[b].r0)
+        FA_CUDA(cudaMemcpyAsync(h->spec_sink + (size_t)subs[b].r0 * h->M, h->d_spec.as<float>() + (size_t)subs[b].r0 * h->M,
+                                (size_t)(subs[b].r1 - subs[b].r0) * h->M * sizeof(float), cudaMemcpyDeviceToHost, ss));
+      FA_CUDA(cudaEventRecord(h->sub_done[b], ss));
+    }
+    for (size_t b = 0; b < subs.size(); b++) FA_CUDA(cudaStreamWaitEvent(s, h->sub_done[b], 0));
+    for (int i = 1; i <= 4; i++) FA_CUDA(cudaEventRecord(h->ev[i], s));  // per-stage times only exist in serial mode
+  }
+  if (c.output_level >= 3) {
+    int* cnt = h->d_counts.as<int>();
     FaGatherArgs ga;
-    ga.frame_off = meta + 2 * n; ga.n_utt = n; ga.n_segs = g.n_segs; ga.n_rows = g.n_rows; ga.n_syls = g.n_syls;
+    ga.frame_off = meta + 2 * n; ga.n_utt = n; ga.n_segs = cnt; ga.n_rows = cnt + 2 * n; ga.n_syls = cnt + 3 * n;
     ga.n_feat = cnt + 4 * n; ga.off = h->d_off.as<long long>();
-    ga.segs = g.segs; ga.syls = g.syls; ga.formants = g.formants; ga.energy = g.energy;
+    ga.segs = h->d_segs.as<fa_segment>(); ga.syls = h->d_syls.as<fa_syllable>();
+    ga.formants = h->d_formants.as<float>(); ga.energy = h->d_energy.as<float>();
     ga.features = h->d_features.as<double>();
     ga.d_segs = h->g_segs.as<fa_segment>(); ga.d_syls = h->g_syls.as<fa_syllable>();
     ga.d_formants = h->g_formants.as<float>(); ga.d_energy = h->g_energy.as<float>();
     ga.d_features = h->g_features.as<double>();
     FA_CUDA(fa_launch_prefix(ga, s, &h->launches));
     FA_CUDA(fa_launch_gather(ga, s, &h->launches));
-  } else {
-    FA_CUDA(cudaEventRecord(h->ev[3], s));
-    FA_CUDA(cudaEventRecord(h->ev[4], s));
   }
   FA_CUDA(cudaEventRecord(h->ev[5], s));
   h->ran = true;
   h->downloaded = false;
   return FA_OK;
+}
+
+int fa_upload(fa_handle* h) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  int rc = prepare(h);
+  if (rc != FA_OK) return rc;
+  rc = copy_pcm_range(h, 0, (int)h->utts.size(), h->stream);
+  if (rc != FA_OK) return rc;
+  h->uploaded = true;
+  h->ran = false;
+  h->downloaded = false;
+  return FA_OK;
+}
+
+int fa_run_resident(fa_handle* h) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  if (!h->uploaded) return fail(h, FA_ERR_NOT_RUN, "fa_run_resident before fa_upload");
+  cudaSetDevice(h->device);
+  return run_device(h, false, false);
 }
 
 int fa_download(fa_handle* h) {
@@ -535,10 +742,10 @@ int fa_run(fa_handle* h) {
   if (!h) return FA_ERR_INVALID_ARG;
   if (h->ran) return fail(h, FA_ERR_BUSY, "Error: Already playing");
   cudaSetDevice(h->device);
-  FA_CUDA(cudaEventRecord(h->ev[7], h->stream));
-  int rc = fa_upload(h);
+  int rc = prepare(h);
   if (rc != FA_OK) return rc;
-  rc = fa_run_resident(h);
+  h->uploaded = true;
+  rc = run_device(h, true, true);
   if (rc != FA_OK) return rc;
   return fa_download(h);
 }

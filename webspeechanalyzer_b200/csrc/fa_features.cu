@@ -89,7 +89,7 @@ __device__ void slot_features(const float* __restrict__ F, const int len, const 
 }
 
 __global__ void __launch_bounds__(kFeatThreads) fa_features_kernel(const FaFeatureParams p) {
-  const int u = blockIdx.x;
+  const int u = p.utt_begin + blockIdx.x;
   const long long row0 = p.frame_off[u], sb = row0 + u;
   const int nseg = p.n_segs[u];
   const bool per_syl = p.level == 13;
@@ -229,8 +229,8 @@ __global__ void __launch_bounds__(128) fa_gather_kernel(const FaGatherArgs g) {
 }  // namespace
 
 cudaError_t fa_launch_features(const FaFeatureParams& p, cudaStream_t s, int* launches) {
-  if (p.n_utt <= 0) return cudaSuccess;
-  fa_features_kernel<<<p.n_utt, kFeatThreads, 0, s>>>(p);
+  if (p.utt_count <= 0) return cudaSuccess;
+  fa_features_kernel<<<p.utt_count, kFeatThreads, 0, s>>>(p);
   if (launches) (*launches)++;
   return cudaGetLastError();
 }

@@ -20,7 +20,9 @@ struct FaSpectrumParams {
   const long long* utt_off;      // [n_utt] first sample of utterance u
   const long long* utt_len;      // [n_utt] samples
   const long long* frame_off;    // [n_utt + 1] first frame row of utterance u
-  int n_utt;
+  int n_utt;                     // utterances of the whole batch (length of the tables above)
+  int utt_begin, utt_count;      // the sub-batch this launch covers
+  long long row_begin;           // first frame row of the sub-batch
   int hop, N, M, logM, B;
   const float* win;              // [N]
   const float2* tw;              // [M/2]   W_M^j
@@ -39,7 +41,7 @@ struct FaSpectrumParams {
                                  // generic path: dB rows or nullptr
   int scratch_mag;               // 1: spec_db is allocated and may be used as the K1a -> K1b magnitude buffer
   int write_db;                  // 1: the caller wants the dB rows
-  long long n_rows;              // total frames of the batch
+  long long n_rows;              // frames of the sub-batch
   uint32_t* frames;              // [F_total][B] or nullptr
   int* work_counter;             // dynamic utterance queue
 };
@@ -47,7 +49,8 @@ struct FaSpectrumParams {
 struct FaPeaksParams {
   const uint32_t* frames;        // [F_total][B]
   int B, maxp;
-  long long n_frames;
+  long long n_frames;            // frames of the sub-batch
+  long long row_begin;
   uint32_t* cand;                // [F_total][maxp] packed lo | hi<<8 | pk<<16 | last<<24
   int* ncand;                    // [F_total]
   double* gsum;                  // [F_total] sum e[1..B-1]
@@ -61,6 +64,7 @@ struct FaSegmentParams {
   const double* gsum;
   const long long* frame_off;    // [n_utt + 1]
   int n_utt, B, maxp, level;
+  int utt_begin, utt_count;
   // reset_segmentation @B25053
   int max_voiced_bin, seg_min_frames, auto_gate;
   double seg_breaker, y0, v0;
@@ -84,6 +88,7 @@ struct FaSegmentParams {
 struct FaFeatureParams {
   const long long* frame_off;
   int n_utt, level;
+  int utt_begin, utt_count;
   const fa_segment* segs; const int* n_segs;
   const fa_syllable* syls; const int* n_syls;
   const float* formants;

@@ -19,8 +19,9 @@ constexpr int kPeakThreads = 128;
 // (rows are 512 B for B = 128: four full cache lines, every byte used; K1 has just written them, so most
 // come from L2) and runs the automaton in registers.  200k frames = 6250 warps: one wave at full occupancy.
 __global__ void __launch_bounds__(kPeakThreads) fa_peaks_kernel(const FaPeaksParams p) {
-  const long long f = (long long)blockIdx.x * kPeakThreads + threadIdx.x;
-  if (f >= p.n_frames) return;
+  const long long fi = (long long)blockIdx.x * kPeakThreads + threadIdx.x;
+  if (fi >= p.n_frames) return;
+  const long long f = p.row_begin + fi;
   const int B = p.B;
   const uint32_t* __restrict__ e = p.frames + (size_t)f * B;
   uint32_t* out = p.cand + (size_t)f * p.maxp;

@@ -525,8 +525,9 @@ __global__ void __launch_bounds__(kWarps * 32) fa_segment_kernel(const FaSegment
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpShared* sh = reinterpret_cast<WarpShared*>(smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int u = blockIdx.x * kWarps + wib;
-  if (u >= p.n_utt) return;
+  const int ui = blockIdx.x * kWarps + wib;
+  if (ui >= p.utt_count) return;
+  const int u = p.utt_begin + ui;
   WarpShared& S = sh[wib];
   Bases bs;
   bs.row0 = p.frame_off[u];
@@ -651,8 +652,8 @@ __global__ void __launch_bounds__(kWarps * 32) fa_segment_kernel(const FaSegment
 }  // namespace
 
 cudaError_t fa_launch_segment(const FaSegmentParams& p, cudaStream_t s, int* launches) {
-  if (p.n_utt <= 0) return cudaSuccess;
-  const int grid = (p.n_utt + kWarps - 1) / kWarps;
+  if (p.utt_count <= 0) return cudaSuccess;
+  const int grid = (p.utt_count + kWarps - 1) / kWarps;
   const int bytes = (int)sizeof(WarpShared) * kWarps;
   cudaError_t e = cudaFuncSetAttribute(fa_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;

@@ -86,6 +86,26 @@ class Engine:
         pcm = np.ascontiguousarray(pcm, np.float32)
         return self._check(self._lib.fa_submit_pcm(self._h, utt_id, pcm.ctypes.data, pcm.size, sample_rate))
 
+    def submit_batch(self, first_utt_id: int, pcm: np.ndarray, offsets: np.ndarray, sample_rate: int) -> int:
+        """Whole batch in one float32 buffer; zero-copy when `pcm` is page-locked (keep it alive until sync())."""
+        assert pcm.dtype == np.float32 and pcm.flags.c_contiguous
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        self._keep = (pcm, offsets)
+        return self._check(self._lib.fa_submit_pcm_batch(self._h, first_utt_id, pcm.ctypes.data, offsets.ctypes.data,
+                                                         offsets.size - 1, sample_rate))
+
+    def set_pipeline(self, n_sub: int):
+        self._check(self._lib.fa_set_pipeline(self._h, n_sub))
+
+    def set_spectrum_sink(self, dst: np.ndarray | None):
+        if dst is None:
+            self._sink = None
+            self._check(self._lib.fa_set_spectrum_sink(self._h, None, 0))
+        else:
+            assert dst.dtype == np.float32 and dst.flags.c_contiguous and dst.shape[1] == self.cfg.fft_size // 2
+            self._sink = dst
+            self._check(self._lib.fa_set_spectrum_sink(self._h, dst.ctypes.data, dst.shape[0]))
+
     def run(self):
         self._check(self._lib.fa_run(self._h))
 
