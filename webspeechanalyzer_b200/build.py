@@ -51,7 +51,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {s}")
     subprocess.check_call([NVCC, "-shared", "-o", LIB + ".tmp"] + objs + ["-Xcompiler", "-fPIC", "-cudart", "static"])
     os.replace(LIB + ".tmp", LIB)
+    build_node_addon()
     return LIB
+
+
+def build_node_addon() -> str:
+    """The Node.js addon over the C-ABI (webspeechanalyzer_b200/node).  No Node here: compile-checked against the
+    minimal N-API declarations in node/node_api_min.h; the napi_* symbols resolve when node loads the addon."""
+    node = os.path.join(HERE, "node")
+    out = os.path.join(node, "fa_b200.node")
+    subprocess.check_call(["gcc", "-std=gnu11", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-I",
+                           os.path.join(ROOT, "include"), "-o", out, os.path.join(node, "fa_napi.c"), "-L", HERE,
+                           "-lfa_b200", "-Wl,-rpath,$ORIGIN/.."])
+    return out
 
 
 if __name__ == "__main__":
