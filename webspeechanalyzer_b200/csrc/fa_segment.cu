@@ -44,6 +44,7 @@ struct WarpShared {
   double a_vel[ACAP], a_sum_e[ACAP], a_sum_eb[ACAP];
   double cand_sc[CMAX][ACAP];              // [k][slot]: lane-consecutive slots -> conflict free
   unsigned char cand_o[CMAX][ACAP];
+  unsigned char cand_n[ACAP];              // candidates of the slot this frame
 };
 
 struct ScanState {
@@ -198,12 +199,13 @@ __device__ __noinline__ void accumulate_fm(const FaSegmentParams& p, WarpShared&
   }
   // (1) score every (live track, peak within its window): lane per track.  best[o] = max score via
   //     shared-memory atomicMax on the bit pattern; ties go to the earlier track via atomicMin on the slot.
-  int my_cnt[ACAP / 32];
-#pragma unroll
-  for (int ps = 0; ps < ACAP / 32; ps++) {
-    my_cnt[ps] = 0;
+  // (live tracks: 17 on average, rarely more than 40 -> usually one pass of 32 lanes)
+  const int n_pass = (st.n_act + 31) >> 5;
+  bool ovf = false;
+  for (int ps = 0; ps < n_pass; ps++) {
     const int r = ps * 32 + lane;
     if (r < st.n_act) {
+      int cnt = 0;
       const int gap = n_label - S.a_last_frame[r];
       if (gap >= 0 && gap < 4) {
         const int lb = S.a_last_bin[r];
@@ -214,7 +216,6 @@ __device__ __noinline__ void accumulate_fm(const FaSegmentParams& p, WarpShared&
         unsigned bits = (unsigned)(two >> sh) & ((2u << (whi - wlo)) - 1u);
         const double amp_old = (double)S.a_last_amp[r], vel = S.a_vel[r];
         const int np = S.a_npts[r];
-        int cnt = 0;
         while (bits) {
           const int j = __ffs(bits) - 1;
           bits &= bits - 1;
@@ -230,21 +231,17 @@ __device__ __noinline__ void accumulate_fm(const FaSegmentParams& p, WarpShared&
             atomicMax(&S.bestbits[o], (unsigned long long)__double_as_longlong(sc));
           }
         }
-        my_cnt[ps] = cnt;
       }
+      ovf |= cnt > CMAX;
+      S.cand_n[r] = (unsigned char)(cnt > CMAX ? CMAX : cnt);
     }
   }
-  {
-    bool ovf = false;
-#pragma unroll
-    for (int ps = 0; ps < ACAP / 32; ps++) ovf |= my_cnt[ps] > CMAX;
-    if (__any_sync(FULL, ovf)) { st.overflow = 1; return; }
-  }
+  if (__any_sync(FULL, ovf)) { st.overflow = 1; return; }
   __syncwarp();
-#pragma unroll
-  for (int ps = 0; ps < ACAP / 32; ps++) {
+  for (int ps = 0; ps < n_pass; ps++) {
     const int r = ps * 32 + lane;
-    for (int k = 0; k < my_cnt[ps]; k++) {
+    const int cnt = r < st.n_act ? S.cand_n[r] : 0;
+    for (int k = 0; k < cnt; k++) {
       const int o = S.cand_o[k][r];
       if ((unsigned long long)__double_as_longlong(S.cand_sc[k][r]) == S.bestbits[o]) atomicMin(&S.owner[o], r);
     }
@@ -252,12 +249,12 @@ __device__ __noinline__ void accumulate_fm(const FaSegmentParams& p, WarpShared&
   __syncwarp();
   // (2) every owning track absorbs its (merged) peaks: lane per track, its owned peaks are among its candidates
   unsigned long long moved = 0;
-#pragma unroll
-  for (int ps = 0; ps < ACAP / 32; ps++) {
+  for (int ps = 0; ps < n_pass; ps++) {
     const int r = ps * 32 + lane;
     int first = -1, lo = 0, hi = 0, o_bin = 0;
     uint32_t bamp = 0;
-    for (int k = 0; k < my_cnt[ps]; k++) {
+    const int my_cnt = r < st.n_act ? S.cand_n[r] : 0;
+    for (int k = 0; k < my_cnt; k++) {
       const int o = S.cand_o[k][r];
       if (S.owner[o] == r) {
         const int pk = S.ppk[o];
