@@ -3,10 +3,10 @@
 //
 // Restates formant_features (/root/reference/dist/main.js:2@B32369, vector assembly @B33436) and the
 // stats helpers it calls (/root/reference/src/stats.js:29-64: array_mean_NZ, only_std_NZ,
-// mean_std_NZ, arraySum).  A row is a segmented reduction over its frames; the three formant slots
-// of a row are independent, so the unit of work is (row, slot): one thread walks the slot's frames
-// in array order (the reference's summation order, so the doubles come out bit-identical to the
-// oracle's) in two passes -- sums and the accent automaton first, squared deviations second.
+// mean_std_NZ, arraySum).  A row is a segmented reduction over its frames: one warp per row; the
+// 20*log10(E) of every (frame, slot) is computed lane-parallel, then one lane per formant slot walks
+// the frames in array order (the reference's summation order, so the doubles come out bit-identical
+// to the oracle's) in two passes -- sums and the accent automaton first, squared deviations second.
 // FP64 throughout, log10 from include/fa_jsmath.h.  Kilobytes per row: latency bound, not HBM bound.
 #include "fa_internal.cuh"
 #include "fa_jsmath.h"
@@ -15,107 +15,133 @@ namespace {
 
 constexpr int kFeatThreads = 64;
 
-__device__ void slot_features(const float* __restrict__ F, const int len, const int n, const double ymax,
-                              double* __restrict__ out /*16*/) {
-  double cnt = 0, runs = 0, up = 0, down = 0;
-  double sum_c = 0, sum_w = 0, sum_T = 0, sum_k = 0, sum_knz = 0, sum_M = 0, sum_Anz = 0;
-  int m = 0, n_knz = 0, na = 0, n_anz = 0;
-  {
+constexpr int kChunk = 256;   // frames per chunk: dB values of 3 slots x 256 frames in shared memory per warp
+
+struct SlotAcc {
+  double cnt, runs, up, down, sum_c, sum_w, sum_T, sum_k, sum_knz, sum_M, sum_Anz, L;
+  double acc_w, acc_k, acc_a, mean_w, dbm, accm;
+  int m, n_knz, na, n_anz, S;
+  bool prev;
+};
+
+// Per row: the expensive part (20*log10(E), fdlibm, ~150 dependent FP64 ops) is done lane-per-frame into
+// shared memory; the order-sensitive part (sums in array order, run / jump / accent automaton) is done by three
+// lanes, one per formant slot, over the precomputed values.  Two passes: sums, then squared deviations.
+__device__ void row_features(const float* __restrict__ F, const int len, const double ymax, double (*sdb)[kChunk],
+                             const int lane, double* __restrict__ out /* 48 = 3 x 16 */) {
+  SlotAcc A;
+  A.cnt = A.runs = A.up = A.down = A.sum_c = A.sum_w = A.sum_T = A.sum_k = A.sum_knz = A.sum_M = A.sum_Anz = A.L = 0;
+  A.acc_w = A.acc_k = A.acc_a = A.mean_w = A.dbm = A.accm = 0;
+  A.m = A.n_knz = A.na = A.n_anz = A.S = 0;
+  A.prev = false;
+  const int n = lane;  // slot handled by this lane in the sequential phases (lanes 0..2)
+  for (int pass = 0; pass < 2; pass++) {
     bool prev = false;
     int S = 0;
     double L = 0;
-    for (int t = 0; t < len; t++) {
-      const double r = (double)F[(size_t)t * 9 + 3 * n], a = (double)F[(size_t)t * 9 + 3 * n + 1];
-      if (r > 0 && a > 0) {
-        const double f = (double)F[(size_t)t * 9 + 3 * n + 2], d = 20.0 * fa_js_log10(a);
-        sum_c += r * d; sum_w += r; sum_M += f * d; sum_T += a; sum_k += d;
-        if (d > 0) { sum_knz += d; n_knz++; }
-        m++;
-        if (prev) {
-          const double j = r - (double)F[(size_t)(t - 1) * 9 + 3 * n];
-          if (j > 1) up += j; else if (j < -1) down += -1 * j;
-          if (a > L) { L = a; S = 1; }
-          else if (S == 1 && a < L / 2) {
-            if (L > 10) { na++; if (d > 0) { sum_Anz += d; n_anz++; } }
-            L = 0; S = -1;
-          }
+    for (int c0 = 0; c0 < len; c0 += kChunk) {
+      const int cn = min(kChunk, len - c0);
+      __syncwarp();
+      for (int i = lane; i < 3 * cn; i += 32) {
+        const int sl = i / cn, t = i - sl * cn;
+        const double a = (double)F[(size_t)(c0 + t) * 9 + 3 * sl + 1];
+        sdb[sl][t] = a > 0 ? 20.0 * fa_js_log10(a) : 0.0;
+      }
+      __syncwarp();
+      if (lane < 3) {
+        for (int t = 0; t < cn; t++) {
+          const size_t row = (size_t)(c0 + t) * 9 + 3 * n;
+          const double r = (double)F[row], a = (double)F[row + 1];
+          if (r > 0 && a > 0) {
+            const double d = sdb[n][t];
+            if (pass == 0) {
+              const double f = (double)F[row + 2];
+              A.sum_c += r * d; A.sum_w += r; A.sum_M += f * d; A.sum_T += a; A.sum_k += d;
+              if (d > 0) { A.sum_knz += d; A.n_knz++; }
+              A.m++;
+            } else {
+              const double dw = r - A.mean_w, dk = d - A.dbm;
+              A.acc_w += dw * dw;
+              A.acc_k += dk * dk;
+            }
+            if (prev) {
+              if (pass == 0) {
+                const double j = r - (double)F[row - 9];
+                if (j > 1) A.up += j; else if (j < -1) A.down += -1 * j;
+              }
+              if (a > L) { L = a; S = 1; }
+              else if (S == 1 && a < L / 2) {
+                if (L > 10) {
+                  if (pass == 0) { A.na++; if (d > 0) { A.sum_Anz += d; A.n_anz++; } }
+                  else { const double da = d - A.accm; A.acc_a += da * da; }
+                }
+                L = 0; S = -1;
+              }
+            }
+            if (pass == 0) {
+              if (!prev) A.runs += 1;
+              A.cnt += 1;
+            }
+            prev = true;
+          } else { prev = false; S = 0; L = 0; }
         }
-        if (!prev) runs += 1;
-        prev = true;
-        cnt += 1;
-      } else { prev = false; S = 0; L = 0; }
+      }
+    }
+    if (pass == 0 && lane < 3 && A.runs > 0) {
+      A.mean_w = A.sum_w / (double)A.m;  // every bin in the list is > 0
+      A.dbm = A.sum_knz / (double)A.n_knz;
+      if (A.na > 0) A.accm = A.sum_Anz / (double)A.n_anz;
     }
   }
-  double fmean = 0, fstd = 0, dbm = 0, dbs = 0, e_len = 0, e_cnt = 0, span = 0, accm = 0, accs = 0, prom = 0;
-  if (runs > 0) {
-    e_len = sum_T / (double)len * 100 / ymax;
-    e_cnt = sum_T / cnt * 100 / ymax;
-    fmean = sum_c / sum_k;
-    span = sum_M / sum_k;
-    const double mean_w = sum_w / (double)m;  // every bin in the list is > 0
-    dbm = sum_knz / (double)n_knz;
-    if (na > 0) accm = sum_Anz / (double)n_anz;
-    double acc_w = 0, acc_k = 0, acc_a = 0;
-    bool prev = false;
-    int S = 0;
-    double L = 0;
-    for (int t = 0; t < len; t++) {
-      const double r = (double)F[(size_t)t * 9 + 3 * n], a = (double)F[(size_t)t * 9 + 3 * n + 1];
-      if (r > 0 && a > 0) {
-        const double d = 20.0 * fa_js_log10(a);
-        const double dw = r - mean_w, dk = d - dbm;
-        acc_w += dw * dw;
-        acc_k += dk * dk;
-        if (prev) {
-          if (a > L) { L = a; S = 1; }
-          else if (S == 1 && a < L / 2) {
-            if (L > 10) { const double da = d - accm; acc_a += da * da; }
-            L = 0; S = -1;
-          }
-        }
-        prev = true;
-      } else { prev = false; S = 0; L = 0; }
+  if (lane < 3) {
+    double fmean = 0, fstd = 0, dbm = 0, dbs = 0, e_len = 0, e_cnt = 0, span = 0, accm = 0, accs = 0, prom = 0;
+    if (A.runs > 0) {
+      e_len = A.sum_T / (double)len * 100 / ymax;
+      e_cnt = A.sum_T / A.cnt * 100 / ymax;
+      fmean = A.sum_c / A.sum_k;
+      span = A.sum_M / A.sum_k;
+      dbm = A.dbm;
+      fstd = fa_sqrt(A.acc_w / (double)A.m);
+      dbs = fa_sqrt(A.acc_k / (double)A.m);
+      if (A.na > 0) {
+        accm = A.accm;
+        accs = fa_sqrt(A.acc_a / (double)A.na);
+        prom = 100 * (accm / (A.sum_k / (double)A.m) - 1);
+      }
     }
-    fstd = fa_sqrt(acc_w / (double)m);
-    dbs = fa_sqrt(acc_k / (double)m);
-    if (na > 0) {
-      accs = fa_sqrt(acc_a / (double)na);
-      prom = 100 * (accm / (sum_k / (double)m) - 1);
-    }
+    double* o = out + 16 * n;
+    o[0] = fmean; o[1] = fstd; o[2] = dbm; o[3] = dbs; o[4] = e_len; o[5] = e_cnt; o[6] = span;
+    o[7] = A.cnt; o[8] = A.runs; o[9] = A.up; o[10] = A.down; o[11] = (double)A.na; o[12] = accm; o[13] = accs;
+    o[14] = prom; o[15] = 100 * A.cnt / (double)len;
   }
-  out[0] = fmean; out[1] = fstd; out[2] = dbm; out[3] = dbs; out[4] = e_len; out[5] = e_cnt; out[6] = span;
-  out[7] = cnt; out[8] = runs; out[9] = up; out[10] = down; out[11] = (double)na; out[12] = accm; out[13] = accs;
-  out[14] = prom; out[15] = 100 * cnt / (double)len;
 }
 
 __global__ void __launch_bounds__(kFeatThreads) fa_features_kernel(const FaFeatureParams p) {
+  __shared__ double s_db[kFeatThreads / 32][3][kChunk];
   const int u = p.utt_begin + blockIdx.x;
   const long long row0 = p.frame_off[u], sb = row0 + u;
   const int nseg = p.n_segs[u];
   const bool per_syl = p.level == 13;
-  const int nrows = per_syl ? p.n_syls[u] : 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // level 5: rows are the stored segments, in seg_ci order
   __shared__ int s_rows;
-  if (!per_syl) {
-    if (threadIdx.x == 0) {
-      int c = 0;
-      for (int s = 0; s < nseg; s++) c += p.segs[sb + s].stored >= 0;
-      s_rows = c;
-    }
-    __syncthreads();
+  if (threadIdx.x == 0) {
+    int c = 0;
+    if (per_syl) c = p.n_syls[u];
+    else for (int s = 0; s < nseg; s++) c += p.segs[sb + s].stored >= 0;
+    s_rows = c;
+    p.n_feat[u] = c;
   }
-  const int R = per_syl ? nrows : s_rows;
-  if (threadIdx.x == 0) p.n_feat[u] = R;
-  for (int item = threadIdx.x; item < R * 3; item += kFeatThreads) {
-    const int row = item / 3, slot = item - row * 3;
+  __syncthreads();
+  const int R = s_rows;
+  for (int row = warp; row < R; row += kFeatThreads / 32) {
     const float* F;
     int len;
     const fa_segment* sg;
     if (per_syl) {
       const fa_syllable sy = p.syls[sb + row];
-      // find the owning segment: stored indices are increasing in seg_ci order
       int s = 0;
-      while (p.segs[sb + s].stored != sy.stored_seg) s++;
+      while (p.segs[sb + s].stored != sy.stored_seg) s++;  // stored indices increase in seg_ci order
       sg = &p.segs[sb + s];
       F = p.formants + (size_t)(row0 + sg->row_offset + sy.start) * 9;
       len = sy.len;
@@ -127,14 +153,14 @@ __global__ void __launch_bounds__(kFeatThreads) fa_features_kernel(const FaFeatu
       len = sg->len;
     }
     double* out = p.features + (size_t)(sb + row) * FA_N_FEATURES;
-    if (slot == 0) {
+    if (lane == 3) {
       out[0] = (double)len;
       out[1] = fa_sqrt((double)len);
       out[2] = sg->cs_ratio;
       out[3] = fa_js_log10(sg->ymax);
       out[4] = sg->vmin;
     }
-    slot_features(F, len, slot, sg->ymax, out + 5 + 16 * slot);
+    row_features(F, len, sg->ymax, s_db[warp], lane, out + 5);
   }
 }
 

@@ -23,7 +23,7 @@
 
 namespace {
 
-constexpr int kWarps = 4;
+constexpr int kWarps = 2;   // 47 KB of shared memory per CTA: fits beside two K1a CTAs, so sub-batches overlap
 constexpr int ACAP = 128;  // live-track slots per utterance (tracks with lastFrame >= c_ci - 3)
 constexpr int PCAP = 136;  // accepted peaks per frame (>= maxp = B/2 + 4)
 constexpr unsigned FULL = 0xffffffffu;
