@@ -202,6 +202,9 @@ FA_API int fa_copy_features(fa_handle* h, int64_t utt_id, double* dst, size_t ca
 FA_API int fa_copy_peak_candidates(fa_handle* h, int64_t utt_id, uint32_t* packed, int32_t* counts, size_t cap_rows,
                             int32_t* max_per_frame);
 
+/* Stage-2 tap: g = sum e[1..B-1] of every frame (exact in double). */
+FA_API int fa_copy_gsum(fa_handle* h, int64_t utt_id, double* dst, size_t cap_rows);
+
 /* Host-side helpers that the shims share (no device needed). */
 FA_API int fa_hop_samples(const fa_config* cfg, int sample_rate);
 FA_API int fa_frames_for(const fa_config* cfg, int sample_rate, size_t n_samples);

@@ -23,7 +23,7 @@ EXPORTS = [
     "fa_set_stream", "fa_set_pipeline", "fa_set_spectrum_sink", "fa_reset", "fa_submit_pcm", "fa_submit_pcm_i16", "fa_submit_pcm_batch", "fa_run", "fa_sync", "fa_upload",
     "fa_run_resident", "fa_download", "fa_stage_times", "fa_launch_count", "fa_num_utterances", "fa_result_counts",
     "fa_total_counts", "fa_copy_spectrum", "fa_copy_frames", "fa_copy_segments", "fa_copy_formants", "fa_copy_energy",
-    "fa_copy_syllables", "fa_copy_features", "fa_copy_peak_candidates", "fa_hop_samples", "fa_frames_for",
+    "fa_copy_syllables", "fa_copy_features", "fa_copy_peak_candidates", "fa_copy_gsum", "fa_hop_samples", "fa_frames_for",
     "fa_spec_bands", "fa_synth_speech",
 ]
 
@@ -68,7 +68,7 @@ def lib() -> C.CDLL:
     L.fa_stage_times.argtypes = [H, C.POINTER(C.c_float)]
     L.fa_result_counts.argtypes = [H, C.c_int64, C.POINTER(FaCounts)]
     L.fa_total_counts.argtypes = [H, C.POINTER(FaCounts)]
-    for n in ("fa_copy_spectrum", "fa_copy_frames", "fa_copy_segments", "fa_copy_formants", "fa_copy_energy",
+    for n in ("fa_copy_gsum", "fa_copy_spectrum", "fa_copy_frames", "fa_copy_segments", "fa_copy_formants", "fa_copy_energy",
               "fa_copy_syllables", "fa_copy_features"):
         getattr(L, n).argtypes = [H, C.c_int64, C.c_void_p, C.c_size_t]
     L.fa_copy_peak_candidates.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32)]

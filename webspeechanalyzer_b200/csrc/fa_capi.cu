@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -575,12 +576,14 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
   sp.frames = h->d_frames.as<uint32_t>();
   sp.work_counter = h->d_counter.as<int>() + slot;
   FA_CUDA(fa_launch_spectrum(sp, s, &h->launches));
+  if (getenv("FA_DEBUG_SYNC")) FA_CUDA(cudaStreamSynchronize(s));
   if (ev) FA_CUDA(cudaEventRecord(ev[1], s));
   if (c.output_level >= 3 && sb.r1 > sb.r0) {
     FaPeaksParams pp;
     pp.frames = h->d_frames.as<uint32_t>(); pp.B = h->B; pp.maxp = h->maxp; pp.n_frames = sb.r1 - sb.r0; pp.row_begin = sb.r0;
     pp.cand = h->d_cand.as<uint32_t>(); pp.ncand = h->d_ncand.as<int>(); pp.gsum = h->d_gsum.as<double>();
     FA_CUDA(fa_launch_peaks(pp, s, &h->launches));
+    if (getenv("FA_DEBUG_SYNC")) FA_CUDA(cudaStreamSynchronize(s));
   }
   if (ev) FA_CUDA(cudaEventRecord(ev[2], s));
   if (c.output_level >= 3) {
@@ -903,6 +906,12 @@ int fa_copy_peak_candidates(fa_handle* h, int64_t utt_id, uint32_t* packed, int3
   int rc = copy_rows_device(h, utt_id, h->d_cand.p, (size_t)h->maxp * sizeof(uint32_t), packed, cap_rows);
   if (rc < 0) return rc;
   return copy_rows_device(h, utt_id, h->d_ncand.p, sizeof(int), counts, cap_rows);
+}
+
+int fa_copy_gsum(fa_handle* h, int64_t utt_id, double* dst, size_t cap_rows) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  if (h->cfg.output_level < 3) return fail(h, FA_ERR_INVALID_ARG, "no peak scan below output_level 3");
+  return copy_rows_device(h, utt_id, h->d_gsum.p, sizeof(double), dst, cap_rows);
 }
 
 }  // extern "C"

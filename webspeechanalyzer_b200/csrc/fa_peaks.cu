@@ -15,6 +15,11 @@ namespace {
 
 constexpr int kPeakThreads = 128;
 
+// NOTE (round 1): variants of this loop that hoist several row loads ahead of the automaton (manual 8 x 16 B
+// batches, or `#pragma unroll 4` + __restrict__) produced wrong g / candidates for one warp of rows on the B200
+// (rows 992..1023 of an 8 x 200-frame batch, deterministic, also with a stream sync before the launch) while a
+// host build of the same source matches the oracle; unresolved, so the plain one-load-per-iteration loop stays.
+// tests/test_gpu_parity.py now checks g and the candidates of every frame.
 // One thread per frame, no shared memory: the thread streams its own 4*B-byte row with 16-byte loads
 // (rows are 512 B for B = 128: four full cache lines, every byte used; K1 has just written them, so most
 // come from L2) and runs the automaton in registers.  200k frames = 6250 warps: one wave at full occupancy.
@@ -67,32 +72,7 @@ __global__ void __launch_bounds__(kPeakThreads) fa_peaks_kernel(const FaPeaksPar
   };
 
   uint32_t e1 = 0, e2 = 0, e3 = 0;  // e[a-1], e[a-2], e[a-3]
-  if ((B & 31) == 0) {
-    // 32 bins (8 x 16 B) per batch, the next batch in flight while this one is scanned: B/32 exposed load
-    // latencies per row instead of B/4
-    const uint4* e4 = reinterpret_cast<const uint4*>(e);
-    uint4 cur[8], nxt[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) cur[i] = __ldg(e4 + i);
-    for (int q0 = 0; q0 < B / 4; q0 += 8) {
-      if (q0 + 8 < B / 4) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) nxt[i] = __ldg(e4 + q0 + 8 + i);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const uint4 x = cur[i];
-        const int a = 4 * (q0 + i);
-        if (a) step(a, x.x, e1, e2, e3);
-        step(a + 1, x.y, x.x, e1, e2);
-        step(a + 2, x.z, x.y, x.x, e1);
-        step(a + 3, x.w, x.z, x.y, x.x);
-        e3 = x.y; e2 = x.z; e1 = x.w;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; i++) cur[i] = nxt[i];
-    }
-  } else if ((B & 3) == 0) {
+  if ((B & 3) == 0) {
     const uint4* e4 = reinterpret_cast<const uint4*>(e);
     for (int q = 0; q < B / 4; q++) {
       const uint4 x = __ldg(e4 + q);

@@ -18,6 +18,8 @@
 // bit-exact against oracle/fa_oracle.c.
 //
 // This kernel moves kilobytes per utterance; it is latency bound, not HBM bound.
+#include <cstdlib>
+
 #include "fa_internal.cuh"
 #include "fa_jsmath.h"
 
@@ -518,11 +520,11 @@ __device__ __noinline__ int finalize_segment(const FaSegmentParams& p, WarpShare
   return 1;
 }
 
-__global__ void __launch_bounds__(kWarps * 32) fa_segment_kernel(const FaSegmentParams p) {
+__global__ void __launch_bounds__(128) fa_segment_kernel(const FaSegmentParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpShared* sh = reinterpret_cast<WarpShared*>(smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int ui = blockIdx.x * kWarps + wib;
+  const int ui = blockIdx.x * (int)(blockDim.x >> 5) + wib;
   if (ui >= p.utt_count) return;
   const int u = p.utt_begin + ui;
   WarpShared& S = sh[wib];
@@ -650,11 +652,13 @@ __global__ void __launch_bounds__(kWarps * 32) fa_segment_kernel(const FaSegment
 
 cudaError_t fa_launch_segment(const FaSegmentParams& p, cudaStream_t s, int* launches) {
   if (p.utt_count <= 0) return cudaSuccess;
-  const int grid = (p.utt_count + kWarps - 1) / kWarps;
-  const int bytes = (int)sizeof(WarpShared) * kWarps;
+  int kw = kWarps;
+  if (const char* ev = getenv("FA_K3_WARPS")) { const int v = atoi(ev); if (v >= 1 && v <= 4) kw = v; }  // tuning knob
+  const int grid = (p.utt_count + kw - 1) / kw;
+  const int bytes = (int)sizeof(WarpShared) * kw;
   cudaError_t e = cudaFuncSetAttribute(fa_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
-  fa_segment_kernel<<<grid, kWarps * 32, bytes, s>>>(p);
+  fa_segment_kernel<<<grid, kw * 32, bytes, s>>>(p);
   if (launches) (*launches)++;
   return cudaGetLastError();
 }

@@ -152,6 +152,10 @@ class Engine:
         c = self.counts(utt_id)
         return self._rows(self._lib.fa_copy_frames, utt_id, c["frames"], (c["bands"],), np.uint32)
 
+    def gsum(self, utt_id: int | None = None) -> np.ndarray:
+        c = self.counts(utt_id)
+        return self._rows(self._lib.fa_copy_gsum, utt_id, c["frames"], (), np.float64)
+
     def peak_candidates(self, utt_id: int):
         c = self.counts(utt_id)
         maxp = C.c_int32(0)
