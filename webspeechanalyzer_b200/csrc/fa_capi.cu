@@ -80,7 +80,7 @@ struct Region {
 
 struct SubBatch { int u0, u1; long long r0, r1; };
 
-constexpr int kMaxSub = 8;
+constexpr int kMaxSub = 16;
 
 }  // namespace
 
@@ -467,7 +467,7 @@ static int prepare(fa_handle* h) {
   const size_t Fz = (size_t)std::max<long long>(F, 1), nz = (size_t)n;
   if (h->want_spec || h->N == 2048) FA_CUDA(h->d_spec.reserve(Fz * h->M * sizeof(float)));  // also the K1a -> K1b magnitude rows
   FA_CUDA(h->d_frames.reserve(Fz * h->B * sizeof(uint32_t)));
-  FA_CUDA(h->d_counter.reserve(16 * sizeof(int)));
+  FA_CUDA(h->d_counter.reserve(2 * kMaxSub * sizeof(int)));
   if (h->cfg.output_level >= 3) {
     FA_CUDA(h->d_cand.reserve(Fz * h->maxp * sizeof(uint32_t)));
     FA_CUDA(h->d_ncand.reserve(Fz * sizeof(int)));
@@ -504,7 +504,7 @@ static int prepare(fa_handle* h) {
 static std::vector<SubBatch> plan(const fa_handle* h) {
   const int n = (int)h->utts.size();
   int S = h->pipeline;
-  if (S == 0) S = std::min(kMaxSub, std::max(1, n / 96));
+  if (S == 0) S = std::min(kMaxSub, std::max(1, n / 60));
   S = std::max(1, std::min(S, n));
   std::vector<SubBatch> out;
   const long long F = h->total_frames;
