@@ -51,6 +51,16 @@ def make_workload(rank: int, n_utt: int):
         return list(ex.map(lambda u: synth_speech(n, SR, 20261017, rank * n_utt + u), range(n_utt)))
 
 
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
+    (profiles/r1_ncu_kernels.json, written by profiles/ncu_kernels.py); None if there is no capture."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_kernels.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p)).get(kernel)
+    return None if not d else d.get("dram_bytes")
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -145,6 +155,8 @@ def main():
     ap.add_argument("--utts", type=int, default=N_UTT, help="utterances per GPU per step (default: the C2 workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="one sub-batch (profiling: full-batch kernel launches)")
+    ap.add_argument("--pipeline", type=int, default=0, help="sub-batches for the resident timed region (0 = automatic)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -176,6 +188,7 @@ def main():
     stream = torch.cuda.Stream()
     eng = Engine(cfg, device=local)
     eng.set_stream(stream.cuda_stream)
+    eng.set_pipeline(1 if args.serial else args.pipeline)
     for i, p in enumerate(pcms):
         eng.submit(i, p, SR)
     eng.upload()
@@ -207,7 +220,7 @@ def main():
         st = eng.stage_times()
         stage_acc += np.array([st["spectrum"], st["peaks"], st["segment"], st["features"], st["total"]])
     stage_ms = stage_acc / min(args.steps, 5)
-    eng.set_pipeline(0)
+    eng.set_pipeline(1 if args.serial else 0)
     eng.download()
     eng.sync()
     tot = eng.counts()
@@ -286,7 +299,9 @@ def main():
                        "l2": "inputs (320 MB PCM + 819 MB spectrum rows per step) exceed the 126 MB L2; no flush needed"},
             "roofline": {"bound": "hbm", "kernel": {"spectrum": "fa_spectrum_2048_kernel", "peaks": "fa_peaks_kernel",
                                                     "segment": "fa_segment_kernel", "features": "fa_features_kernel"}[top],
-                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": ncu_traffic({"spectrum": "fa_fftmag_2048_kernel", "peaks": "fa_peaks_kernel",
+                                                 "segment": "fa_segment_kernel", "features": "fa_features_kernel"}[top]),
                          "peak_source": peak_src, "share_of_step": shares[top],
                          "note": "segment scan / features are latency bound (sequential state machine), spectrum is FP32-issue bound; see DESIGN.md"},
             "stages": stages,

@@ -145,7 +145,7 @@ FA_API const char* fa_last_error(const fa_handle* h);
 FA_API int fa_set_stream(fa_handle* h, void* cuda_stream);
 
 /* Number of sub-batches a run is split into (each on its own forked stream so that H2D, the kernels of different
- * sub-batches and the spectrum D2H overlap): 0 = automatic, 1 = serial (per-stage timings are only defined then). */
+ * sub-batches and the spectrum D2H overlap; at most 16): 0 = automatic, 1 = serial (per-stage timings are only defined then). */
 FA_API int fa_set_pipeline(fa_handle* h, int n_sub_batches);
 
 /* Caller-owned destination (ideally page-locked) for the dB spectrum rows of the whole batch, in submission order:

@@ -501,10 +501,12 @@ static int prepare(fa_handle* h) {
 }
 
 // split the batch into sub-batches of whole utterances with about equal frame counts
-static std::vector<SubBatch> plan(const fa_handle* h) {
+static std::vector<SubBatch> plan(const fa_handle* h, bool with_copies) {
   const int n = (int)h->utts.size();
   int S = h->pipeline;
-  if (S == 0) S = std::min(kMaxSub, std::max(1, n / 60));
+  // automatic: many sub-batches when PCIe copies have to overlap the kernels, few when the data is resident (every
+  // stage but K1a is a per-utterance latency chain, so extra sub-batches only add launches)
+  if (S == 0) S = with_copies ? std::min(kMaxSub, std::max(1, n / 60)) : std::min(4, std::max(1, n / 250));
   S = std::max(1, std::min(S, n));
   std::vector<SubBatch> out;
   const long long F = h->total_frames;
@@ -641,7 +643,7 @@ static int run_device(fa_handle* h, bool with_h2d, bool with_sink) {
   h->launches = 0;
   if (c.output_level >= 3) FA_CUDA(cudaMemsetAsync(h->d_counts.p, 0, sizeof(int) * 6 * (size_t)n, s));
   FA_CUDA(cudaEventRecord(h->ev[0], s));
-  const std::vector<SubBatch> subs = plan(h);
+  const std::vector<SubBatch> subs = plan(h, with_h2d || (with_sink && h->spec_sink));
   const bool sink = with_sink && h->spec_sink && h->want_spec;
   if (sink && (size_t)h->total_frames > h->spec_sink_rows) return fail(h, FA_ERR_CAPACITY, "spectrum sink too small");
   if (subs.size() <= 1) {
