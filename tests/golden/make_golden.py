@@ -69,9 +69,13 @@ def main():
             "kwargs": kw, "frames": int(fe["frames"].shape[0]), "max_band": int(fe["frames"].max()),
             "frames_sha": sha(fe["frames"]), "seg_ci": an.seg_ci, "syllables": len(an.syllables),
             "feature_rows": int(an.features.shape[0]), "features_sha": sha(an.features),
+            "formants_sha": sha(an.formants), "syllable_table": [(int(y["stored_seg"]), int(y["start"]), int(y["len"])) for y in an.syllables],
             "last_row_head": [float(x) for x in an.features[-1][:6]],
         }
     np.savez_compressed(os.path.join(HERE, "sample_excerpt.npz"), **out)
+    # the whole demo file (BASELINE config 1 input) as int16, so that the -m gpu tests can run C1 in full on the GPU
+    # box, where /root/reference does not exist
+    np.savez_compressed(os.path.join(HERE, "sample_full_pcm.npz"), pcm_i16=i16, sample_rate=np.int32(sr))
     json.dump(full, open(os.path.join(HERE, "sample_full.json"), "w"), indent=1)
 
     synth = {"cases": []}
