@@ -107,7 +107,7 @@ struct fa_handle {
   bool prepared = false;
   long long total_frames = 0;
   HostBuf h_pcm, h_meta, h_counts, h_off, h_segs, h_syls, h_formants, h_energy, h_features;
-  DevBuf d_pcm, d_meta, d_spec, d_frames, d_cand, d_ncand, d_gsum, d_counter;
+  DevBuf d_pcm, d_meta, d_spec, d_frames, d_cand, d_camp, d_cpl, d_cph, d_ncand, d_gsum, d_counter;
   DevBuf d_win, d_tw, d_tws, d_ws, d_bmi, d_bmw, d_emph;
   DevBuf d_trkbase, d_trk_i, d_trk_d, d_trk_slot, d_pt_i, d_pt_e, d_rows, d_rowlist;
   DevBuf d_segs, d_syls, d_formants, d_energy, d_features, d_counts, d_off;
@@ -281,7 +281,7 @@ int fa_destroy(fa_handle* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   for (int i = 0; i < kMaxSub; i++) if (h->sub_stream[i]) cudaStreamSynchronize(h->sub_stream[i]);
-  for (DevBuf* b : {&h->d_pcm, &h->d_meta, &h->d_spec, &h->d_frames, &h->d_cand, &h->d_ncand, &h->d_gsum, &h->d_counter,
+  for (DevBuf* b : {&h->d_pcm, &h->d_meta, &h->d_spec, &h->d_frames, &h->d_cand, &h->d_camp, &h->d_cpl, &h->d_cph, &h->d_ncand, &h->d_gsum, &h->d_counter,
                     &h->d_win, &h->d_tw, &h->d_tws, &h->d_ws, &h->d_bmi, &h->d_bmw, &h->d_emph, &h->d_trkbase, &h->d_trk_i,
                     &h->d_trk_d, &h->d_trk_slot, &h->d_pt_i, &h->d_pt_e, &h->d_rows, &h->d_rowlist, &h->d_segs, &h->d_syls,
                     &h->d_formants, &h->d_energy, &h->d_features, &h->d_counts, &h->d_off, &h->g_segs, &h->g_syls,
@@ -470,6 +470,9 @@ static int prepare(fa_handle* h) {
   FA_CUDA(h->d_counter.reserve(2 * kMaxSub * sizeof(int)));
   if (h->cfg.output_level >= 3) {
     FA_CUDA(h->d_cand.reserve(Fz * h->maxp * sizeof(uint32_t)));
+    FA_CUDA(h->d_camp.reserve(Fz * h->maxp * sizeof(uint32_t)));
+    FA_CUDA(h->d_cpl.reserve(Fz * h->maxp * sizeof(unsigned long long)));
+    FA_CUDA(h->d_cph.reserve(Fz * h->maxp * sizeof(unsigned long long)));
     FA_CUDA(h->d_ncand.reserve(Fz * sizeof(int)));
     FA_CUDA(h->d_gsum.reserve(Fz * sizeof(double)));
     const size_t T = (size_t)std::max<long long>(tb, 1);
@@ -583,6 +586,7 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
   if (c.output_level >= 3 && sb.r1 > sb.r0) {
     FaPeaksParams pp;
     pp.frames = h->d_frames.as<uint32_t>(); pp.B = h->B; pp.maxp = h->maxp; pp.n_frames = sb.r1 - sb.r0; pp.row_begin = sb.r0;
+    pp.camp = h->d_camp.as<uint32_t>(); pp.cpl = h->d_cpl.as<unsigned long long>(); pp.cph = h->d_cph.as<unsigned long long>();
     pp.cand = h->d_cand.as<uint32_t>(); pp.ncand = h->d_ncand.as<int>(); pp.gsum = h->d_gsum.as<double>();
     FA_CUDA(fa_launch_peaks(pp, s, &h->launches));
     if (getenv("FA_DEBUG_SYNC")) FA_CUDA(cudaStreamSynchronize(s));
@@ -594,7 +598,8 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
     const size_t R = (size_t)std::max<long long>(F, 1) + n;
     FaSegmentParams g;
     memset(&g, 0, sizeof(g));
-    g.frames = h->d_frames.as<uint32_t>(); g.cand = h->d_cand.as<uint32_t>(); g.ncand = h->d_ncand.as<int>();
+    g.cand = h->d_cand.as<uint32_t>(); g.camp = h->d_camp.as<uint32_t>(); g.cpl = h->d_cpl.as<unsigned long long>();
+    g.cph = h->d_cph.as<unsigned long long>(); g.ncand = h->d_ncand.as<int>();
     g.gsum = h->d_gsum.as<double>(); g.frame_off = meta + 2 * n; g.n_utt = n; g.B = h->B; g.maxp = h->maxp;
     g.utt_begin = sb.u0; g.utt_count = sb.u1 - sb.u0;
     g.level = c.output_level;

@@ -52,14 +52,19 @@ struct FaPeaksParams {
   long long n_frames;            // frames of the sub-batch
   long long row_begin;
   uint32_t* cand;                // [F_total][maxp] packed lo | hi<<8 | pk<<16 | last<<24
+  uint32_t* camp;                // [F_total][maxp] e[pk]
+  unsigned long long* cpl;       // [F_total][maxp] P[lo - 1]  (P = inclusive prefix sums of the frame, exact)
+  unsigned long long* cph;       // [F_total][maxp] P[hi]
   int* ncand;                    // [F_total]
   double* gsum;                  // [F_total] sum e[1..B-1]
 };
 
 // per-utterance scan state that survives across time chunks (reserved for the stream stitcher)
 struct FaSegmentParams {
-  const uint32_t* frames;
   const uint32_t* cand;
+  const uint32_t* camp;
+  const unsigned long long* cpl;
+  const unsigned long long* cph;
   const int* ncand;
   const double* gsum;
   const long long* frame_off;    // [n_utt + 1]

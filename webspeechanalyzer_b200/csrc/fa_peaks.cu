@@ -30,32 +30,58 @@ __global__ void __launch_bounds__(kPeakThreads) fa_peaks_kernel(const FaPeaksPar
   const int B = p.B;
   const uint32_t* __restrict__ e = p.frames + (size_t)f * B;
   uint32_t* out = p.cand + (size_t)f * p.maxp;
+  uint32_t* out_amp = p.camp + (size_t)f * p.maxp;
+  unsigned long long* out_pl = p.cpl + (size_t)f * p.maxp;
+  unsigned long long* out_ph = p.cph + (size_t)f * p.maxp;
   int n = 0, lo = 0, pk = 0, hi = 0, flat = 0, dir = 0;
   unsigned long long g = 0;
   uint32_t epk = 0;  // e[pk]
+  // exact prefix sums P[b] = e[0] + .. + e[b] at the raw bounds: pl = P[lo - 1], ph = P[hi] (K3 gets the
+  // bandwidth energy of accumulate_fm @B35952 as ph - pl without touching the frame again)
+  unsigned long long pre = 0, pl = 0, ph = 0;
 
   auto emit = [&](int last) {
     int l2 = lo, h2 = hi;
     // e[i] < e[pk]/10 in doubles  <=>  10*e[i] < e[pk] in integers (both exact)
     const unsigned long long top = epk;
-    while (l2 < pk && 10ull * __ldg(e + l2) < top) l2++;
-    while (h2 > pk && 10ull * __ldg(e + h2) < top) h2--;
-    if (n < p.maxp) out[n] = (uint32_t)l2 | ((uint32_t)h2 << 8) | ((uint32_t)pk << 16) | ((uint32_t)last << 24);
+    unsigned long long pl2 = pl, ph2 = ph;
+    for (;;) {
+      if (l2 >= pk) break;
+      const uint32_t x = __ldg(e + l2);
+      if (!(10ull * x < top)) break;
+      pl2 += x;
+      l2++;
+    }
+    for (;;) {
+      if (h2 <= pk) break;
+      const uint32_t x = __ldg(e + h2);
+      if (!(10ull * x < top)) break;
+      ph2 -= x;
+      h2--;
+    }
+    if (n < p.maxp) {
+      out[n] = (uint32_t)l2 | ((uint32_t)h2 << 8) | ((uint32_t)pk << 16) | ((uint32_t)last << 24);
+      out_amp[n] = epk;
+      out_pl[n] = pl2;
+      out_ph[n] = ph2;
+    }
     n++;
   };
   auto step = [&](const int a, const uint32_t ea, const uint32_t e1, const uint32_t e2, const uint32_t e3) {
     g += ea;
+    // here pre == P[a - 1]
     const bool rise = ea > e1 && (a < 2 || ea > e2) && (a < 3 || ea > e3);
     const bool fall = ea < e1 && (a < 2 || ea < e2) && (a < 3 || ea < e3);
     if (rise) {
       if (dir != 1) {
         if (dir == -1 && lo <= pk && pk < hi) emit(0);
         lo = a - 1;
+        pl = pre - e1;
       }
       pk = a; epk = ea;
       dir = 1;
     } else if (fall) {
-      if (dir != 0) { hi = a; dir = -1; }
+      if (dir != 0) { hi = a; ph = pre + ea; dir = -1; }
     } else if (dir == -1) {
       if (++flat > 2) {
         flat = 0;
@@ -67,8 +93,10 @@ __global__ void __launch_bounds__(kPeakThreads) fa_peaks_kernel(const FaPeaksPar
     }
     if (a == B - 1 && dir == 1) {
       hi = a; pk = a; epk = ea;
+      ph = pre + ea;
       if (lo < pk && pk <= hi) emit(1);
     }
+    pre += ea;
   };
 
   uint32_t e1 = 0, e2 = 0, e3 = 0;  // e[a-1], e[a-2], e[a-3]
@@ -77,7 +105,7 @@ __global__ void __launch_bounds__(kPeakThreads) fa_peaks_kernel(const FaPeaksPar
     for (int q = 0; q < B / 4; q++) {
       const uint4 x = __ldg(e4 + q);
       const int a = 4 * q;
-      if (q) step(a, x.x, e1, e2, e3);
+      if (q) step(a, x.x, e1, e2, e3); else pre = x.x;
       step(a + 1, x.y, x.x, e1, e2);
       step(a + 2, x.z, x.y, x.x, e1);
       step(a + 3, x.w, x.z, x.y, x.x);
@@ -85,6 +113,7 @@ __global__ void __launch_bounds__(kPeakThreads) fa_peaks_kernel(const FaPeaksPar
     }
   } else {
     e1 = __ldg(e);
+    pre = e1;
     for (int a = 1; a < B; a++) {
       const uint32_t ea = __ldg(e + a);
       step(a, ea, e1, e2, e3);

@@ -9,13 +9,26 @@
 //   get_ranked_formants / straighten_formants             @B35670, @B35074
 //   sep_syllables                                         @B34757
 // The state machine is strictly sequential in time (the threshold v of frame t depends on frame
-// t-1), so the time loop is serial and the 32 lanes parallelise what is parallel inside a frame:
-// candidate filtering, track x peak scoring (lane per live track, warp arg-max per peak), the
-// bandwidth energy sums, and at finalisation the ranking (count-smaller sort), the per-row
-// application of track points (lane per frame row) and the syllable bit scan.
-// All decisions are integer compares or IEEE double arithmetic without contraction
-// (--fmad=false) and the V8-equivalent log10/pow of include/fa_jsmath.h, so boundaries are
-// bit-exact against oracle/fa_oracle.c.
+// t-1), so the time loop is serial and the kernel is LATENCY bound: with ~2 warps per scheduler what
+// matters is the dependent instruction chain per frame and -- measured with ncu -- the size of the
+// hot loop (instruction-fetch stalls were 29 % of the issue slots of an unrolled variant).  Hence:
+//   * K2 hands over, per candidate peak, its amplitude e[pk] and the exact prefix sums P[lo-1],
+//     P[hi] of the frame, so this kernel never touches the uint32 frame: the bandwidth energy of a
+//     (merged) peak is max(P[hi]) - min(P[lo-1]);
+//   * candidates live one per lane; the gate filter and the (n, d, h, p) statistics are single
+//     redux.sync / ballot instructions;
+//   * live tracks sit in shared memory in fixed slots, lane per slot, 32 slots per pass (one pass
+//     covers the usual <= 32 live tracks); expired tracks free their slot, new tracks take free slots,
+//     no compaction.  Track order only matters for score ties (the reference keeps the earlier
+//     track: strict '>' @B35952), which the creation index resolves;
+//   * ownership of a peak = shared-memory atomicMax on the score bits, then atomicMin on the creation
+//     index among the exact ties;
+//   * every track update is written through to the track table / point pool in HBM (fire and forget),
+//     so finalisation needs no flush;
+//   * one compact code path (run-time loops over the slot passes, nothing unrolled four-fold).
+// All decisions are integer compares or IEEE double arithmetic without contraction (--fmad=false)
+// and the V8-equivalent log10/pow of include/fa_jsmath.h, so boundaries are bit-exact against
+// oracle/fa_oracle.c.
 //
 // This kernel moves kilobytes per utterance; it is latency bound, not HBM bound.
 #include <cstdlib>
@@ -25,34 +38,37 @@
 
 namespace {
 
-constexpr int kWarps = 2;   // 47 KB of shared memory per CTA: fits beside two K1a CTAs, so sub-batches overlap
+constexpr int kWarps = 2;
 constexpr int ACAP = 128;  // live-track slots per utterance (tracks with lastFrame >= c_ci - 3)
 constexpr int PCAP = 136;  // accepted peaks per frame (>= maxp = B/2 + 4)
+constexpr int CMAX = 9;    // a +-8 bin window holds at most 9 peaks (they are >= 2 bins apart)
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int BIG = 0x7fffffff;
 
-constexpr int CMAX = 10;   // candidate peaks per live track: a +-8 bin window holds <= 9 peaks (>= 2 bins apart)
-
 struct WarpShared {
-  uint32_t e[FA_MAX_BANDS];
-  unsigned long long P[FA_MAX_BANDS];      // inclusive prefix sums of e (exact)
-  uint32_t pmask[FA_MAX_BANDS / 32 + 1];   // bit b: an accepted peak has pk == b
-  unsigned char pidx[FA_MAX_BANDS];        // its index in the accepted list
-  unsigned char plo[PCAP], phi[PCAP], ppk[PCAP];
-  int owner[PCAP];
-  unsigned long long bestbits[PCAP];       // best score per peak (bit pattern of a positive double)
-  int a_id[ACAP], a_last_frame[ACAP], a_last_bin[ACAP], a_npts[ACAP], a_b2[ACAP], a_b3[ACAP];
-  uint32_t a_last_amp[ACAP];
-  double a_vel[ACAP], a_sum_e[ACAP], a_sum_eb[ACAP];
-  double cand_sc[CMAX][ACAP];              // [k][slot]: lane-consecutive slots -> conflict free
-  unsigned char cand_o[CMAX][ACAP];
-  unsigned char cand_n[ACAP];              // candidates of the slot this frame
+  // accepted peaks of the frame
+  ulonglong2 plh[PCAP];                       // P[lo-1], P[hi]
+  uint2 pa[PCAP];                             // packed lo | hi<<8 | pk<<16 | last<<24, amplitude e[pk]
+  unsigned long long best[PCAP];              // best score per peak (bit pattern of a positive double)
+  int owner[PCAP];                            // creation index of the owning track, BIG = none
+  uint32_t pmask[FA_MAX_BANDS / 32 + 1];      // bit b: an accepted peak has pk == b
+  unsigned char pidx[FA_MAX_BANDS];           // its index in the accepted list
+  unsigned char newlist[PCAP];                // un-owned peaks above the gate, in peak order
+  // live tracks of the current segment (field list of l[r] @B35952)
+  int t_id[ACAP];                             // creation index inside the segment, -1 = free slot
+  int t_lf[ACAP];                             // lastFrame
+  int t_bins[ACAP];                           // last three peak bins: b1 | b2 << 8 | b3 << 16
+  int t_np[ACAP];                             // points so far
+  uint32_t t_amp[ACAP];                       // lastAmp
+  uint32_t t_wm[ACAP];                        // this frame: retained candidates (bit j = bin wlo + j)
+  double t_vel[ACAP], t_se[ACAP], t_seb[ACAP];
+  unsigned long long cs[CMAX][ACAP];          // [j][slot]: score of the slot's j-th retained candidate
 };
 
 struct ScanState {
   int current_frame, no_fm_segs, c_ci, c_started, w, k;
   double y, v, x, v0, T, s_energy, c_energy;
-  int n_tr, n_act, n_pts;
+  int n_tr, n_pts, n_slots;   // n_slots: high-water mark of used track slots (multiple passes of 32 beyond 32)
   int n_segs, n_stored, n_rows, n_syls;
   int overflow;
 };
@@ -65,20 +81,12 @@ struct Bases {
   int F, tcap;
 };
 
-__device__ __forceinline__ int warp_min_i(int v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
-  return v;
-}
-__device__ __forceinline__ int warp_max_i(int v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
-  return v;
-}
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-  return v;
+  // exact: four 16-bit digit sums (each < 2^21) recombined
+  const unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+  const unsigned long long s0 = __reduce_add_sync(FULL, lo & 0xffffu), s1 = __reduce_add_sync(FULL, lo >> 16);
+  const unsigned long long s2 = __reduce_add_sync(FULL, hi & 0xffffu), s3 = __reduce_add_sync(FULL, hi >> 16);
+  return s0 + (s1 << 16) + (s2 << 32) + (s3 << 48);
 }
 
 // _() @B37340
@@ -97,23 +105,27 @@ __device__ __forceinline__ double fm_score(int gap, double dist, int count, int 
   if (t < 0) return 0;
   if (t < 1) t = 1;
   const int i = count > 10 ? 10 : count;
-  return 10.0 / (double)gap * (t * t + (double)i * s);
+  // 10 / gap for gap in {1, 2, 3}: the correctly rounded quotients
+  const double f = gap == 1 ? 10.0 : gap == 2 ? 5.0 : 10.0 / 3.0;
+  return f * (t * t + (double)i * s);
 }
 
 // L() @B25649 (+ clear_fm @B35919)
-__device__ __forceinline__ void seg_reset(ScanState& st, int started) {
+__device__ __forceinline__ void seg_reset(ScanState& st, WarpShared& S, int started, const int lane) {
   st.c_ci = 0;
   st.c_started = started;
   st.no_fm_segs = 0;
   st.n_tr = 0;
-  st.n_act = 0;
   st.n_pts = 0;
   st.s_energy = 0.0;
   st.c_energy = 0.0;
+  for (int r = lane; r < st.n_slots; r += 32) S.t_id[r] = -1;
+  st.n_slots = 0;
+  __syncwarp();
 }
 
 // C() @B28506
-__device__ __noinline__ void noise_gate(ScanState& st, double e) {
+__device__ __forceinline__ void noise_gate(ScanState& st, WarpShared& S, double e, const int lane) {
   st.w++;
   if (e > st.y || (st.w > 40 && e > 2 * st.v)) {
     if (e >= st.y) { st.w = 0; st.x = st.y = e; }
@@ -126,7 +138,7 @@ __device__ __noinline__ void noise_gate(ScanState& st, double e) {
     else if (t > 1) st.v = fa_js_parse_int(st.y / 10);
     else st.v = 1;
     st.v0 = st.v;
-    if (st.k > 0 && st.T / (double)st.k < 30 * st.v) { seg_reset(st, 0); st.k = 0; st.T = 0; }
+    if (st.k > 0 && st.T / (double)st.k < 30 * st.v) { seg_reset(st, S, 0, lane); st.k = 0; st.T = 0; }
     st.T += st.y;
     st.k += 1;
   } else if (st.v > 10 && st.v > st.v0 / 10 && st.w > 20) {
@@ -136,161 +148,128 @@ __device__ __noinline__ void noise_gate(ScanState& st, double e) {
 }
 
 // accumulate_fm @B35952
-__device__ __noinline__ void accumulate_fm(const FaSegmentParams& p, WarpShared& S, ScanState& st, const Bases& bs,
-                                           const int n_peaks, const int n_label, const double g, const double vmin,
-                                           const int lane) {
+__device__ __forceinline__ void accumulate_fm(const FaSegmentParams& p, WarpShared& S, ScanState& st, const Bases& bs,
+                                              const int n_peaks, const int n_label, const double g, const double vmin,
+                                              const int lane) {
   if (n_peaks < 1) return;
   st.s_energy += g;
-  // drop tracks that can no longer match (gap >= 4); the reference keeps them but never touches them again
-  {
-    int n_new = 0;
-    for (int r0 = 0; r0 < st.n_act; r0 += 32) {
-      const int r = r0 + lane;
-      const bool valid = r < st.n_act;
-      int id = 0, lf = 0, lb = 0, np = 0, b2 = 0, b3 = 0;
-      uint32_t la = 0;
-      double vel = 0, se = 0, seb = 0;
-      if (valid) {
-        id = S.a_id[r]; lf = S.a_last_frame[r]; lb = S.a_last_bin[r]; np = S.a_npts[r]; b2 = S.a_b2[r];
-        b3 = S.a_b3[r]; la = S.a_last_amp[r]; vel = S.a_vel[r]; se = S.a_sum_e[r]; seb = S.a_sum_eb[r];
-      }
-      const bool keep = valid && (n_label - lf < 4);
-      if (valid && !keep) {
-        p.trk_count[bs.tb + id] = np;
-        p.trk_sum_e[bs.tb + id] = se;
-        p.trk_sum_eb[bs.tb + id] = seb;
-      }
-      const unsigned m = __ballot_sync(FULL, keep);
-      __syncwarp();
-      if (keep) {
-        const int d = n_new + __popc(m & ((1u << lane) - 1));
-        S.a_id[d] = id; S.a_last_frame[d] = lf; S.a_last_bin[d] = lb; S.a_npts[d] = np; S.a_b2[d] = b2;
-        S.a_b3[d] = b3; S.a_last_amp[d] = la; S.a_vel[d] = vel; S.a_sum_e[d] = se; S.a_sum_eb[d] = seb;
-      }
-      n_new += __popc(m);
-      __syncwarp();
-    }
-    st.n_act = n_new;
-  }
-  // per-frame tables: peak bitmask + index, exact prefix sums of the frame
+  const unsigned lt = (1u << lane) - 1u;
   const int B = p.B;
-  {
-    const int nw = (B + 31) >> 5;
-    if (lane <= nw) S.pmask[lane] = 0u;
-    const int C = (B + 31) >> 5;            // bins per lane
-    const int b0 = lane * C, b1 = min(b0 + C, B);
-    unsigned long long loc = 0;
-    for (int b = b0; b < b1; b++) loc += S.e[b];
-    unsigned long long incl = loc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long t = __shfl_up_sync(FULL, incl, o);
-      if (lane >= o) incl += t;
-    }
-    unsigned long long run = incl - loc;
-    for (int b = b0; b < b1; b++) { run += S.e[b]; S.P[b] = run; }
-    __syncwarp();
-    for (int o = lane; o < n_peaks; o += 32) {
-      const int pk = S.ppk[o];
-      atomicOr(&S.pmask[pk >> 5], 1u << (pk & 31));
-      S.pidx[pk] = (unsigned char)o;
-      S.owner[o] = BIG;
-      S.bestbits[o] = 0ull;
-    }
-    __syncwarp();
-  }
-  // (1) score every (live track, peak within its window): lane per track.  best[o] = max score via
-  //     shared-memory atomicMax on the bit pattern; ties go to the earlier track via atomicMin on the slot.
-  // (live tracks: 17 on average, rarely more than 40 -> usually one pass of 32 lanes)
-  const int n_pass = (st.n_act + 31) >> 5;
-  bool ovf = false;
-  for (int ps = 0; ps < n_pass; ps++) {
-    const int r = ps * 32 + lane;
-    if (r < st.n_act) {
-      int cnt = 0;
-      const int gap = n_label - S.a_last_frame[r];
-      if (gap >= 0 && gap < 4) {
-        const int lb = S.a_last_bin[r];
+  const int n_slots = st.n_slots;
+  // (1) lane per track slot: expire, window of candidate peaks, scores, arg-max per peak (atomicMax on the bits)
+  bool bad = false;
+  for (int r0 = 0; r0 < n_slots; r0 += 32) {
+    const int r = r0 + lane;
+    const int id = S.t_id[r];
+    const int gap = n_label - S.t_lf[r];
+    unsigned kept = 0u;
+    if (id >= 0) {
+      if (gap >= 4) S.t_id[r] = -1;  // can never match again (the reference keeps it but never touches it)
+      else if (gap >= 0) {
+        const int lb = S.t_bins[r] & 255;
         const int lim = gap == 0 ? 3 : gap == 1 ? 4 : gap == 2 ? 6 : 9;  // DIST @B32325
         const int wlo = max(lb - lim + 1, 0), whi = min(lb + lim - 1, B - 1);
         const int word = wlo >> 5, sh = wlo & 31;
         const unsigned long long two = (unsigned long long)S.pmask[word] | ((unsigned long long)S.pmask[word + 1] << 32);
         unsigned bits = (unsigned)(two >> sh) & ((2u << (whi - wlo)) - 1u);
-        const double amp_old = (double)S.a_last_amp[r], vel = S.a_vel[r];
-        const int np = S.a_npts[r];
-        while (bits) {
-          const int j = __ffs(bits) - 1;
-          bits &= bits - 1;
-          const int bin = wlo + j;
-          const double sc = fm_score(gap, (double)abs(lb - bin), np, lb, bin, amp_old, (double)S.e[bin], vel);
-          if (sc > 1) {
+        if (bits) {
+          const double amp_old = (double)S.t_amp[r], vel = S.t_vel[r];
+          const int np = S.t_np[r];
+          int j = 0;
+          do {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int bin = wlo + b;
             const int o = S.pidx[bin];
-            if (cnt < CMAX) {
-              S.cand_sc[cnt][r] = sc;
-              S.cand_o[cnt][r] = (unsigned char)o;
+            const double sc = fm_score(gap, (double)abs(lb - bin), np, lb, bin, amp_old, (double)S.pa[o].y, vel);
+            if (sc > 1) {
+              const unsigned long long sb = (unsigned long long)__double_as_longlong(sc);
+              if (j < CMAX) S.cs[j][r] = sb;
+              j++;
+              kept |= 1u << b;
+              atomicMax(&S.best[o], sb);
             }
-            cnt++;
-            atomicMax(&S.bestbits[o], (unsigned long long)__double_as_longlong(sc));
+          } while (bits);
+          bad |= j > CMAX;
+        }
+      }
+    }
+    S.t_wm[r] = kept;
+  }
+  if (__any_sync(FULL, bad)) { st.overflow = 1; return; }
+  __syncwarp();
+  // exact ties go to the earlier track
+  for (int r0 = 0; r0 < n_slots; r0 += 32) {
+    const int r = r0 + lane;
+    unsigned bits = S.t_wm[r];
+    if (bits) {
+      const int id = S.t_id[r];
+      const int gap = n_label - S.t_lf[r];
+      const int lb = S.t_bins[r] & 255;
+      const int lim = gap == 0 ? 3 : gap == 1 ? 4 : gap == 2 ? 6 : 9;
+      const int wlo = max(lb - lim + 1, 0);
+      int j = 0;
+      do {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int o = S.pidx[wlo + b];
+        if (S.cs[j][r] == S.best[o]) atomicMin(&S.owner[o], id);
+        j++;
+      } while (bits);
+    }
+  }
+  __syncwarp();
+  // (2) every owning track absorbs its (merged) peaks
+  unsigned long long moved = 0;
+  for (int r0 = 0; r0 < n_slots; r0 += 32) {
+    const int r = r0 + lane;
+    unsigned bits = S.t_wm[r];
+    uint32_t amp0 = 0, bamp = 0;
+    int ob = 0, lo_b = 0, hi_b = 0, id = -1, tb = 0;
+    unsigned long long pl = 0, ph = 0;
+    if (bits) {
+      id = S.t_id[r];
+      tb = S.t_bins[r];
+      const int gap = n_label - S.t_lf[r];
+      const int lb = tb & 255;
+      const int lim = gap == 0 ? 3 : gap == 1 ? 4 : gap == 2 ? 6 : 9;
+      const int wlo = max(lb - lim + 1, 0);
+      do {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int bin = wlo + b;
+        const int o = S.pidx[bin];
+        if (S.owner[o] == id) {
+          const uint2 pa = S.pa[o];
+          const ulonglong2 e2 = S.plh[o];
+          const int l_b = pa.x & 0xff, h_b = (pa.x >> 8) & 0xff;
+          if (amp0 == 0u) { amp0 = pa.y; bamp = pa.y; ob = bin; pl = e2.x; ph = e2.y; lo_b = l_b; hi_b = h_b; }
+          else {
+            pl = e2.x < pl ? e2.x : pl; ph = e2.y > ph ? e2.y : ph; lo_b = min(lo_b, l_b); hi_b = max(hi_b, h_b);
+            if (pa.y > bamp) { bamp = pa.y; ob = bin; }
           }
         }
-      }
-      ovf |= cnt > CMAX;
-      S.cand_n[r] = (unsigned char)(cnt > CMAX ? CMAX : cnt);
+      } while (bits);
     }
-  }
-  if (__any_sync(FULL, ovf)) { st.overflow = 1; return; }
-  __syncwarp();
-  for (int ps = 0; ps < n_pass; ps++) {
-    const int r = ps * 32 + lane;
-    const int cnt = r < st.n_act ? S.cand_n[r] : 0;
-    for (int k = 0; k < cnt; k++) {
-      const int o = S.cand_o[k][r];
-      if ((unsigned long long)__double_as_longlong(S.cand_sc[k][r]) == S.bestbits[o]) atomicMin(&S.owner[o], r);
-    }
-  }
-  __syncwarp();
-  // (2) every owning track absorbs its (merged) peaks: lane per track, its owned peaks are among its candidates
-  unsigned long long moved = 0;
-  for (int ps = 0; ps < n_pass; ps++) {
-    const int r = ps * 32 + lane;
-    int first = -1, lo = 0, hi = 0, o_bin = 0;
-    uint32_t bamp = 0;
-    const int my_cnt = r < st.n_act ? S.cand_n[r] : 0;
-    for (int k = 0; k < my_cnt; k++) {
-      const int o = S.cand_o[k][r];
-      if (S.owner[o] == r) {
-        const int pk = S.ppk[o];
-        const uint32_t a = S.e[pk];
-        if (first < 0) { first = o; lo = S.plo[o]; hi = S.phi[o]; o_bin = pk; bamp = a; }
-        else {
-          lo = min(lo, (int)S.plo[o]);
-          hi = max(hi, (int)S.phi[o]);
-          if (a > bamp) { bamp = a; o_bin = pk; }
-        }
-      }
-    }
-    bool upd = false;
-    uint32_t amp0 = 0;
-    if (first >= 0) {
-      amp0 = S.e[S.ppk[first]];
-      upd = (double)amp0 > vmin;
-    }
+    const bool upd = amp0 != 0u && (double)amp0 > vmin;
     const unsigned um = __ballot_sync(FULL, upd);
     if (upd) {
-      const unsigned long long Ei = S.P[hi] - (lo > 0 ? S.P[lo - 1] : 0ull);
+      const unsigned long long Ei = ph - pl;
       const double E = (double)Ei;
       moved += Ei;
-      const int h = S.a_npts[r];
-      const int b1 = S.a_last_bin[r], b2 = S.a_b2[r], b3 = S.a_b3[r];
-      double vel = S.a_vel[r];
-      if (h >= 3) vel = (double)(o_bin - b1 + (b2 - b1) + (b3 - b2)) / 3;
-      else if (h == 2) vel = (double)(o_bin - b1 + (b2 - b1)) / 2;
-      else if (h == 1) vel = (double)(o_bin - b1);
-      S.a_vel[r] = vel; S.a_last_frame[r] = n_label; S.a_b3[r] = b2; S.a_b2[r] = b1; S.a_last_bin[r] = o_bin;
-      S.a_last_amp[r] = amp0; S.a_npts[r] = h + 1; S.a_sum_e[r] += E; S.a_sum_eb[r] += E * (double)o_bin;
-      const long long q = bs.pb + st.n_pts + __popc(um & ((1u << lane) - 1));
-      p.pt_track[q] = S.a_id[r]; p.pt_ord[q] = h; p.pt_frame[q] = n_label;
-      p.pt_binspan[q] = o_bin | ((hi - lo + 1) << 16); p.pt_e[q] = E;
+      const int h = S.t_np[r];
+      const int b1 = tb & 255, b2 = (tb >> 8) & 255, b3 = (tb >> 16) & 255;
+      if (h >= 3) S.t_vel[r] = (double)(ob - b1 + (b2 - b1) + (b3 - b2)) / 3;
+      else if (h == 2) S.t_vel[r] = (double)(ob - b1 + (b2 - b1)) / 2;
+      else if (h == 1) S.t_vel[r] = (double)(ob - b1);
+      const double se = S.t_se[r] + E, seb = S.t_seb[r] + E * (double)ob;
+      S.t_lf[r] = n_label; S.t_bins[r] = ob | (b1 << 8) | (b2 << 16); S.t_amp[r] = amp0; S.t_np[r] = h + 1;
+      S.t_se[r] = se; S.t_seb[r] = seb;
+      const long long q = bs.pb + st.n_pts + __popc(um & lt);
+      p.pt_track[q] = id; p.pt_ord[q] = h; p.pt_frame[q] = n_label;
+      p.pt_binspan[q] = ob | ((hi_b - lo_b + 1) << 16); p.pt_e[q] = E;
+      const long long ti = bs.tb + id;
+      p.trk_count[ti] = h + 1; p.trk_sum_e[ti] = se; p.trk_sum_eb[ti] = seb;
     }
     st.n_pts += __popc(um);
   }
@@ -299,51 +278,59 @@ __device__ __noinline__ void accumulate_fm(const FaSegmentParams& p, WarpShared&
     st.s_energy -= mv;
     st.c_energy += mv;
   }
-  __syncwarp();
-  // (3) un-owned peaks above the gate start new tracks, in peak order
+  // (3) un-owned peaks above the gate start new tracks, in peak order, in free slots
+  int nn = 0;
   for (int o0 = 0; o0 < n_peaks; o0 += 32) {
     const int o = o0 + lane;
-    const bool valid = o < n_peaks;
-    const int pk = valid ? S.ppk[o] : 0;
-    const uint32_t amp = valid ? S.e[pk] : 0;
-    const bool mk = valid && S.owner[o] == BIG && (double)amp > vmin;
-    const unsigned m = __ballot_sync(FULL, mk);
-    const int cnt = __popc(m);
-    if (st.n_act + cnt > ACAP || st.n_tr + cnt > bs.tcap) { st.overflow = 1; return; }
-    if (mk) {
-      const int pos = __popc(m & ((1u << lane) - 1));
-      const int slot = st.n_act + pos, id = st.n_tr + pos;
-      const int lo = S.plo[o], hi = S.phi[o];
-      const double E = (double)(S.P[hi] - (lo > 0 ? S.P[lo - 1] : 0ull));
-      S.a_id[slot] = id; S.a_last_frame[slot] = n_label; S.a_last_bin[slot] = pk; S.a_last_amp[slot] = amp;
-      S.a_vel[slot] = 0; S.a_npts[slot] = 1; S.a_b2[slot] = 0; S.a_b3[slot] = 0; S.a_sum_e[slot] = E;
-      S.a_sum_eb[slot] = E * (double)pk;
-      const long long q = bs.pb + st.n_pts + pos;
-      p.pt_track[q] = id; p.pt_ord[q] = 0; p.pt_frame[q] = n_label; p.pt_binspan[q] = pk | ((hi - lo + 1) << 16);
-      p.pt_e[q] = E;
-    }
-    st.n_act += cnt;
-    st.n_tr += cnt;
-    st.n_pts += cnt;
+    const bool mk = o < n_peaks && S.owner[o] == BIG && (double)S.pa[o].y > vmin;
+    const unsigned nm = __ballot_sync(FULL, mk);
+    if (mk) S.newlist[nn + __popc(nm & lt)] = (unsigned char)o;
+    nn += __popc(nm);
   }
-  __syncwarp();
+  if (nn > 0) {
+    if (st.n_tr + nn > bs.tcap) { st.overflow = 1; return; }
+    __syncwarp();
+    int taken = 0, hw = n_slots;
+    for (int r0 = 0; r0 < ACAP && taken < nn; r0 += 32) {
+      const int r = r0 + lane;
+      const bool fr = r >= n_slots || S.t_id[r] < 0;
+      const unsigned fm = __ballot_sync(FULL, fr);
+      const int i = taken + __popc(fm & lt);
+      if (fr && i < nn) {
+        const int o = S.newlist[i];
+        const uint2 pa = S.pa[o];
+        const ulonglong2 e2 = S.plh[o];
+        const int pk = (pa.x >> 16) & 0xff;
+        const double E = (double)(e2.y - e2.x);
+        const int id = st.n_tr + i;
+        S.t_id[r] = id; S.t_lf[r] = n_label; S.t_bins[r] = pk; S.t_amp[r] = pa.y; S.t_vel[r] = 0; S.t_np[r] = 1;
+        S.t_se[r] = E; S.t_seb[r] = E * (double)pk; S.t_wm[r] = 0u;
+        const long long q = bs.pb + st.n_pts + i;
+        p.pt_track[q] = id; p.pt_ord[q] = 0; p.pt_frame[q] = n_label;
+        p.pt_binspan[q] = pk | (((int)((pa.x >> 8) & 0xff) - (int)(pa.x & 0xff) + 1) << 16); p.pt_e[q] = E;
+        const long long ti = bs.tb + id;
+        p.trk_count[ti] = 1; p.trk_sum_e[ti] = E; p.trk_sum_eb[ti] = E * (double)pk;
+      }
+      // new high-water mark: one past the last slot taken in this pass
+      const unsigned took = __ballot_sync(FULL, fr && i < nn);
+      if (took) hw = max(hw, r0 + 32 - __clz(took));
+      taken += __popc(fm);
+    }
+    if (taken < nn) { st.overflow = 1; return; }
+    st.n_slots = hw;
+    st.n_tr += nn;
+    st.n_pts += nn;
+  }
 }
 
 // O() @B27088.  Returns 1 stored, 0 ignored, -1 rejected (where the JS throws inside straighten_formants).
-__device__ __noinline__ int finalize_segment(const FaSegmentParams& p, WarpShared& S, ScanState& st, const Bases& bs,
-                                             const int n_arg, const int lane) {
+__device__ __noinline__ int finalize_segment(const FaSegmentParams p, ScanState& st, const Bases bs, const int n_arg,
+                                             const int lane) {
   const int len = n_arg - st.no_fm_segs;
   if (!(len > p.seg_min_frames && st.c_started >= 2)) return 0;
   const int start = st.current_frame - len;
   const double vmin = st.v;
-  // flush live tracks
-  for (int r = lane; r < st.n_act; r += 32) {
-    const int id = S.a_id[r];
-    p.trk_count[bs.tb + id] = S.a_npts[r];
-    p.trk_sum_e[bs.tb + id] = S.a_sum_e[r];
-    p.trk_sum_eb[bs.tb + id] = S.a_sum_eb[r];
-  }
-  __syncwarp();
+  __syncwarp();  // the track table is written through at every update (by whichever lane owns the track)
   const int T = st.n_tr;
   // get_ranked_formants @B35670: count >= 2, mean >= 7, stable ascending by mean
   int nr = 0;
@@ -520,6 +507,15 @@ __device__ __noinline__ int finalize_segment(const FaSegmentParams& p, WarpShare
   return 1;
 }
 
+// finalisation works on a copy so that the scan state itself stays in registers (the call is out of line)
+__device__ __forceinline__ int finalize_copy(const FaSegmentParams& p, ScanState& st, const Bases& bs, const int n_arg,
+                                             const int lane) {
+  ScanState cp = st;
+  const int r = finalize_segment(p, cp, bs, n_arg, lane);
+  st.n_segs = cp.n_segs; st.n_stored = cp.n_stored; st.n_rows = cp.n_rows; st.n_syls = cp.n_syls;
+  return r;
+}
+
 __global__ void __launch_bounds__(128) fa_segment_kernel(const FaSegmentParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpShared* sh = reinterpret_cast<WarpShared*>(smem_raw);
@@ -535,43 +531,41 @@ __global__ void __launch_bounds__(128) fa_segment_kernel(const FaSegmentParams p
   bs.tcap = (int)(p.track_base[u + 1] - bs.tb);
   bs.pb = bs.row0 * p.maxp;
   bs.sb = bs.row0 + u;
-  const int B = p.B;
+  const unsigned lt = (1u << lane) - 1u;
 
   ScanState st;
   st.current_frame = 0; st.no_fm_segs = 0; st.c_ci = 0; st.c_started = -1; st.w = 0; st.k = 0;
   st.y = p.y0; st.v = p.v0; st.x = p.y0; st.v0 = p.v0; st.T = 0; st.s_energy = 0; st.c_energy = 0;
-  st.n_tr = 0; st.n_act = 0; st.n_pts = 0; st.n_segs = 0; st.n_stored = 0; st.n_rows = 0; st.n_syls = 0;
+  st.n_tr = 0; st.n_pts = 0; st.n_slots = 0; st.n_segs = 0; st.n_stored = 0; st.n_rows = 0; st.n_syls = 0;
   st.overflow = 0;
+  for (int r = lane; r < ACAP; r += 32) S.t_id[r] = -1;
+  if (lane <= FA_MAX_BANDS / 32) S.pmask[lane] = 0u;
+  __syncwarp();
 
-  const int epl = (B + 31) >> 5;                     // frame words per lane (<= 8)
-  const int cpl = (p.maxp + 31) >> 5;                // candidate words per lane (<= 5)
-  uint32_t e_next[8], c_next[5];
+  // software prefetch of the next frame: count, g, and the first 32 candidates (one per lane)
+  uint32_t pkd_next = 0, amp_next = 0;
+  unsigned long long pl_next = 0, ph_next = 0;
   int nc_next = 0;
   double g_next = 0;
   auto prefetch = [&](int t) {
-    const uint32_t* fr = p.frames + (size_t)(bs.row0 + t) * B;
-    const uint32_t* cd = p.cand + (size_t)(bs.row0 + t) * p.maxp;
-#pragma unroll
-    for (int i = 0; i < 8; i++) e_next[i] = (i < epl && lane + 32 * i < B) ? __ldg(fr + lane + 32 * i) : 0u;
-#pragma unroll
-    for (int i = 0; i < 5; i++) c_next[i] = (i < cpl && lane + 32 * i < p.maxp) ? __ldg(cd + lane + 32 * i) : 0u;
-    nc_next = __ldg(p.ncand + bs.row0 + t);
-    g_next = __ldg(p.gsum + bs.row0 + t);
+    const size_t row = (size_t)(bs.row0 + t);
+    nc_next = __ldg(p.ncand + row);
+    g_next = __ldg(p.gsum + row);
+    if (lane < p.maxp) {
+      const size_t c = row * p.maxp + lane;
+      pkd_next = __ldg(p.cand + c); amp_next = __ldg(p.camp + c); pl_next = __ldg(p.cpl + c); ph_next = __ldg(p.cph + c);
+    }
   };
   if (bs.F > 0) prefetch(0);
 
   for (int t = 0; t < bs.F && !st.overflow; t++) {
     // ---- spectrum_push @B30392 ----
     st.current_frame++;
-    uint32_t cand[5];
-#pragma unroll
-    for (int i = 0; i < 8; i++) if (i < epl && lane + 32 * i < B) S.e[lane + 32 * i] = e_next[i];
-#pragma unroll
-    for (int i = 0; i < 5; i++) cand[i] = c_next[i];
+    const uint32_t pkd0 = pkd_next, amp0 = amp_next;
+    const unsigned long long pl0 = pl_next, ph0 = ph_next;
     const int nc = min(nc_next, p.maxp);
     if (nc_next > p.maxp) st.overflow = 1;
     const double g = g_next;
-    __syncwarp();
     if (t + 1 < bs.F) prefetch(t + 1);
 
     // ---- D() @B25717: filter the candidates of K2 by the gate v (value at frame start) ----
@@ -580,33 +574,40 @@ __global__ void __launch_bounds__(128) fa_segment_kernel(const FaSegmentParams p
     int n = 0, pbin = 0;
     unsigned long long dsum = 0;
     double h = 2 * v;
-#pragma unroll
-    for (int i = 0; i < 5; i++) {
-      if (i * 32 < nc) {
-        const int c = i * 32 + lane;
-        const bool valid = c < nc;
-        const uint32_t pkd = cand[i];
-        const int pk = (pkd >> 16) & 0xff;
-        const uint32_t amp = valid ? S.e[pk] : 0u;
-        const bool acc = valid && (double)amp > v;
-        const unsigned m = __ballot_sync(FULL, acc);
-        if (acc) {
-          const int pos = n + __popc(m & ((1u << lane) - 1));
-          if (pos < PCAP) { S.plo[pos] = pkd & 0xff; S.phi[pos] = (pkd >> 8) & 0xff; S.ppk[pos] = pk; }
-        }
-        n += __popc(m);
-        dsum += warp_sum_u64(acc ? (unsigned long long)amp : 0ull);
-        // h / p: first strictly greater wins; the last-bin peak never updates them
-        const bool hp = acc && !((pkd >> 24) & 1u);
-        uint32_t mx = hp ? amp : 0u;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
-        const unsigned who = __ballot_sync(FULL, hp && amp == mx);
-        if (who && (double)mx > h) {
-          h = (double)mx;
-          pbin = __shfl_sync(FULL, pk, __ffs(who) - 1);
+    auto filter = [&](const int c0, const uint32_t pkd, const uint32_t amp, const unsigned long long pl,
+                      const unsigned long long ph) {
+      const bool acc = c0 + lane < nc && (double)amp > v;
+      const unsigned m = __ballot_sync(FULL, acc);
+      if (m == 0u) return;
+      const int pk = (pkd >> 16) & 0xff;
+      if (acc) {
+        const int pos = n + __popc(m & lt);
+        if (pos < PCAP) {
+          S.pa[pos] = make_uint2(pkd, amp); S.plh[pos] = make_ulonglong2(pl, ph);
+          S.best[pos] = 0ull; S.owner[pos] = BIG;
+          S.pidx[pk] = (unsigned char)pos;
+          atomicOr(&S.pmask[pk >> 5], 1u << (pk & 31));
         }
       }
+      n += __popc(m);
+      const uint32_t a = acc ? amp : 0u;
+      dsum += (unsigned long long)__reduce_add_sync(FULL, a & 0xffffu) +
+              ((unsigned long long)__reduce_add_sync(FULL, a >> 16) << 16);
+      // h / p: first strictly greater wins; the last-bin peak never updates them
+      const bool hp = acc && !((pkd >> 24) & 1u);
+      const uint32_t mx = __reduce_max_sync(FULL, hp ? amp : 0u);
+      const unsigned who = __ballot_sync(FULL, hp && amp == mx);
+      if (who && (double)mx > h) {
+        h = (double)mx;
+        pbin = __shfl_sync(FULL, pk, __ffs(who) - 1);
+      }
+    };
+    filter(0, pkd0, amp0, pl0, ph0);
+    for (int c0 = 32; c0 < nc; c0 += 32) {  // more than 32 candidates in a frame: rare
+      const size_t c = (size_t)(bs.row0 + t) * p.maxp + c0 + lane;
+      const bool in = c0 + lane < nc;
+      filter(c0, in ? __ldg(p.cand + c) : 0u, in ? __ldg(p.camp + c) : 0u, in ? __ldg(p.cpl + c) : 0ull,
+             in ? __ldg(p.cph + c) : 0ull);
     }
     if (n > PCAP) { st.overflow = 1; break; }
     __syncwarp();
@@ -615,29 +616,31 @@ __global__ void __launch_bounds__(128) fa_segment_kernel(const FaSegmentParams p
     int fin = -2;
     if (st.c_started < 0) {
       const double ratio = d > h ? h * (double)(n - 1) / (d - h) : 0;
-      if (n > 0 && pbin > 7 && pbin < p.max_voiced_bin && n > 4 && ratio > 4) { seg_reset(st, 0); st.c_started = 0; }
+      if (n > 0 && pbin > 7 && pbin < p.max_voiced_bin && n > 4 && ratio > 4) { seg_reset(st, S, 0, lane); st.c_started = 0; }
       else st.no_fm_segs++;
     }
     if (st.c_started >= 0) {
       if (n == 0 || pbin < 7 || pbin >= p.max_voiced_bin || (n > 3 && d / (g - d) < 0.1)) {
         st.no_fm_segs++;
         if (st.c_started < 2) st.c_started--;
-        else if ((double)st.no_fm_segs >= p.seg_breaker) fin = finalize_segment(p, S, st, bs, st.c_ci + 1, lane);
-        else if (p.auto_gate) noise_gate(st, h);
+        else if ((double)st.no_fm_segs >= p.seg_breaker) fin = finalize_copy(p, st, bs, st.c_ci + 1, lane);
+        else if (p.auto_gate) noise_gate(st, S, h, lane);
       } else {
-        if (p.auto_gate) noise_gate(st, h);
+        if (p.auto_gate) noise_gate(st, S, h, lane);
         accumulate_fm(p, S, st, bs, n, t_stale, g, st.v, lane);
         if (st.c_started < 2) st.c_started++; else st.no_fm_segs = 0;
       }
     }
     st.c_ci++;
-    if (fin != -2) seg_reset(st, -1);  // the promise's micro-task runs before the next frame
+    if (fin != -2) seg_reset(st, S, -1, lane);  // the promise's micro-task runs before the next frame
+    __syncwarp();
+    if (n > 0 && lane <= FA_MAX_BANDS / 32) S.pmask[lane] = 0u;
     __syncwarp();
   }
   // segment_truncate @B30800
   if (!st.overflow) {
-    finalize_segment(p, S, st, bs, st.c_ci, lane);
-    seg_reset(st, 1);
+    finalize_copy(p, st, bs, st.c_ci, lane);
+    seg_reset(st, S, 1, lane);
   }
   if (lane == 0) {
     p.n_segs[u] = st.n_segs;
