@@ -107,9 +107,9 @@ struct fa_handle {
   bool prepared = false;
   long long total_frames = 0;
   HostBuf h_pcm, h_meta, h_counts, h_off, h_segs, h_syls, h_formants, h_energy, h_features;
-  DevBuf d_pcm, d_meta, d_spec, d_frames, d_cand, d_camp, d_cpl, d_cph, d_ncand, d_gsum, d_counter;
+  DevBuf d_pcm, d_meta, d_spec, d_frames, d_cand, d_ncand, d_gsum, d_counter;
   DevBuf d_win, d_tw, d_tws, d_ws, d_bmi, d_bmw, d_emph;
-  DevBuf d_trkbase, d_trk_i, d_trk_d, d_trk_slot, d_pt_i, d_pt_e, d_rows, d_rowlist;
+  DevBuf d_spill, d_trkbase, d_trk_i, d_trk_d, d_trk_slot, d_pt_i, d_pt_e, d_rows, d_rowlist;
   DevBuf d_segs, d_syls, d_formants, d_energy, d_features, d_counts, d_off;
   DevBuf g_segs, g_syls, g_formants, g_energy, g_features;
   int n_weights = 0;
@@ -281,8 +281,8 @@ int fa_destroy(fa_handle* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   for (int i = 0; i < kMaxSub; i++) if (h->sub_stream[i]) cudaStreamSynchronize(h->sub_stream[i]);
-  for (DevBuf* b : {&h->d_pcm, &h->d_meta, &h->d_spec, &h->d_frames, &h->d_cand, &h->d_camp, &h->d_cpl, &h->d_cph, &h->d_ncand, &h->d_gsum, &h->d_counter,
-                    &h->d_win, &h->d_tw, &h->d_tws, &h->d_ws, &h->d_bmi, &h->d_bmw, &h->d_emph, &h->d_trkbase, &h->d_trk_i,
+  for (DevBuf* b : {&h->d_pcm, &h->d_meta, &h->d_spec, &h->d_frames, &h->d_cand, &h->d_ncand, &h->d_gsum, &h->d_counter,
+                    &h->d_win, &h->d_tw, &h->d_tws, &h->d_ws, &h->d_bmi, &h->d_bmw, &h->d_emph, &h->d_spill, &h->d_trkbase, &h->d_trk_i,
                     &h->d_trk_d, &h->d_trk_slot, &h->d_pt_i, &h->d_pt_e, &h->d_rows, &h->d_rowlist, &h->d_segs, &h->d_syls,
                     &h->d_formants, &h->d_energy, &h->d_features, &h->d_counts, &h->d_off, &h->g_segs, &h->g_syls,
                     &h->g_formants, &h->g_energy, &h->g_features})
@@ -469,10 +469,7 @@ static int prepare(fa_handle* h) {
   FA_CUDA(h->d_frames.reserve(Fz * h->B * sizeof(uint32_t)));
   FA_CUDA(h->d_counter.reserve(2 * kMaxSub * sizeof(int)));
   if (h->cfg.output_level >= 3) {
-    FA_CUDA(h->d_cand.reserve(Fz * h->maxp * sizeof(uint32_t)));
-    FA_CUDA(h->d_camp.reserve(Fz * h->maxp * sizeof(uint32_t)));
-    FA_CUDA(h->d_cpl.reserve(Fz * h->maxp * sizeof(unsigned long long)));
-    FA_CUDA(h->d_cph.reserve(Fz * h->maxp * sizeof(unsigned long long)));
+    FA_CUDA(h->d_cand.reserve(Fz * h->maxp * sizeof(FaCand)));
     FA_CUDA(h->d_ncand.reserve(Fz * sizeof(int)));
     FA_CUDA(h->d_gsum.reserve(Fz * sizeof(double)));
     const size_t T = (size_t)std::max<long long>(tb, 1);
@@ -484,6 +481,7 @@ static int prepare(fa_handle* h) {
     FA_CUDA(h->d_pt_e.reserve(P * sizeof(double)));
     FA_CUDA(h->d_rows.reserve((Fz + nz) * 2 * sizeof(int)));
     FA_CUDA(h->d_rowlist.reserve(P * sizeof(int)));
+    FA_CUDA(h->d_spill.reserve(nz * 6 * 128 * sizeof(unsigned long long)));
     FA_CUDA(h->d_segs.reserve((Fz + nz) * sizeof(fa_segment)));
     FA_CUDA(h->d_syls.reserve((Fz + nz) * sizeof(fa_syllable)));
     FA_CUDA(h->d_formants.reserve(Fz * 9 * sizeof(float)));
@@ -586,8 +584,7 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
   if (c.output_level >= 3 && sb.r1 > sb.r0) {
     FaPeaksParams pp;
     pp.frames = h->d_frames.as<uint32_t>(); pp.B = h->B; pp.maxp = h->maxp; pp.n_frames = sb.r1 - sb.r0; pp.row_begin = sb.r0;
-    pp.camp = h->d_camp.as<uint32_t>(); pp.cpl = h->d_cpl.as<unsigned long long>(); pp.cph = h->d_cph.as<unsigned long long>();
-    pp.cand = h->d_cand.as<uint32_t>(); pp.ncand = h->d_ncand.as<int>(); pp.gsum = h->d_gsum.as<double>();
+    pp.cand = h->d_cand.as<FaCand>(); pp.ncand = h->d_ncand.as<int>(); pp.gsum = h->d_gsum.as<double>();
     FA_CUDA(fa_launch_peaks(pp, s, &h->launches));
     if (getenv("FA_DEBUG_SYNC")) FA_CUDA(cudaStreamSynchronize(s));
   }
@@ -598,8 +595,7 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
     const size_t R = (size_t)std::max<long long>(F, 1) + n;
     FaSegmentParams g;
     memset(&g, 0, sizeof(g));
-    g.cand = h->d_cand.as<uint32_t>(); g.camp = h->d_camp.as<uint32_t>(); g.cpl = h->d_cpl.as<unsigned long long>();
-    g.cph = h->d_cph.as<unsigned long long>(); g.ncand = h->d_ncand.as<int>();
+    g.cand = h->d_cand.as<FaCand>(); g.ncand = h->d_ncand.as<int>();
     g.gsum = h->d_gsum.as<double>(); g.frame_off = meta + 2 * n; g.n_utt = n; g.B = h->B; g.maxp = h->maxp;
     g.utt_begin = sb.u0; g.utt_count = sb.u1 - sb.u0;
     g.level = c.output_level;
@@ -616,6 +612,8 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
     g.pt_track = h->d_pt_i.as<int>(); g.pt_ord = g.pt_track + P; g.pt_frame = g.pt_ord + P; g.pt_binspan = g.pt_frame + P;
     g.pt_e = h->d_pt_e.as<double>();
     g.row_count = h->d_rows.as<int>(); g.row_off = g.row_count + R; g.row_list = h->d_rowlist.as<int>();
+    g.cs_spill = h->d_spill.as<unsigned long long>();
+    g.finalize_in_smem = getenv("FA_K3_FINALIZE_HBM") ? 0 : 1;
     g.segs = h->d_segs.as<fa_segment>(); g.syls = h->d_syls.as<fa_syllable>();
     g.formants = h->d_formants.as<float>(); g.energy = h->d_energy.as<float>();
     int* cnt = h->d_counts.as<int>();
@@ -910,8 +908,24 @@ int fa_copy_peak_candidates(fa_handle* h, int64_t utt_id, uint32_t* packed, int3
   if (!h) return FA_ERR_INVALID_ARG;
   if (h->cfg.output_level < 3) return fail(h, FA_ERR_INVALID_ARG, "no peak scan below output_level 3");
   if (max_per_frame) *max_per_frame = h->maxp;
-  int rc = copy_rows_device(h, utt_id, h->d_cand.p, (size_t)h->maxp * sizeof(uint32_t), packed, cap_rows);
-  if (rc < 0) return rc;
+  // the packed word of every 32-byte candidate record
+  int rc = need_results(h);
+  if (rc != FA_OK) return rc;
+  {
+    long long r0 = 0, nr = h->total_frames;
+    if (utt_id >= 0) {
+      Utt* u = find_utt(h, utt_id);
+      if (!u) return fail(h, FA_ERR_UNKNOWN_UTT, "unknown utterance id");
+      r0 = u->row0; nr = u->frames;
+    }
+    if ((size_t)nr > cap_rows) return fail(h, FA_ERR_CAPACITY, "destination too small");
+    if (nr && !packed) return FA_ERR_INVALID_ARG;
+    if (nr) {
+      FA_CUDA(cudaMemcpy2DAsync(packed, sizeof(uint32_t), h->d_cand.as<FaCand>() + (size_t)r0 * h->maxp, sizeof(FaCand),
+                                sizeof(uint32_t), (size_t)nr * h->maxp, cudaMemcpyDeviceToHost, h->stream));
+      FA_CUDA(cudaStreamSynchronize(h->stream));
+    }
+  }
   return copy_rows_device(h, utt_id, h->d_ncand.p, sizeof(int), counts, cap_rows);
 }
 

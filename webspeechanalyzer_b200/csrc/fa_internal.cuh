@@ -46,25 +46,28 @@ struct FaSpectrumParams {
   int* work_counter;             // dynamic utterance queue
 };
 
+// one candidate peak of a frame (K2 -> K3), 32 bytes = one DRAM sector
+struct __align__(16) FaCand {
+  uint32_t packed;               // lo | hi<<8 | pk<<16 | last<<24 (trimmed bounds)
+  uint32_t amp;                  // e[pk]
+  unsigned long long pl;         // P[lo - 1]  (P = inclusive prefix sums of the frame, exact)
+  unsigned long long ph;         // P[hi]
+  unsigned long long pad;
+};
+
 struct FaPeaksParams {
   const uint32_t* frames;        // [F_total][B]
   int B, maxp;
   long long n_frames;            // frames of the sub-batch
   long long row_begin;
-  uint32_t* cand;                // [F_total][maxp] packed lo | hi<<8 | pk<<16 | last<<24
-  uint32_t* camp;                // [F_total][maxp] e[pk]
-  unsigned long long* cpl;       // [F_total][maxp] P[lo - 1]  (P = inclusive prefix sums of the frame, exact)
-  unsigned long long* cph;       // [F_total][maxp] P[hi]
+  FaCand* cand;                  // [F_total][maxp]
   int* ncand;                    // [F_total]
   double* gsum;                  // [F_total] sum e[1..B-1]
 };
 
 // per-utterance scan state that survives across time chunks (reserved for the stream stitcher)
 struct FaSegmentParams {
-  const uint32_t* cand;
-  const uint32_t* camp;
-  const unsigned long long* cpl;
-  const unsigned long long* cph;
+  const FaCand* cand;            // [F_total][maxp]
   const int* ncand;
   const double* gsum;
   const long long* frame_off;    // [n_utt + 1]
@@ -81,6 +84,8 @@ struct FaSegmentParams {
   int* pt_track; int* pt_ord; int* pt_frame; int* pt_binspan; double* pt_e;
   int* row_count; int* row_off;       // [F_total + n_utt] scratch (per utterance F_u + 1)
   int* row_list;                      // [F_total * maxp]
+  unsigned long long* cs_spill;       // [n_utt][6][128] candidate scores beyond the three kept in shared memory
+  int finalize_in_smem;               // 1: segments that fit are finalised in shared memory (0 forces the HBM path: tests)
   // outputs (per utterance tables at base frame_off[u] + u, capacity F_u + 1)
   fa_segment* segs; int* n_segs; int* n_stored;
   float* formants;                    // [F_total][9]   rows of utterance u start at frame_off[u]

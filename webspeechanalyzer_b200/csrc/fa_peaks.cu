@@ -15,11 +15,12 @@ namespace {
 
 constexpr int kPeakThreads = 128;
 
-// NOTE (round 1): variants of this loop that hoist several row loads ahead of the automaton (manual 8 x 16 B
-// batches, or `#pragma unroll 4` + __restrict__) produced wrong g / candidates for one warp of rows on the B200
-// (rows 992..1023 of an 8 x 200-frame batch, deterministic, also with a stream sync before the launch) while a
-// host build of the same source matches the oracle; unresolved, so the plain one-load-per-iteration loop stays.
-// tests/test_gpu_parity.py now checks g and the candidates of every frame.
+// NOTE (ptxas 12.9, sm_100a): with p.B / p.maxp read straight from the parameter bank, ptxas keeps B in a UNIFORM
+// register (UR4) across the bin loop, but re-loads other parameters (maxp, B - 1) into the same UR4 inside the divergent
+// emit() paths; the loop bound `B / 4` is then computed from whatever the last path left there (seen in the SASS:
+// USHF.R.S32.HI UR4, URZ, 0x2, UR4 at the loop tail) -- rows lose their last iteration or the loop runs away.  Passing
+// the two values through an opaque asm keeps them in ordinary per-thread registers, which sidesteps the problem.
+// tests/test_gpu_parity.py checks g and the candidates of every frame.
 // One thread per frame, no shared memory: the thread streams its own 4*B-byte row with 16-byte loads
 // (rows are 512 B for B = 128: four full cache lines, every byte used; K1 has just written them, so most
 // come from L2) and runs the automaton in registers.  200k frames = 6250 warps: one wave at full occupancy.
@@ -27,12 +28,10 @@ __global__ void __launch_bounds__(kPeakThreads) fa_peaks_kernel(const FaPeaksPar
   const long long fi = (long long)blockIdx.x * kPeakThreads + threadIdx.x;
   if (fi >= p.n_frames) return;
   const long long f = p.row_begin + fi;
-  const int B = p.B;
+  int B = p.B, maxp = p.maxp;
+  asm volatile("" : "+r"(B), "+r"(maxp));  // see the NOTE above
   const uint32_t* __restrict__ e = p.frames + (size_t)f * B;
-  uint32_t* out = p.cand + (size_t)f * p.maxp;
-  uint32_t* out_amp = p.camp + (size_t)f * p.maxp;
-  unsigned long long* out_pl = p.cpl + (size_t)f * p.maxp;
-  unsigned long long* out_ph = p.cph + (size_t)f * p.maxp;
+  FaCand* out = p.cand + (size_t)f * maxp;
   int n = 0, lo = 0, pk = 0, hi = 0, flat = 0, dir = 0;
   unsigned long long g = 0;
   uint32_t epk = 0;  // e[pk]
@@ -59,11 +58,11 @@ __global__ void __launch_bounds__(kPeakThreads) fa_peaks_kernel(const FaPeaksPar
       ph2 -= x;
       h2--;
     }
-    if (n < p.maxp) {
-      out[n] = (uint32_t)l2 | ((uint32_t)h2 << 8) | ((uint32_t)pk << 16) | ((uint32_t)last << 24);
-      out_amp[n] = epk;
-      out_pl[n] = pl2;
-      out_ph[n] = ph2;
+    if (n < maxp) {
+      uint4* o4 = reinterpret_cast<uint4*>(out + n);  // two 16-byte stores into one sector
+      o4[0] = make_uint4((uint32_t)l2 | ((uint32_t)h2 << 8) | ((uint32_t)pk << 16) | ((uint32_t)last << 24), epk,
+                         (uint32_t)pl2, (uint32_t)(pl2 >> 32));
+      o4[1] = make_uint4((uint32_t)ph2, (uint32_t)(ph2 >> 32), 0u, 0u);
     }
     n++;
   };

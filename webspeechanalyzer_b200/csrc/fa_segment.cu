@@ -45,12 +45,17 @@ constexpr int CMAX = 9;    // a +-8 bin window holds at most 9 peaks (they are >
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int BIG = 0x7fffffff;
 
+constexpr int CSM = 3;     // candidate scores per slot kept in shared memory; the rest spill to the point-pool tail
+
 struct WarpShared {
+  // ---- per-frame data; dead while a segment is finalised, so finalize_fast reuses these bytes as scratch ----
+  unsigned long long cs[CSM][ACAP];           // [j][slot]: score of the slot's j-th retained candidate
   // accepted peaks of the frame
   ulonglong2 plh[PCAP];                       // P[lo-1], P[hi]
   uint2 pa[PCAP];                             // packed lo | hi<<8 | pk<<16 | last<<24, amplitude e[pk]
   unsigned long long best[PCAP];              // best score per peak (bit pattern of a positive double)
   int owner[PCAP];                            // creation index of the owning track, BIG = none
+  // ---- end of the scratch-able prefix ----
   uint32_t pmask[FA_MAX_BANDS / 32 + 1];      // bit b: an accepted peak has pk == b
   unsigned char pidx[FA_MAX_BANDS];           // its index in the accepted list
   unsigned char newlist[PCAP];                // un-owned peaks above the gate, in peak order
@@ -62,8 +67,9 @@ struct WarpShared {
   uint32_t t_amp[ACAP];                       // lastAmp
   uint32_t t_wm[ACAP];                        // this frame: retained candidates (bit j = bin wlo + j)
   double t_vel[ACAP], t_se[ACAP], t_seb[ACAP];
-  unsigned long long cs[CMAX][ACAP];          // [j][slot]: score of the slot's j-th retained candidate
 };
+constexpr int kScratchBytes = (int)(sizeof(unsigned long long) * CSM * ACAP + sizeof(ulonglong2) * PCAP + sizeof(uint2) * PCAP +
+                                    sizeof(unsigned long long) * PCAP + sizeof(int) * PCAP);
 
 struct ScanState {
   int current_frame, no_fm_segs, c_ci, c_started, w, k;
@@ -78,7 +84,7 @@ struct Bases {
   long long tb;     // track table base
   long long pb;     // point pool base
   long long sb;     // segment / syllable / row-scratch base (row0 + u)
-  int F, tcap;
+  int F, tcap, u;
 };
 
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
@@ -154,8 +160,10 @@ __device__ __forceinline__ void accumulate_fm(const FaSegmentParams& p, WarpShar
   if (n_peaks < 1) return;
   st.s_energy += g;
   const unsigned lt = (1u << lane) - 1u;
-  const int B = p.B;
+  int B = p.B;
+  asm volatile("" : "+r"(B));
   const int n_slots = st.n_slots;
+  unsigned long long* spill = p.cs_spill + (size_t)bs.u * ((CMAX - CSM) * ACAP);  // > 3 scoring candidates in a window: rare
   // (1) lane per track slot: expire, window of candidate peaks, scores, arg-max per peak (atomicMax on the bits)
   bool bad = false;
   for (int r0 = 0; r0 < n_slots; r0 += 32) {
@@ -184,7 +192,8 @@ __device__ __forceinline__ void accumulate_fm(const FaSegmentParams& p, WarpShar
             const double sc = fm_score(gap, (double)abs(lb - bin), np, lb, bin, amp_old, (double)S.pa[o].y, vel);
             if (sc > 1) {
               const unsigned long long sb = (unsigned long long)__double_as_longlong(sc);
-              if (j < CMAX) S.cs[j][r] = sb;
+              if (j < CSM) S.cs[j][r] = sb;
+              else if (j < CMAX) spill[(j - CSM) * ACAP + r] = sb;
               j++;
               kept |= 1u << b;
               atomicMax(&S.best[o], sb);
@@ -213,7 +222,8 @@ __device__ __forceinline__ void accumulate_fm(const FaSegmentParams& p, WarpShar
         const int b = __ffs(bits) - 1;
         bits &= bits - 1;
         const int o = S.pidx[wlo + b];
-        if (S.cs[j][r] == S.best[o]) atomicMin(&S.owner[o], id);
+        const unsigned long long mine = j < CSM ? S.cs[j][r] : spill[(j - CSM) * ACAP + r];
+        if (mine == S.best[o]) atomicMin(&S.owner[o], id);
         j++;
       } while (bits);
     }
@@ -321,6 +331,214 @@ __device__ __forceinline__ void accumulate_fm(const FaSegmentParams& p, WarpShar
     st.n_tr += nn;
     st.n_pts += nn;
   }
+}
+
+// O() @B27088, fast path: the segment's tables (T tracks, len rows, n_pts points) fit the per-frame shared-memory bytes
+// that are dead during finalisation.  Same results as finalize_segment below, which works in HBM for any size.
+//   scratch: mean f64[T] | rank u8[T] | slot s8[T] | order u8[T] | rc i32[len] | ro i32[len] | key u32[n_pts]
+//   key = rank << 23 | ordinal << 13 | point << 2 | slot  (T <= 255, ordinal < 1024, point < 2048)
+__device__ __forceinline__ bool finalize_fits(const ScanState& st, const int len) {
+  const int T = st.n_tr;
+  const int need = ((8 * T + 3 * T + 7) & ~7) + 8 * len + 4 * st.n_pts;
+  return T <= 255 && st.n_pts < 2048 && st.c_ci + 1 < 1024 && len < 1024 && need <= kScratchBytes;
+}
+
+__device__ __noinline__ int finalize_fast(const FaSegmentParams p, WarpShared& S, ScanState& st, const Bases bs,
+                                          const int n_arg, const int lane) {
+  const int len = n_arg - st.no_fm_segs;
+  const int start = st.current_frame - len;
+  const double vmin = st.v;
+  const int T = st.n_tr, NP = st.n_pts;
+  unsigned char* W = reinterpret_cast<unsigned char*>(&S);
+  double* mean = reinterpret_cast<double*>(W);
+  unsigned char* rank = W + 8 * T;
+  signed char* slot = reinterpret_cast<signed char*>(rank + T);
+  unsigned char* order = rank + 2 * T;
+  int* rc = reinterpret_cast<int*>(W + ((11 * T + 7) & ~7));
+  int* ro = rc + len;
+  uint32_t* key = reinterpret_cast<uint32_t*>(ro + len);
+  __syncwarp();  // the track table is written through at every update (by whichever lane owns the track)
+  // get_ranked_formants @B35670: count >= 2, mean >= 7, stable ascending by mean
+  int nr = 0;
+  for (int i0 = 0; i0 < T; i0 += 32) {
+    const int i = i0 + lane;
+    bool elig = false;
+    if (i < T) {
+      const double m = p.trk_sum_eb[bs.tb + i] / p.trk_sum_e[bs.tb + i];
+      elig = p.trk_count[bs.tb + i] >= 2 && m >= 7;
+      mean[i] = elig ? m : -1.0;
+      slot[i] = -1;
+    }
+    nr += __popc(__ballot_sync(FULL, elig));
+  }
+  for (int r = lane; r < len; r += 32) rc[r] = 0;
+  __syncwarp();
+  for (int i = lane; i < T; i += 32) {
+    const double m = mean[i];
+    if (m >= 7) {
+      int rk = 0;
+#pragma unroll 4
+      for (int j = 0; j < T; j++) {
+        const double mj = mean[j];
+        rk += (mj >= 7 && (mj < m || (mj == m && j < i))) ? 1 : 0;
+      }
+      rank[i] = (unsigned char)rk;
+      order[rk] = (unsigned char)i;
+    }
+  }
+  __syncwarp();
+  // slot assignment of straighten_formants @B35074 (sequential over the ranking)
+  {
+    double anchor = 0;
+    int sl = 0;
+    for (int r = 0; r < nr; r++) {
+      const int i = order[r];
+      const double m = mean[i];
+      if (fabs(m - anchor) > 20) {
+        anchor = m;
+        sl++;
+        if (sl >= 3) break;
+      }
+      if (lane == 0) slot[i] = (signed char)sl;
+    }
+  }
+  __syncwarp();
+
+  const int si = st.n_segs;
+  fa_segment seg;
+  seg.start = start; seg.len = len; seg.stored = -1; seg.n_syllables = 0; seg.first_syllable = -1; seg.row_offset = -1;
+  seg.ymax = st.y; seg.vmin = st.v; seg.cs_ratio = st.c_energy / st.s_energy;
+  st.n_segs++;
+
+  // rows: which points land on which frame row (counting sort by row, in shared memory)
+  bool thrown = false;
+  for (int q0 = 0; q0 < NP; q0 += 32) {
+    const int q = q0 + lane;
+    if (q < NP) {
+      const int i = p.pt_track[bs.pb + q];
+      const int sl = slot[i];
+      uint32_t k = 0xffffffffu;
+      if (sl >= 0) {
+        const int fr = p.pt_frame[bs.pb + q];
+        if (fr < 0 || fr >= len) thrown = true;  // r[d] is undefined -> TypeError -> .catch(L(-1))
+        else {
+          atomicAdd(&rc[fr], 1);
+          k = ((uint32_t)rank[i] << 23) | ((uint32_t)p.pt_ord[bs.pb + q] << 13) | ((uint32_t)q << 2) | (uint32_t)sl;
+        }
+      }
+      // park the key in the row_list of HBM until the offsets are known (one coalesced store/load per point)
+      p.row_list[bs.pb + q] = (int)k;
+    }
+  }
+  thrown = __any_sync(FULL, thrown);
+  if (thrown) {
+    if (lane == 0) p.segs[bs.sb + si] = seg;
+    return -1;
+  }
+  __syncwarp();
+  {
+    int run = 0;
+    for (int r0 = 0; r0 < len; r0 += 32) {
+      const int r = r0 + lane;
+      const int c = r < len ? rc[r] : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (r < len) { ro[r] = run + incl - c; rc[r] = 0; }
+      run += __shfl_sync(FULL, incl, 31);
+    }
+  }
+  __syncwarp();
+  for (int q0 = 0; q0 < NP; q0 += 32) {
+    const int q = q0 + lane;
+    if (q < NP) {
+      const uint32_t k = (uint32_t)p.row_list[bs.pb + q];
+      if (k != 0xffffffffu) {
+        const int fr = p.pt_frame[bs.pb + q];
+        key[ro[fr] + atomicAdd(&rc[fr], 1)] = k;
+      }
+    }
+  }
+  __syncwarp();
+  // apply: lane per row, points ordered by (track rank, point ordinal)
+  float* Fout = p.formants + (size_t)(bs.row0 + st.n_rows) * 9;
+  float* Eout = p.energy + (size_t)(bs.row0 + st.n_rows) * 3;
+  for (int fr = lane; fr < len; fr += 32) {
+    const int k = rc[fr], off = ro[fr];
+    float f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0, f6 = 0, f7 = 0, f8 = 0, g0 = 0, g1 = 0, g2 = 0;
+    long long last = -1;
+    for (int it = 0; it < k; it++) {
+      long long bestkey = 0x7fffffffffffffffll;
+      for (int z = 0; z < k; z++) {
+        const long long kz = (long long)key[off + z];
+        if (kz > last && kz < bestkey) bestkey = kz;
+      }
+      last = bestkey;
+      const int bq = (int)((bestkey >> 2) & 2047);
+      int sl = (int)(bestkey & 3);
+      const int bs_ = p.pt_binspan[bs.pb + bq];
+      const int bin = bs_ & 0xffff, span = bs_ >> 16;
+      const double E = p.pt_e[bs.pb + bq];
+      const float cur = sl == 0 ? f0 : sl == 1 ? f3 : f6;
+      if ((double)cur > vmin && (double)cur < (double)bin && sl < 2) sl++;
+      const float fb = (float)bin, fe = (float)E, fs = (float)span;
+      if (sl == 0) { f0 = fb; f1 = fe; f2 = fs; }
+      else if (sl == 1) { f3 = fb; f4 = fe; f5 = fs; }
+      else { f6 = fb; f7 = fe; f8 = fs; }
+      g0 = (float)((double)g0 + (double)bin * E);
+      g1 = (float)((double)g1 + E);
+      g2 = (float)((double)g2 + (double)span * E);
+    }
+    float* fo = Fout + (size_t)fr * 9;
+    fo[0] = f0; fo[1] = f1; fo[2] = f2; fo[3] = f3; fo[4] = f4; fo[5] = f5; fo[6] = f6; fo[7] = f7; fo[8] = f8;
+    float* eo = Eout + (size_t)fr * 3;
+    eo[0] = g0; eo[1] = g1; eo[2] = g2;
+    // sep_syllables needs "energy > vmin" per row: keep the flag in rc (row scratch)
+    rc[fr] = (double)g1 > vmin ? 1 : 0;
+  }
+  __syncwarp();
+  seg.stored = st.n_stored;
+  seg.row_offset = st.n_rows;
+  seg.first_syllable = st.n_syls;
+  // sep_syllables @B34757
+  int nsyl = 0;
+  if (p.level == 10 || p.level == 11 || p.level == 13) {
+    int sstart = -1, quiet = 0, loud = 0;
+    for (int e0 = 0; e0 < len; e0 += 32) {
+      const int e = e0 + lane;
+      const bool is_loud = e < len && rc[e] != 0;
+      const unsigned bits = __ballot_sync(FULL, is_loud);
+      const int cnt = min(32, len - e0);
+      for (int b = 0; b < cnt; b++) {
+        const int ee = e0 + b;
+        if ((bits >> b) & 1u) { quiet = 0; loud++; if (sstart < 0) sstart = ee; }
+        else quiet++;
+        if ((loud > 20 && quiet > 0) || (loud > 10 && quiet > 1) || (loud > 0 && quiet > 4) || (ee >= len - 1 && loud > 4)) {
+          const int end = ee - quiet;
+          if (end - sstart > 1) {
+            if (lane == 0) {
+              fa_syllable sy;
+              sy.stored_seg = st.n_stored; sy.start = sstart; sy.len = end - sstart; sy.reserved = 0;
+              p.syls[bs.sb + st.n_syls + nsyl] = sy;
+            }
+            nsyl++;
+            sstart = -1;
+            loud = 0;
+          }
+        }
+      }
+    }
+  }
+  seg.n_syllables = nsyl;
+  if (lane == 0) p.segs[bs.sb + si] = seg;
+  st.n_syls += nsyl;
+  st.n_stored++;
+  st.n_rows += len;
+  __syncwarp();
+  return 1;
 }
 
 // O() @B27088.  Returns 1 stored, 0 ignored, -1 rejected (where the JS throws inside straighten_formants).
@@ -508,10 +726,13 @@ __device__ __noinline__ int finalize_segment(const FaSegmentParams p, ScanState&
 }
 
 // finalisation works on a copy so that the scan state itself stays in registers (the call is out of line)
-__device__ __forceinline__ int finalize_copy(const FaSegmentParams& p, ScanState& st, const Bases& bs, const int n_arg,
-                                             const int lane) {
+__device__ __forceinline__ int finalize_copy(const FaSegmentParams& p, WarpShared& S, ScanState& st, const Bases& bs,
+                                             const int n_arg, const int lane) {
+  const int len = n_arg - st.no_fm_segs;
+  if (!(len > p.seg_min_frames && st.c_started >= 2)) return 0;
   ScanState cp = st;
-  const int r = finalize_segment(p, cp, bs, n_arg, lane);
+  const int r = (p.finalize_in_smem && finalize_fits(st, len)) ? finalize_fast(p, S, cp, bs, n_arg, lane)
+                                                                : finalize_segment(p, cp, bs, n_arg, lane);
   st.n_segs = cp.n_segs; st.n_stored = cp.n_stored; st.n_rows = cp.n_rows; st.n_syls = cp.n_syls;
   return r;
 }
@@ -529,8 +750,11 @@ __global__ void __launch_bounds__(128) fa_segment_kernel(const FaSegmentParams p
   bs.F = (int)(p.frame_off[u + 1] - bs.row0);
   bs.tb = p.track_base[u];
   bs.tcap = (int)(p.track_base[u + 1] - bs.tb);
-  bs.pb = bs.row0 * p.maxp;
+  int maxp = p.maxp;
+  asm volatile("" : "+r"(maxp));  // keep it in an ordinary register (ptxas uniform-register hazard, see fa_peaks.cu)
+  bs.pb = bs.row0 * maxp;
   bs.sb = bs.row0 + u;
+  bs.u = u;
   const unsigned lt = (1u << lane) - 1u;
 
   ScanState st;
@@ -551,9 +775,10 @@ __global__ void __launch_bounds__(128) fa_segment_kernel(const FaSegmentParams p
     const size_t row = (size_t)(bs.row0 + t);
     nc_next = __ldg(p.ncand + row);
     g_next = __ldg(p.gsum + row);
-    if (lane < p.maxp) {
-      const size_t c = row * p.maxp + lane;
-      pkd_next = __ldg(p.cand + c); amp_next = __ldg(p.camp + c); pl_next = __ldg(p.cpl + c); ph_next = __ldg(p.cph + c);
+    if (lane < maxp) {
+      const uint4* c4 = reinterpret_cast<const uint4*>(p.cand + row * maxp + lane);
+      const uint4 a = __ldg(c4), b = __ldg(c4 + 1);
+      pkd_next = a.x; amp_next = a.y; pl_next = a.z | ((unsigned long long)a.w << 32); ph_next = b.x | ((unsigned long long)b.y << 32);
     }
   };
   if (bs.F > 0) prefetch(0);
@@ -563,8 +788,8 @@ __global__ void __launch_bounds__(128) fa_segment_kernel(const FaSegmentParams p
     st.current_frame++;
     const uint32_t pkd0 = pkd_next, amp0 = amp_next;
     const unsigned long long pl0 = pl_next, ph0 = ph_next;
-    const int nc = min(nc_next, p.maxp);
-    if (nc_next > p.maxp) st.overflow = 1;
+    const int nc = min(nc_next, maxp);
+    if (nc_next > maxp) st.overflow = 1;
     const double g = g_next;
     if (t + 1 < bs.F) prefetch(t + 1);
 
@@ -604,10 +829,12 @@ __global__ void __launch_bounds__(128) fa_segment_kernel(const FaSegmentParams p
     };
     filter(0, pkd0, amp0, pl0, ph0);
     for (int c0 = 32; c0 < nc; c0 += 32) {  // more than 32 candidates in a frame: rare
-      const size_t c = (size_t)(bs.row0 + t) * p.maxp + c0 + lane;
-      const bool in = c0 + lane < nc;
-      filter(c0, in ? __ldg(p.cand + c) : 0u, in ? __ldg(p.camp + c) : 0u, in ? __ldg(p.cpl + c) : 0ull,
-             in ? __ldg(p.cph + c) : 0ull);
+      uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+      if (c0 + lane < nc) {
+        const uint4* c4 = reinterpret_cast<const uint4*>(p.cand + (size_t)(bs.row0 + t) * maxp + c0 + lane);
+        a = __ldg(c4); b = __ldg(c4 + 1);
+      }
+      filter(c0, a.x, a.y, a.z | ((unsigned long long)a.w << 32), b.x | ((unsigned long long)b.y << 32));
     }
     if (n > PCAP) { st.overflow = 1; break; }
     __syncwarp();
@@ -623,7 +850,7 @@ __global__ void __launch_bounds__(128) fa_segment_kernel(const FaSegmentParams p
       if (n == 0 || pbin < 7 || pbin >= p.max_voiced_bin || (n > 3 && d / (g - d) < 0.1)) {
         st.no_fm_segs++;
         if (st.c_started < 2) st.c_started--;
-        else if ((double)st.no_fm_segs >= p.seg_breaker) fin = finalize_copy(p, st, bs, st.c_ci + 1, lane);
+        else if ((double)st.no_fm_segs >= p.seg_breaker) fin = finalize_copy(p, S, st, bs, st.c_ci + 1, lane);
         else if (p.auto_gate) noise_gate(st, S, h, lane);
       } else {
         if (p.auto_gate) noise_gate(st, S, h, lane);
@@ -639,7 +866,7 @@ __global__ void __launch_bounds__(128) fa_segment_kernel(const FaSegmentParams p
   }
   // segment_truncate @B30800
   if (!st.overflow) {
-    finalize_copy(p, st, bs, st.c_ci, lane);
+    finalize_copy(p, S, st, bs, st.c_ci, lane);
     seg_reset(st, S, 1, lane);
   }
   if (lane == 0) {
