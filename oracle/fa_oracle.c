@@ -586,6 +586,11 @@ static int finalize_segment(fao_state* st, fao_result* R, int n_arg) {
   int start = st->current_frame - len;
   int* ranked = (int*)malloc(sizeof(int) * (size_t)(st->n_tr > 0 ? st->n_tr : 1));
   int nr = ranked_formants(st, ranked);
+  if (getenv("FAO_DEBUG_SEG")) {
+    int np = 0;
+    for (int t = 0; t < st->n_tr; t++) np += st->tr[t].count;
+    fprintf(stderr, "FAO_SEG T=%d NP=%d len=%d cci=%d nr=%d\n", st->n_tr, np, len, st->c_ci, nr);
+  }
   ivec_push(&R->seg_start, start);
   ivec_push(&R->seg_len, len);
   ivec_push(&R->seg_stored, -1);

@@ -31,6 +31,7 @@
 // oracle/fa_oracle.c.
 //
 // This kernel moves kilobytes per utterance; it is latency bound, not HBM bound.
+#include <cstddef>
 #include <cstdlib>
 
 #include "fa_internal.cuh"
@@ -48,28 +49,27 @@ constexpr int BIG = 0x7fffffff;
 constexpr int CSM = 3;     // candidate scores per slot kept in shared memory; the rest spill to the point-pool tail
 
 struct WarpShared {
-  // ---- per-frame data; dead while a segment is finalised, so finalize_fast reuses these bytes as scratch ----
+  // ---- everything up to pmask is dead while a segment is finalised: finalize_fast reuses these bytes as scratch ----
   unsigned long long cs[CSM][ACAP];           // [j][slot]: score of the slot's j-th retained candidate
   // accepted peaks of the frame
   ulonglong2 plh[PCAP];                       // P[lo-1], P[hi]
   uint2 pa[PCAP];                             // packed lo | hi<<8 | pk<<16 | last<<24, amplitude e[pk]
   unsigned long long best[PCAP];              // best score per peak (bit pattern of a positive double)
   int owner[PCAP];                            // creation index of the owning track, BIG = none
-  // ---- end of the scratch-able prefix ----
-  uint32_t pmask[FA_MAX_BANDS / 32 + 1];      // bit b: an accepted peak has pk == b
-  unsigned char pidx[FA_MAX_BANDS];           // its index in the accepted list
-  unsigned char newlist[PCAP];                // un-owned peaks above the gate, in peak order
   // live tracks of the current segment (field list of l[r] @B35952)
+  double t_vel[ACAP], t_se[ACAP], t_seb[ACAP];
   int t_id[ACAP];                             // creation index inside the segment, -1 = free slot
   int t_lf[ACAP];                             // lastFrame
   int t_bins[ACAP];                           // last three peak bins: b1 | b2 << 8 | b3 << 16
   int t_np[ACAP];                             // points so far
   uint32_t t_amp[ACAP];                       // lastAmp
   uint32_t t_wm[ACAP];                        // this frame: retained candidates (bit j = bin wlo + j)
-  double t_vel[ACAP], t_se[ACAP], t_seb[ACAP];
+  unsigned char pidx[FA_MAX_BANDS];           // index of the accepted peak at bin b in the accepted list
+  unsigned char newlist[PCAP];                // un-owned peaks above the gate, in peak order
+  // ---- end of the scratch-able prefix ----
+  uint32_t pmask[FA_MAX_BANDS / 32 + 1];      // bit b: an accepted peak has pk == b (all zero between frames)
 };
-constexpr int kScratchBytes = (int)(sizeof(unsigned long long) * CSM * ACAP + sizeof(ulonglong2) * PCAP + sizeof(uint2) * PCAP +
-                                    sizeof(unsigned long long) * PCAP + sizeof(int) * PCAP);
+constexpr int kScratchBytes = (int)offsetof(WarpShared, pmask);
 
 struct ScanState {
   int current_frame, no_fm_segs, c_ci, c_started, w, k;
@@ -336,11 +336,12 @@ __device__ __forceinline__ void accumulate_fm(const FaSegmentParams& p, WarpShar
 // O() @B27088, fast path: the segment's tables (T tracks, len rows, n_pts points) fit the per-frame shared-memory bytes
 // that are dead during finalisation.  Same results as finalize_segment below, which works in HBM for any size.
 //   scratch: mean f64[T] | rank u8[T] | slot s8[T] | order u8[T] | rc i32[len] | ro i32[len] | key u32[n_pts]
-//   key = rank << 23 | ordinal << 13 | point << 2 | slot  (T <= 255, ordinal < 1024, point < 2048)
+//   key = rank << 24 | ordinal << 14 | point << 2 | slot  (T <= 255, ordinal < 1024, point < 4096)
+// Returns -3 (nothing changed) when the selected points turn out not to fit: the caller then takes the HBM path.
 __device__ __forceinline__ bool finalize_fits(const ScanState& st, const int len) {
   const int T = st.n_tr;
-  const int need = ((8 * T + 3 * T + 7) & ~7) + 8 * len + 4 * st.n_pts;
-  return T <= 255 && st.n_pts < 2048 && st.c_ci + 1 < 1024 && len < 1024 && need <= kScratchBytes;
+  const int need = ((8 * T + 3 * T + 7) & ~7) + 8 * len;
+  return T <= 255 && st.n_pts < 4096 && st.c_ci + 1 < 1024 && len < 1024 && need + 1024 <= kScratchBytes;
 }
 
 __device__ __noinline__ int finalize_fast(const FaSegmentParams p, WarpShared& S, ScanState& st, const Bases bs,
@@ -408,7 +409,6 @@ __device__ __noinline__ int finalize_fast(const FaSegmentParams p, WarpShared& S
   fa_segment seg;
   seg.start = start; seg.len = len; seg.stored = -1; seg.n_syllables = 0; seg.first_syllable = -1; seg.row_offset = -1;
   seg.ymax = st.y; seg.vmin = st.v; seg.cs_ratio = st.c_energy / st.s_energy;
-  st.n_segs++;
 
   // rows: which points land on which frame row (counting sort by row, in shared memory)
   bool thrown = false;
@@ -423,7 +423,7 @@ __device__ __noinline__ int finalize_fast(const FaSegmentParams p, WarpShared& S
         if (fr < 0 || fr >= len) thrown = true;  // r[d] is undefined -> TypeError -> .catch(L(-1))
         else {
           atomicAdd(&rc[fr], 1);
-          k = ((uint32_t)rank[i] << 23) | ((uint32_t)p.pt_ord[bs.pb + q] << 13) | ((uint32_t)q << 2) | (uint32_t)sl;
+          k = ((uint32_t)rank[i] << 24) | ((uint32_t)p.pt_ord[bs.pb + q] << 14) | ((uint32_t)q << 2) | (uint32_t)sl;
         }
       }
       // park the key in the row_list of HBM until the offsets are known (one coalesced store/load per point)
@@ -432,6 +432,7 @@ __device__ __noinline__ int finalize_fast(const FaSegmentParams p, WarpShared& S
   }
   thrown = __any_sync(FULL, thrown);
   if (thrown) {
+    st.n_segs++;
     if (lane == 0) p.segs[bs.sb + si] = seg;
     return -1;
   }
@@ -450,7 +451,9 @@ __device__ __noinline__ int finalize_fast(const FaSegmentParams p, WarpShared& S
       if (r < len) { ro[r] = run + incl - c; rc[r] = 0; }
       run += __shfl_sync(FULL, incl, 31);
     }
+    if ((int)(reinterpret_cast<unsigned char*>(key) - W) + 4 * run > kScratchBytes) return -3;  // selected points do not fit
   }
+  st.n_segs++;
   __syncwarp();
   for (int q0 = 0; q0 < NP; q0 += 32) {
     const int q = q0 + lane;
@@ -477,7 +480,7 @@ __device__ __noinline__ int finalize_fast(const FaSegmentParams p, WarpShared& S
         if (kz > last && kz < bestkey) bestkey = kz;
       }
       last = bestkey;
-      const int bq = (int)((bestkey >> 2) & 2047);
+      const int bq = (int)((bestkey >> 2) & 4095);
       int sl = (int)(bestkey & 3);
       const int bs_ = p.pt_binspan[bs.pb + bq];
       const int bin = bs_ & 0xffff, span = bs_ >> 16;
@@ -731,8 +734,12 @@ __device__ __forceinline__ int finalize_copy(const FaSegmentParams& p, WarpShare
   const int len = n_arg - st.no_fm_segs;
   if (!(len > p.seg_min_frames && st.c_started >= 2)) return 0;
   ScanState cp = st;
-  const int r = (p.finalize_in_smem && finalize_fits(st, len)) ? finalize_fast(p, S, cp, bs, n_arg, lane)
-                                                                : finalize_segment(p, cp, bs, n_arg, lane);
+  int r = -3;
+  if (p.finalize_in_smem && finalize_fits(st, len)) {
+    r = finalize_fast(p, S, cp, bs, n_arg, lane);
+    st.n_slots = ACAP;  // the track slots were used as scratch: the seg_reset that follows clears all of them
+  }
+  if (r == -3) r = finalize_segment(p, cp, bs, n_arg, lane);
   st.n_segs = cp.n_segs; st.n_stored = cp.n_stored; st.n_rows = cp.n_rows; st.n_syls = cp.n_syls;
   return r;
 }
