@@ -32,6 +32,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# Hardware work queues: with the default of 8, the streams of two batches in flight (1 + sub-batches each) alias onto the
+# same queue and a 1 ms segment scan falsely serialises other streams' kernels (profiles/r1_sweep_overlap.txt).
+# Read by the CUDA driver at context creation, so it has to be set before torch / the library touch the device.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 N_UTT, SECONDS, SR = 1000, 5, 16000
 WORKLOAD = ("C2: 1000 synthetic 5 s 16 kHz utterances per GPU, spectrum + formants output modes + 53-dim Segment "
@@ -156,7 +160,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--serial", action="store_true", help="one sub-batch (profiling: full-batch kernel launches)")
-    ap.add_argument("--pipeline", type=int, default=0, help="sub-batches for the resident timed region (0 = automatic)")
+    ap.add_argument("--pipeline", type=int, default=2, help="sub-batches for the resident timed region (0 = automatic)")
+    ap.add_argument("--depth", type=int, default=2,
+                    help="batches in flight: one handle + stream per batch slot, steps alternate between them so that batch "
+                         "i+1's spectrum kernels overlap batch i's (latency-bound) segment scan and PCIe copies")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -185,17 +192,27 @@ def main():
     pcms = make_workload(rank, n_utt)
     audio_per_step = n_utt * SECONDS
     frames_per_step = n_utt * (SECONDS * SR // 400)
+    depth = 1 if args.serial else max(1, min(args.depth, 4))
     stream = torch.cuda.Stream()
-    eng = Engine(cfg, device=local)
-    eng.set_stream(stream.cuda_stream)
-    eng.set_pipeline(1 if args.serial else args.pipeline)
-    for i, p in enumerate(pcms):
-        eng.submit(i, p, SR)
-    eng.upload()
+    # one handle (+ its own stream and its own resident batch) per batch slot; slot j holds utterances of the same
+    # synthetic family with different seeds, every step is one full pass over one 1000-utterance batch
+    engs, streams = [], []
+    for j in range(depth):
+        e = Engine(cfg, device=local)
+        sj = stream if j == 0 else torch.cuda.Stream()
+        e.set_stream(sj.cuda_stream)
+        e.set_pipeline(1 if args.serial else args.pipeline)
+        batch = pcms if j == 0 else make_workload(rank + 1000 * j, n_utt)
+        for i, p in enumerate(batch):
+            e.submit(i, p, SR)
+        e.upload()
+        engs.append(e)
+        streams.append(sj)
+    eng = engs[0]
 
     # ---- device-resident throughput ----
-    for _ in range(max(3, args.warmup)):
-        eng.run_resident()
+    for k in range(max(3, args.warmup) * depth):
+        engs[k % depth].run_resident()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -203,8 +220,12 @@ def main():
     stage_acc = np.zeros(5)
     barrier()
     ev0.record(stream)
-    for _ in range(args.steps):
-        eng.run_resident()
+    for sj in streams[1:]:
+        sj.wait_event(ev0)
+    for k in range(args.steps):
+        engs[k % depth].run_resident()
+    for sj in streams[1:]:
+        stream.wait_stream(sj)
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -234,41 +255,65 @@ def main():
     e2e = None
     if not args.no_e2e:
         M = cfg.fft_size // 2
-        # the caller's buffers: page-locked host memory for the PCM batch (inputs) and for the dB spectrum (output)
-        spec_host = torch.empty((frames_per_step, M), dtype=torch.float32, pin_memory=True).numpy()
-        pcm_host = torch.empty(sum(p.size for p in pcms), dtype=torch.float32, pin_memory=True).numpy()
+        # the caller's buffers: page-locked host memory for the PCM batches (inputs) and for the dB spectra (outputs);
+        # one set per batch slot.  A step = reset + submit one 1000-utterance batch from HOST memory + run; its results
+        # (spectrum in the sink, every dense table through fa_copy_*) are read back `depth` steps later, after fa_sync,
+        # so the PCIe copies of consecutive batches run back to back.  All K batches are drained inside the timed region.
         offs = np.zeros(n_utt + 1, np.int64)
         offs[1:] = np.cumsum([p.size for p in pcms])
-        for i, p in enumerate(pcms):
-            pcm_host[offs[i]: offs[i + 1]] = p
-        h2d = pcm_host.nbytes
+        spec_hosts, pcm_hosts = [], []
+        for j in range(depth):
+            spec_hosts.append(torch.empty((frames_per_step, M), dtype=torch.float32, pin_memory=True).numpy())
+            ph = torch.empty(int(offs[-1]), dtype=torch.float32, pin_memory=True).numpy()
+            for i, p in enumerate(pcms):
+                ph[offs[i]: offs[i + 1]] = p
+            pcm_hosts.append(ph)
+        h2d = pcm_hosts[0].nbytes
+        d2h_seen = []
 
-        def e2e_step():
-            eng.reset()
-            eng.submit_batch(0, pcm_host, offs, SR)        # zero copy: H2D reads the pinned caller buffer
-            eng.set_spectrum_sink(spec_host)               # dB rows stream back while later sub-batches compute
-            eng.run()
-            eng.sync()
-            r = eng.result(None)
-            return r, frames_per_step
+        def launch(j):
+            e = engs[j]
+            e.reset()
+            e.submit_batch(0, pcm_hosts[j], offs, SR)     # zero copy: H2D reads the pinned caller buffer
+            e.set_spectrum_sink(spec_hosts[j])             # dB rows stream back while later sub-batches compute
+            e.run()                                        # asynchronous
 
-        for _ in range(2):
-            e2e_step()
+        def collect(j):
+            e = engs[j]
+            e.sync()
+            r = e.result(None)
+            d2h_seen.append(spec_hosts[j].nbytes + r.segments.nbytes + r.formants.nbytes + r.energy.nbytes +
+                            r.features.nbytes + r.syllables.nbytes)
+            return r
+
+        def e2e_steps(k_steps):
+            inflight = []
+            for k in range(k_steps):
+                j = k % depth
+                if len(inflight) == depth:
+                    collect(inflight.pop(0))
+                launch(j)
+                inflight.append(j)
+            while inflight:
+                collect(inflight.pop(0))
+
+        for e in engs:
+            e.set_pipeline(1 if args.serial else 0)
+        e2e_steps(2 * depth)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            r, n = e2e_step()
+        e2e_steps(args.steps)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        d2h = spec_host.nbytes + r.segments.nbytes + r.formants.nbytes + r.energy.nbytes + r.features.nbytes + r.syllables.nbytes
+        d2h = d2h_seen[-1]
         e2e = {"value": world * audio_per_step * args.steps / float(tt.item()), "unit": "audio-s/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": 1e3 * float(tt.item()) / args.steps,
-               "path": "fa_reset + fa_submit_pcm_batch (pinned host PCM) + fa_set_spectrum_sink (pinned) + fa_run + fa_sync + "
-                       "fa_copy_{segments,formants,energy,syllables,features}"}
+               "ms_per_step": 1e3 * float(tt.item()) / args.steps, "batches_in_flight": depth,
+               "path": "per batch: fa_reset + fa_submit_pcm_batch (pinned host PCM) + fa_set_spectrum_sink (pinned) + fa_run "
+                       "(async) ... fa_sync + fa_copy_{segments,formants,energy,syllables,features}; one handle per batch slot"}
 
     clocks = sampler.stop()
     if rank == 0:
@@ -296,6 +341,7 @@ def main():
             "vs_baseline": None, "dtype": "f32 spectrum / u32 peaks / f64 features", "data": "synthetic",
             "frames_per_sec": world * frames_per_step * args.steps / (ms_max / 1e3),
             "config": {"workload": WORKLOAD, "utterances_per_gpu": n_utt, "parallelism": f"shard-by-utterance x{world}",
+                       "batches_in_flight": depth,
                        "l2": "inputs (320 MB PCM + 819 MB spectrum rows per step) exceed the 126 MB L2; no flush needed"},
             "roofline": {"bound": "hbm", "kernel": {"spectrum": "fa_spectrum_2048_kernel", "peaks": "fa_peaks_kernel",
                                                     "segment": "fa_segment_kernel", "features": "fa_features_kernel"}[top],
@@ -320,7 +366,8 @@ def main():
                                     "frames_per_sec": fr / dt,
                                     "sample": f"first {len(sub)} of {n_utt} utterances ({len(sub) * SECONDS} s of audio), C oracle, OpenMP over utterances"}
         print(json.dumps(line))
-    eng.close()
+    for e in engs:
+        e.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

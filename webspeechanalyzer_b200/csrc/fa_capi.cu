@@ -102,7 +102,9 @@ struct fa_handle {
   float* spec_sink = nullptr;  // caller-owned destination of the dB rows (filled during fa_run)
   size_t spec_sink_rows = 0;
   cudaStream_t sub_stream[kMaxSub] = {};
-  cudaEvent_t sub_done[kMaxSub] = {};
+  cudaStream_t sub_hi[kMaxSub] = {};    // high-priority streams for the latency-bound segment scan + features of a sub-batch
+  cudaEvent_t sub_done[kMaxSub] = {}, sub_mid[kMaxSub] = {}, sub_hi_done[kMaxSub] = {};
+  bool k3_priority = false;  // FA_K3_PRIO=1: measured slower on C2 (profiles/r1_sweep_overlap.txt), kept as a knob
   cudaEvent_t fork_ev = nullptr;
   bool prepared = false;
   long long total_frames = 0;
@@ -114,7 +116,7 @@ struct fa_handle {
   DevBuf g_segs, g_syls, g_formants, g_energy, g_features;
   int n_weights = 0;
   long long track_total = 0;
-  bool uploaded = false, ran = false, downloaded = false, want_spec = false;
+  bool uploaded = false, ran = false, downloaded = false, want_spec = false, from_host = false;
   long long tot[4] = {0, 0, 0, 0};  // segs, rows, syls, feat
   cudaEvent_t ev[8] = {};
   float stage_ms[5] = {0, 0, 0, 0, 0};
@@ -265,9 +267,15 @@ int fa_create(const fa_config* cfg, int device, fa_handle** out) {
   }
   h->stream = h->own_stream;
   for (auto& e : h->ev) cudaEventCreate(&e);
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lowest = greatest priority
+  if (const char* ev = getenv("FA_K3_PRIO")) h->k3_priority = atoi(ev) != 0;
   for (int i = 0; i < kMaxSub; i++) {
     cudaStreamCreateWithFlags(&h->sub_stream[i], cudaStreamNonBlocking);
+    cudaStreamCreateWithPriority(&h->sub_hi[i], cudaStreamNonBlocking, prio_hi);
     cudaEventCreateWithFlags(&h->sub_done[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->sub_mid[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->sub_hi_done[i], cudaEventDisableTiming);
   }
   cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming);
   h->want_spec = cfg->want_spectrum || cfg->output_level <= 2;
@@ -281,6 +289,7 @@ int fa_destroy(fa_handle* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   for (int i = 0; i < kMaxSub; i++) if (h->sub_stream[i]) cudaStreamSynchronize(h->sub_stream[i]);
+  for (int i = 0; i < kMaxSub; i++) if (h->sub_hi[i]) cudaStreamSynchronize(h->sub_hi[i]);
   for (DevBuf* b : {&h->d_pcm, &h->d_meta, &h->d_spec, &h->d_frames, &h->d_cand, &h->d_ncand, &h->d_gsum, &h->d_counter,
                     &h->d_win, &h->d_tw, &h->d_tws, &h->d_ws, &h->d_bmi, &h->d_bmw, &h->d_emph, &h->d_spill, &h->d_trkbase, &h->d_trk_i,
                     &h->d_trk_d, &h->d_trk_slot, &h->d_pt_i, &h->d_pt_e, &h->d_rows, &h->d_rowlist, &h->d_segs, &h->d_syls,
@@ -293,7 +302,10 @@ int fa_destroy(fa_handle* h) {
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (int i = 0; i < kMaxSub; i++) {
     if (h->sub_done[i]) cudaEventDestroy(h->sub_done[i]);
+    if (h->sub_mid[i]) cudaEventDestroy(h->sub_mid[i]);
+    if (h->sub_hi_done[i]) cudaEventDestroy(h->sub_hi_done[i]);
     if (h->sub_stream[i]) cudaStreamDestroy(h->sub_stream[i]);
+    if (h->sub_hi[i]) cudaStreamDestroy(h->sub_hi[i]);
   }
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -553,7 +565,11 @@ static int copy_pcm_range(fa_handle* h, int u0, int u1, cudaStream_t s) {
 }
 
 // stages 1-4 of one sub-batch on stream s
-static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s, cudaEvent_t* ev /* 5 or null */) {
+// (s3 != s: the segment scan + features go to the high-priority stream s3 so that their few, long-lived warps are placed
+// ahead of the queued spectrum CTAs of other sub-batches / batches and run beside them)
+static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s, cudaEvent_t* ev /* 5 or null */,
+                      cudaStream_t s3 = nullptr) {
+  if (!s3) s3 = s;
   const fa_config& c = h->cfg;
   const int n = (int)h->utts.size();
   const long long F = h->total_frames;
@@ -589,6 +605,10 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
     if (getenv("FA_DEBUG_SYNC")) FA_CUDA(cudaStreamSynchronize(s));
   }
   if (ev) FA_CUDA(cudaEventRecord(ev[2], s));
+  if (s3 != s && c.output_level >= 3) {
+    FA_CUDA(cudaEventRecord(h->sub_mid[slot], s));
+    FA_CUDA(cudaStreamWaitEvent(s3, h->sub_mid[slot], 0));
+  }
   if (c.output_level >= 3) {
     const size_t T = (size_t)std::max<long long>(h->track_total, 1);
     const size_t P = (size_t)std::max<long long>(F, 1) * h->maxp;
@@ -618,7 +638,7 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
     g.formants = h->d_formants.as<float>(); g.energy = h->d_energy.as<float>();
     int* cnt = h->d_counts.as<int>();
     g.n_segs = cnt; g.n_stored = cnt + n; g.n_rows = cnt + 2 * n; g.n_syls = cnt + 3 * n; g.overflow = cnt + 5 * n;
-    FA_CUDA(fa_launch_segment(g, s, &h->launches));
+    FA_CUDA(fa_launch_segment(g, s3, &h->launches));
     if (ev) FA_CUDA(cudaEventRecord(ev[3], s));
     if (c.output_level == 5 || c.output_level == 13) {
       FaFeatureParams fp;
@@ -626,8 +646,9 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
       fp.utt_begin = sb.u0; fp.utt_count = sb.u1 - sb.u0;
       fp.segs = g.segs; fp.n_segs = g.n_segs; fp.syls = g.syls; fp.n_syls = g.n_syls; fp.formants = g.formants;
       fp.features = h->d_features.as<double>(); fp.n_feat = cnt + 4 * n;
-      FA_CUDA(fa_launch_features(fp, s, &h->launches));
+      FA_CUDA(fa_launch_features(fp, s3, &h->launches));
     }
+    if (s3 != s) FA_CUDA(cudaEventRecord(h->sub_hi_done[slot], s3));
     if (ev) FA_CUDA(cudaEventRecord(ev[4], s));
   } else if (ev) {
     FA_CUDA(cudaEventRecord(ev[3], s));
@@ -662,11 +683,13 @@ static int run_device(fa_handle* h, bool with_h2d, bool with_sink) {
       cudaStream_t ss = h->sub_stream[b];
       FA_CUDA(cudaStreamWaitEvent(ss, h->fork_ev, 0));
       if (with_h2d) { const int rc = copy_pcm_range(h, subs[b].u0, subs[b].u1, ss); if (rc != FA_OK) return rc; }
-      const int rc = launch_sub(h, subs[b], (int)b, ss, nullptr);
+      const bool hi = h->k3_priority && c.output_level >= 3;
+      const int rc = launch_sub(h, subs[b], (int)b, ss, nullptr, hi ? h->sub_hi[b] : nullptr);
       if (rc != FA_OK) return rc;
       if (sink && subs[b].r1 > subs[b].r0)
         FA_CUDA(cudaMemcpyAsync(h->spec_sink + (size_t)subs[b].r0 * h->M, h->d_spec.as<float>() + (size_t)subs[b].r0 * h->M,
                                 (size_t)(subs[b].r1 - subs[b].r0) * h->M * sizeof(float), cudaMemcpyDeviceToHost, ss));
+      if (hi) FA_CUDA(cudaStreamWaitEvent(ss, h->sub_hi_done[b], 0));
       FA_CUDA(cudaEventRecord(h->sub_done[b], ss));
     }
     for (size_t b = 0; b < subs.size(); b++) FA_CUDA(cudaStreamWaitEvent(s, h->sub_done[b], 0));
@@ -709,6 +732,7 @@ int fa_run_resident(fa_handle* h) {
   if (!h) return FA_ERR_INVALID_ARG;
   if (!h->uploaded) return fail(h, FA_ERR_NOT_RUN, "fa_run_resident before fa_upload");
   cudaSetDevice(h->device);
+  h->from_host = false;
   return run_device(h, false, false);
 }
 
@@ -753,9 +777,10 @@ int fa_run(fa_handle* h) {
   int rc = prepare(h);
   if (rc != FA_OK) return rc;
   h->uploaded = true;
-  rc = run_device(h, true, true);
-  if (rc != FA_OK) return rc;
-  return fa_download(h);
+  h->from_host = true;
+  // asynchronous: nothing here waits for the device, so several handles can be driven from one host thread (batch i+1's
+  // H2D and kernels overlap batch i's spectrum D2H); the dense result tables are fetched by fa_sync
+  return run_device(h, true, true);
 }
 
 int fa_sync(fa_handle* h) {
@@ -765,6 +790,11 @@ int fa_sync(fa_handle* h) {
   if (h->ran) {
     for (int i = 0; i < 4; i++) cudaEventElapsedTime(&h->stage_ms[i], h->ev[i], h->ev[i + 1]);
     cudaEventElapsedTime(&h->stage_ms[4], h->ev[0], h->ev[5]);
+    if (h->from_host && !h->downloaded) {  // fa_run: the table sizes are known now; fetch the dense tables
+      const int rc = fa_download(h);
+      if (rc != FA_OK) return rc;
+      FA_CUDA(cudaStreamSynchronize(h->stream));
+    }
   }
   return FA_OK;
 }

@@ -744,7 +744,9 @@ __device__ __forceinline__ int finalize_copy(const FaSegmentParams& p, WarpShare
   return r;
 }
 
-__global__ void __launch_bounds__(128) fa_segment_kernel(const FaSegmentParams p) {
+// kBound only sets the register cap (65536 / kBound): 128 -> 127 registers, 640 -> 96, 1024 -> 64
+template <int kBound>
+__global__ void __launch_bounds__(kBound) fa_segment_kernel(const FaSegmentParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpShared* sh = reinterpret_cast<WarpShared*>(smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -893,9 +895,16 @@ cudaError_t fa_launch_segment(const FaSegmentParams& p, cudaStream_t s, int* lau
   if (const char* ev = getenv("FA_K3_WARPS")) { const int v = atoi(ev); if (v >= 1 && v <= 4) kw = v; }  // tuning knob
   const int grid = (p.utt_count + kw - 1) / kw;
   const int bytes = (int)sizeof(WarpShared) * kw;
-  cudaError_t e = cudaFuncSetAttribute(fa_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e != cudaSuccess) return e;
-  fa_segment_kernel<<<grid, kw * 32, bytes, s>>>(p);
+  static int regs = -1;
+  if (regs < 0) { const char* ev = getenv("FA_K3_REGS"); regs = ev ? atoi(ev) : 128; }
+  auto launch = [&](auto kernel) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, kw * 32, bytes, s>>>(p);
+    return cudaGetLastError();
+  };
+  const cudaError_t e = regs <= 64 ? launch(fa_segment_kernel<1024>) : regs <= 96 ? launch(fa_segment_kernel<640>)
+                                                                                   : launch(fa_segment_kernel<128>);
   if (launches) (*launches)++;
-  return cudaGetLastError();
+  return e;
 }
