@@ -590,6 +590,12 @@ static int finalize_segment(fao_state* st, fao_result* R, int n_arg) {
     int np = 0;
     for (int t = 0; t < st->n_tr; t++) np += st->tr[t].count;
     fprintf(stderr, "FAO_SEG T=%d NP=%d len=%d cci=%d nr=%d\n", st->n_tr, np, len, st->c_ci, nr);
+    for (int t = 0; t < st->n_tr; t++) {   /* frame labels of a track: increasing, except a stale first label */
+      const fao_track* tk = &st->tr[t];
+      for (int i = 1; i < tk->frames.n; i++)
+        if (tk->frames.d[i] <= tk->frames.d[i - 1])
+          fprintf(stderr, "FAO_SEG   track %d point %d: label %d after %d\n", t, i, tk->frames.d[i], tk->frames.d[i - 1]);
+    }
   }
   ivec_push(&R->seg_start, start);
   ivec_push(&R->seg_len, len);

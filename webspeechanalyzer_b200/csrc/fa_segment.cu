@@ -410,24 +410,60 @@ __device__ __noinline__ int finalize_fast(const FaSegmentParams p, WarpShared& S
   seg.start = start; seg.len = len; seg.stored = -1; seg.n_syllables = 0; seg.first_syllable = -1; seg.row_offset = -1;
   seg.ymax = st.y; seg.vmin = st.v; seg.cs_ratio = st.c_energy / st.s_energy;
 
-  // rows: which points land on which frame row (counting sort by row, in shared memory)
-  bool thrown = false;
-  for (int q0 = 0; q0 < NP; q0 += 32) {
-    const int q = q0 + lane;
-    if (q < NP) {
-      const int i = p.pt_track[bs.pb + q];
-      const int sl = slot[i];
-      uint32_t k = 0xffffffffu;
-      if (sl >= 0) {
-        const int fr = p.pt_frame[bs.pb + q];
-        if (fr < 0 || fr >= len) thrown = true;  // r[d] is undefined -> TypeError -> .catch(L(-1))
-        else {
-          atomicAdd(&rc[fr], 1);
-          k = ((uint32_t)rank[i] << 24) | ((uint32_t)p.pt_ord[bs.pb + q] << 14) | ((uint32_t)q << 2) | (uint32_t)sl;
-        }
+  // rows: which points land on which frame row.  The pool is appended call by call and the label of a call (the stale
+  // c_ci of its frame, quirk #1) grows strictly from the second call of the epoch on, so the points of one row are
+  // contiguous in the pool -- except the run at the pool's head (the first call, whose stale label is arbitrary and may
+  // name a row that comes again later).  One pass therefore does everything: select (track has a slot), check for the
+  // reference's TypeError, compact the selected points' keys into shared memory in pool order, and note where each
+  // row's keys start; the head run is kept as a second key range [0, x_cnt) of row x_row.
+  const unsigned lt = (1u << lane) - 1u;
+  const int cap_keys = (kScratchBytes - (int)(reinterpret_cast<unsigned char*>(key) - W)) / 4;
+  bool thrown = false, nofit = false;
+  int n_sel = 0, x_row = -1, x_cnt = 0, last_label = -1;
+  {
+    const int label0 = NP > 0 ? p.pt_frame[bs.pb] : -1;
+    bool in_head = true;
+    int tr_n = 0, fr_n = 0, od_n = 0;
+    if (lane < NP) { tr_n = p.pt_track[bs.pb + lane]; fr_n = p.pt_frame[bs.pb + lane]; od_n = p.pt_ord[bs.pb + lane]; }
+    for (int q0 = 0; q0 < NP; q0 += 32) {
+      const int q = q0 + lane;
+      const int i = tr_n, fr = fr_n, od = od_n;
+      if (q + 32 < NP) {  // next chunk's loads fly while this one is processed
+        tr_n = p.pt_track[bs.pb + q + 32]; fr_n = p.pt_frame[bs.pb + q + 32]; od_n = p.pt_ord[bs.pb + q + 32];
       }
-      // park the key in the row_list of HBM until the offsets are known (one coalesced store/load per point)
-      p.row_list[bs.pb + q] = (int)k;
+      const bool valid = q < NP;
+      int head_end = 32;
+      if (in_head) {
+        const unsigned diff = __ballot_sync(FULL, valid && fr != label0);
+        if (diff) { head_end = __ffs(diff) - 1; in_head = false; }
+      } else head_end = 0;
+      const int sl = valid ? slot[i] : -1;
+      bool sel = sl >= 0;
+      if (sel && (fr < 0 || fr >= len)) { thrown = true; sel = false; }  // r[d] is undefined -> TypeError -> .catch(L(-1))
+      const unsigned sm = __ballot_sync(FULL, sel);
+      if (sm) {
+        const unsigned before = sm & lt;
+        const int pos = n_sel + __popc(before);
+        const int prev_lane = before ? 31 - __clz(before) : 0;
+        const bool head = lane < head_end;
+        const int lab = head ? -1 : fr;   // a head point never continues a row (its row may come again much later)
+        int prev_label = __shfl_sync(FULL, lab, prev_lane);
+        if (!before) prev_label = last_label;
+        if (sel) {
+          if (pos >= cap_keys) nofit = true;
+          else {
+            key[pos] = ((uint32_t)rank[i] << 24) | ((uint32_t)od << 14) | ((uint32_t)q << 2) | (uint32_t)sl;
+            if (!head) {
+              if (fr != prev_label) ro[fr] = pos;   // first selected point of its row
+              atomicAdd(&rc[fr], 1);
+            }
+          }
+        }
+        const unsigned hm = sm & (head_end >= 32 ? FULL : (1u << head_end) - 1u);
+        if (hm) { x_cnt += __popc(hm); x_row = label0; }
+        n_sel += __popc(sm);
+        last_label = __shfl_sync(FULL, lab, 31 - __clz(sm));
+      }
     }
   }
   thrown = __any_sync(FULL, thrown);
@@ -436,47 +472,26 @@ __device__ __noinline__ int finalize_fast(const FaSegmentParams p, WarpShared& S
     if (lane == 0) p.segs[bs.sb + si] = seg;
     return -1;
   }
-  __syncwarp();
-  {
-    int run = 0;
-    for (int r0 = 0; r0 < len; r0 += 32) {
-      const int r = r0 + lane;
-      const int c = r < len ? rc[r] : 0;
-      int incl = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += t;
-      }
-      if (r < len) { ro[r] = run + incl - c; rc[r] = 0; }
-      run += __shfl_sync(FULL, incl, 31);
-    }
-    if ((int)(reinterpret_cast<unsigned char*>(key) - W) + 4 * run > kScratchBytes) return -3;  // selected points do not fit
-  }
+  if (__any_sync(FULL, nofit)) return -3;  // selected points do not fit: nothing but scratch was touched
   st.n_segs++;
-  __syncwarp();
-  for (int q0 = 0; q0 < NP; q0 += 32) {
-    const int q = q0 + lane;
-    if (q < NP) {
-      const uint32_t k = (uint32_t)p.row_list[bs.pb + q];
-      if (k != 0xffffffffu) {
-        const int fr = p.pt_frame[bs.pb + q];
-        key[ro[fr] + atomicAdd(&rc[fr], 1)] = k;
-      }
-    }
-  }
   __syncwarp();
   // apply: lane per row, points ordered by (track rank, point ordinal)
   float* Fout = p.formants + (size_t)(bs.row0 + st.n_rows) * 9;
   float* Eout = p.energy + (size_t)(bs.row0 + st.n_rows) * 3;
   for (int fr = lane; fr < len; fr += 32) {
-    const int k = rc[fr], off = ro[fr];
+    const int k1 = rc[fr], off = k1 ? ro[fr] : 0;
+    const int k2 = fr == x_row ? x_cnt : 0;   // the head run's keys sit at [0, x_cnt)
+    const int k = k1 + k2;
     float f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0, f6 = 0, f7 = 0, f8 = 0, g0 = 0, g1 = 0, g2 = 0;
     long long last = -1;
     for (int it = 0; it < k; it++) {
       long long bestkey = 0x7fffffffffffffffll;
-      for (int z = 0; z < k; z++) {
+      for (int z = 0; z < k1; z++) {
         const long long kz = (long long)key[off + z];
+        if (kz > last && kz < bestkey) bestkey = kz;
+      }
+      for (int z = 0; z < k2; z++) {
+        const long long kz = (long long)key[z];
         if (kz > last && kz < bestkey) bestkey = kz;
       }
       last = bestkey;
