@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--serial", action="store_true", help="one sub-batch (profiling: full-batch kernel launches)")
     ap.add_argument("--pipeline", type=int, default=2, help="sub-batches for the resident timed region (0 = automatic)")
+    ap.add_argument("--e2e-pipeline", type=int, default=0, help="sub-batches of an e2e step (0 = automatic)")
     ap.add_argument("--depth", type=int, default=2,
                     help="batches in flight: one handle + stream per batch slot, steps alternate between them so that batch "
                          "i+1's spectrum kernels overlap batch i's (latency-bound) segment scan and PCIe copies")
@@ -297,8 +298,10 @@ def main():
             while inflight:
                 collect(inflight.pop(0))
 
+        copy_stream = torch.cuda.Stream()
         for e in engs:
-            e.set_pipeline(1 if args.serial else 0)
+            e.set_pipeline(1 if args.serial else args.e2e_pipeline)
+            e.set_d2h_stream(copy_stream.cuda_stream)   # the batches' dB rows leave in submission order (FIFO on PCIe)
         e2e_steps(2 * depth)
         barrier()
         t0 = time.perf_counter()

@@ -144,6 +144,10 @@ FA_API const char* fa_last_error(const fa_handle* h);
 /* Use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the handle's own. */
 FA_API int fa_set_stream(fa_handle* h, void* cuda_stream);
 
+/* Stream for the spectrum-sink D2H copies (NULL restores the handle's own).  Handles that share one copy stream send their
+ * dB rows back in submission order, one batch after the other, instead of interleaving on the PCIe link. */
+FA_API int fa_set_d2h_stream(fa_handle* h, void* cuda_stream);
+
 /* Number of sub-batches a run is split into (each on its own forked stream so that H2D, the kernels of different
  * sub-batches and the spectrum D2H overlap; at most 16): 0 = automatic, 1 = serial (per-stage timings are only defined then). */
 FA_API int fa_set_pipeline(fa_handle* h, int n_sub_batches);

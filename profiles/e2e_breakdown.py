@@ -1,20 +1,44 @@
-import sys, time; sys.path.insert(0, '.')
+"""Host-side breakdown of the e2e step (two batches in flight): where the wall time of launch / wait / result goes.
+usage (GPU box): python profiles/e2e_breakdown.py"""
+import os, sys, time
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from bench import make_workload, bench_config, SR
 from webspeechanalyzer_b200 import Engine
+
 cfg = bench_config(); pcms = make_workload(0, 1000)
-eng = Engine(cfg)
-spec_host = torch.empty((200000, 1024), dtype=torch.float32, pin_memory=True).numpy()
-def step():
-    t=[time.perf_counter()]
-    eng.reset(); t.append(time.perf_counter())
-    for i,p in enumerate(pcms): eng.submit(i,p,SR)
-    t.append(time.perf_counter())
-    eng.run(); t.append(time.perf_counter())
-    eng.sync(); t.append(time.perf_counter())
-    r = eng.result(None); t.append(time.perf_counter())
-    n = eng._check(eng._lib.fa_copy_spectrum(eng._h, -1, spec_host.ctypes.data, 200000)); t.append(time.perf_counter())
-    return np.diff(t)*1e3
-for _ in range(3): step()
-d = np.mean([step() for _ in range(5)], axis=0)
-print('reset %.2f submit %.2f run(call) %.2f sync %.2f result %.2f spectrum %.2f ms total %.2f' % (*d, d.sum()))
+depth = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+sink = (sys.argv[2] != "nosink") if len(sys.argv) > 2 else True
+offs = np.zeros(1001, np.int64); offs[1:] = np.cumsum([p.size for p in pcms])
+engs, specs, pcmh = [], [], []
+cs = torch.cuda.Stream()
+for j in range(depth):
+    e = Engine(cfg); e.set_d2h_stream(cs.cuda_stream); engs.append(e)
+    specs.append(torch.empty((200000, 1024), dtype=torch.float32, pin_memory=True).numpy())
+    ph = torch.empty(int(offs[-1]), dtype=torch.float32, pin_memory=True).numpy()
+    for i, p in enumerate(pcms): ph[offs[i]:offs[i + 1]] = p
+    pcmh.append(ph)
+T = {"reset": 0.0, "submit": 0.0, "run": 0.0, "sync": 0.0, "result": 0.0}
+def launch(j):
+    e = engs[j]
+    t0 = time.perf_counter(); e.reset(); t1 = time.perf_counter()
+    e.submit_batch(0, pcmh[j], offs, SR); e.set_spectrum_sink(specs[j] if sink else None); t2 = time.perf_counter()
+    e.run(); t3 = time.perf_counter()
+    T["reset"] += t1 - t0; T["submit"] += t2 - t1; T["run"] += t3 - t2
+def collect(j):
+    e = engs[j]
+    t0 = time.perf_counter(); e.sync(); t1 = time.perf_counter(); r = e.result(None); t2 = time.perf_counter()
+    T["sync"] += t1 - t0; T["result"] += t2 - t1
+def steps(k):
+    fl = []
+    for i in range(k):
+        j = i % depth
+        if len(fl) == depth: collect(fl.pop(0))
+        launch(j); fl.append(j)
+    while fl: collect(fl.pop(0))
+steps(2 * depth)
+for k in T: T[k] = 0.0
+K = 10
+t0 = time.perf_counter(); steps(K); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+print(f"depth {depth} sink {sink}: {1e3*dt/K:.2f} ms/step; host ms/step: " + ", ".join(f"{k} {1e3*v/K:.2f}" for k, v in T.items()))

@@ -104,6 +104,14 @@ struct fa_handle {
   cudaStream_t sub_stream[kMaxSub] = {};
   cudaStream_t sub_hi[kMaxSub] = {};    // high-priority streams for the latency-bound segment scan + features of a sub-batch
   cudaEvent_t sub_done[kMaxSub] = {}, sub_mid[kMaxSub] = {}, sub_hi_done[kMaxSub] = {};
+  cudaEvent_t spec_done[kMaxSub] = {}, copy_done[kMaxSub] = {};
+  cudaStream_t own_copy_stream = nullptr, copy_stream = nullptr;
+  // FA_TRACE=1: CUDA-event time stamps of every sub-batch (kernels start / spectrum done / D2H start / D2H end) against a
+  // process-wide base event, printed by fa_sync (profiles/e2e_timeline)
+  int prio_hi = 0, n_sub_streams = 0;
+  bool trace = false;
+  int trace_seq = 0;
+  cudaEvent_t tr_ev[kMaxSub][4] = {};  // spectrum-sink D2H, in sub-batch order (fa_set_d2h_stream)
   bool k3_priority = false;  // FA_K3_PRIO=1: measured slower on C2 (profiles/r1_sweep_overlap.txt), kept as a knob
   cudaEvent_t fork_ev = nullptr;
   bool prepared = false;
@@ -270,13 +278,12 @@ int fa_create(const fa_config* cfg, int device, fa_handle** out) {
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lowest = greatest priority
   if (const char* ev = getenv("FA_K3_PRIO")) h->k3_priority = atoi(ev) != 0;
-  for (int i = 0; i < kMaxSub; i++) {
-    cudaStreamCreateWithFlags(&h->sub_stream[i], cudaStreamNonBlocking);
-    cudaStreamCreateWithPriority(&h->sub_hi[i], cudaStreamNonBlocking, prio_hi);
-    cudaEventCreateWithFlags(&h->sub_done[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->sub_mid[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->sub_hi_done[i], cudaEventDisableTiming);
-  }
+  if (const char* ev = getenv("FA_TRACE")) h->trace = atoi(ev) != 0;
+
+  // Streams are created on first use (ensure_sub_streams): the device has at most 32 hardware work queues
+  // (CUDA_DEVICE_MAX_CONNECTIONS, default 8) and streams beyond that alias onto the same queue, where a stream that waits
+  // for a long D2H falsely blocks its queue mates -- measured: with 34 streams per handle two handles never overlapped.
+  h->prio_hi = prio_hi;
   cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming);
   h->want_spec = cfg->want_spectrum || cfg->output_level <= 2;
   h->regions.push_back(Region{nullptr, 0, 0});
@@ -304,10 +311,14 @@ int fa_destroy(fa_handle* h) {
     if (h->sub_done[i]) cudaEventDestroy(h->sub_done[i]);
     if (h->sub_mid[i]) cudaEventDestroy(h->sub_mid[i]);
     if (h->sub_hi_done[i]) cudaEventDestroy(h->sub_hi_done[i]);
+    if (h->spec_done[i]) cudaEventDestroy(h->spec_done[i]);
+    if (h->copy_done[i]) cudaEventDestroy(h->copy_done[i]);
+    for (int k = 0; k < 4; k++) if (h->tr_ev[i][k]) cudaEventDestroy(h->tr_ev[i][k]);
     if (h->sub_stream[i]) cudaStreamDestroy(h->sub_stream[i]);
     if (h->sub_hi[i]) cudaStreamDestroy(h->sub_hi[i]);
   }
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+  if (h->own_copy_stream) { cudaStreamSynchronize(h->own_copy_stream); cudaStreamDestroy(h->own_copy_stream); }
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return FA_OK;
@@ -320,6 +331,14 @@ int fa_set_stream(fa_handle* h, void* s) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   h->stream = s ? reinterpret_cast<cudaStream_t>(s) : h->own_stream;
+  return FA_OK;
+}
+
+int fa_set_d2h_stream(fa_handle* h, void* s) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  h->copy_stream = s ? reinterpret_cast<cudaStream_t>(s) : h->own_copy_stream;
   return FA_OK;
 }
 
@@ -513,13 +532,28 @@ static int prepare(fa_handle* h) {
   return FA_OK;
 }
 
+static int ensure_sub_streams(fa_handle* h, int n) {
+  for (int i = h->n_sub_streams; i < n && i < kMaxSub; i++) {
+    FA_CUDA(cudaStreamCreateWithFlags(&h->sub_stream[i], cudaStreamNonBlocking));
+    if (h->k3_priority) FA_CUDA(cudaStreamCreateWithPriority(&h->sub_hi[i], cudaStreamNonBlocking, h->prio_hi));
+    FA_CUDA(cudaEventCreateWithFlags(&h->sub_done[i], cudaEventDisableTiming));
+    FA_CUDA(cudaEventCreateWithFlags(&h->sub_mid[i], cudaEventDisableTiming));
+    FA_CUDA(cudaEventCreateWithFlags(&h->sub_hi_done[i], cudaEventDisableTiming));
+    FA_CUDA(cudaEventCreateWithFlags(&h->spec_done[i], cudaEventDisableTiming));
+    FA_CUDA(cudaEventCreateWithFlags(&h->copy_done[i], cudaEventDisableTiming));
+    if (h->trace) for (int k = 0; k < 4; k++) FA_CUDA(cudaEventCreate(&h->tr_ev[i][k]));
+    h->n_sub_streams = i + 1;
+  }
+  return FA_OK;
+}
+
 // split the batch into sub-batches of whole utterances with about equal frame counts
 static std::vector<SubBatch> plan(const fa_handle* h, bool with_copies) {
   const int n = (int)h->utts.size();
   int S = h->pipeline;
   // automatic: many sub-batches when PCIe copies have to overlap the kernels, few when the data is resident (every
   // stage but K1a is a per-utterance latency chain, so extra sub-batches only add launches)
-  if (S == 0) S = with_copies ? std::min(kMaxSub, std::max(1, n / 60)) : std::min(4, std::max(1, n / 250));
+  if (S == 0) S = with_copies ? std::min(8, std::max(1, n / 60)) : std::min(2, std::max(1, n / 250));
   S = std::max(1, std::min(S, n));
   std::vector<SubBatch> out;
   const long long F = h->total_frames;
@@ -597,6 +631,8 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
   FA_CUDA(fa_launch_spectrum(sp, s, &h->launches));
   if (getenv("FA_DEBUG_SYNC")) FA_CUDA(cudaStreamSynchronize(s));
   if (ev) FA_CUDA(cudaEventRecord(ev[1], s));
+  if (!ev) FA_CUDA(cudaEventRecord(h->spec_done[slot], s));  // the dB rows of this sub-batch are final
+  if (!ev && h->trace) FA_CUDA(cudaEventRecord(h->tr_ev[slot][1], s));
   if (c.output_level >= 3 && sb.r1 > sb.r0) {
     FaPeaksParams pp;
     pp.frames = h->d_frames.as<uint32_t>(); pp.B = h->B; pp.maxp = h->maxp; pp.n_frames = sb.r1 - sb.r0; pp.row_begin = sb.r0;
@@ -678,21 +714,37 @@ static int run_device(fa_handle* h, bool with_h2d, bool with_sink) {
     if (sink && h->total_frames)
       FA_CUDA(cudaMemcpyAsync(h->spec_sink, h->d_spec.p, (size_t)h->total_frames * h->M * sizeof(float), cudaMemcpyDeviceToHost, s));
   } else {
+    { const int rc = ensure_sub_streams(h, (int)subs.size()); if (rc != FA_OK) return rc; }
+    if (sink && !h->copy_stream) {
+      if (!h->own_copy_stream) FA_CUDA(cudaStreamCreateWithFlags(&h->own_copy_stream, cudaStreamNonBlocking));
+      h->copy_stream = h->own_copy_stream;
+    }
     FA_CUDA(cudaEventRecord(h->fork_ev, s));
     for (size_t b = 0; b < subs.size(); b++) {
       cudaStream_t ss = h->sub_stream[b];
       FA_CUDA(cudaStreamWaitEvent(ss, h->fork_ev, 0));
+      if (h->trace) FA_CUDA(cudaEventRecord(h->tr_ev[b][0], ss));
       if (with_h2d) { const int rc = copy_pcm_range(h, subs[b].u0, subs[b].u1, ss); if (rc != FA_OK) return rc; }
       const bool hi = h->k3_priority && c.output_level >= 3;
       const int rc = launch_sub(h, subs[b], (int)b, ss, nullptr, hi ? h->sub_hi[b] : nullptr);
       if (rc != FA_OK) return rc;
-      if (sink && subs[b].r1 > subs[b].r0)
+      if (sink && subs[b].r1 > subs[b].r0) {
+        // the dB rows leave as soon as the spectrum kernels of the sub-batch are done (not behind its segment scan), on
+        // the copy stream: FIFO over sub-batches -- and over batches when several handles share one copy stream
+        FA_CUDA(cudaStreamWaitEvent(h->copy_stream, h->spec_done[b], 0));
+        if (h->trace) FA_CUDA(cudaEventRecord(h->tr_ev[b][2], h->copy_stream));
         FA_CUDA(cudaMemcpyAsync(h->spec_sink + (size_t)subs[b].r0 * h->M, h->d_spec.as<float>() + (size_t)subs[b].r0 * h->M,
-                                (size_t)(subs[b].r1 - subs[b].r0) * h->M * sizeof(float), cudaMemcpyDeviceToHost, ss));
+                                (size_t)(subs[b].r1 - subs[b].r0) * h->M * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+        FA_CUDA(cudaEventRecord(h->copy_done[b], h->copy_stream));
+        if (h->trace) FA_CUDA(cudaEventRecord(h->tr_ev[b][3], h->copy_stream));
+      }
       if (hi) FA_CUDA(cudaStreamWaitEvent(ss, h->sub_hi_done[b], 0));
       FA_CUDA(cudaEventRecord(h->sub_done[b], ss));
     }
-    for (size_t b = 0; b < subs.size(); b++) FA_CUDA(cudaStreamWaitEvent(s, h->sub_done[b], 0));
+    for (size_t b = 0; b < subs.size(); b++) {
+      FA_CUDA(cudaStreamWaitEvent(s, h->sub_done[b], 0));
+      if (sink && subs[b].r1 > subs[b].r0) FA_CUDA(cudaStreamWaitEvent(s, h->copy_done[b], 0));
+    }
     for (int i = 1; i <= 4; i++) FA_CUDA(cudaEventRecord(h->ev[i], s));  // per-stage times only exist in serial mode
   }
   if (c.output_level >= 3) {
@@ -790,6 +842,17 @@ int fa_sync(fa_handle* h) {
   if (h->ran) {
     for (int i = 0; i < 4; i++) cudaEventElapsedTime(&h->stage_ms[i], h->ev[i], h->ev[i + 1]);
     cudaEventElapsedTime(&h->stage_ms[4], h->ev[0], h->ev[5]);
+    if (h->trace && h->from_host) {
+      for (int b = 0; b < h->n_sub_streams; b++) {
+        float t[4] = {-1, -1, -1, -1};
+        bool ok = true;
+        for (int k = 0; k < 4; k++) ok = ok && cudaEventElapsedTime(&t[k], h->ev[0], h->tr_ev[b][k]) == cudaSuccess;
+        cudaGetLastError();
+        if (ok) fprintf(stderr, "FA_TRACE h=%p run=%d sub=%d start=%.3f spec_done=%.3f d2h_start=%.3f d2h_end=%.3f total=%.3f\n",
+                        (void*)h, h->trace_seq, b, t[0], t[1], t[2], t[3], h->stage_ms[4]);
+      }
+      h->trace_seq++;
+    }
     if (h->from_host && !h->downloaded) {  // fa_run: the table sizes are known now; fetch the dense tables
       const int rc = fa_download(h);
       if (rc != FA_OK) return rc;

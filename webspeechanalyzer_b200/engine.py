@@ -76,6 +76,10 @@ class Engine:
     def set_stream(self, cuda_stream_ptr: int | None):
         self._check(self._lib.fa_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
 
+    def set_d2h_stream(self, cuda_stream_ptr: int | None):
+        """Stream of the spectrum-sink D2H copies; engines sharing one send their batches back one after the other."""
+        self._check(self._lib.fa_set_d2h_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
     def reset(self):
         self._check(self._lib.fa_reset(self._h))
 
