@@ -496,7 +496,7 @@ static int prepare(fa_handle* h) {
   FA_CUDA(cudaMemcpyAsync(h->d_meta.p, m, sizeof(long long) * (4 * (size_t)n + 2), cudaMemcpyHostToDevice, s));
   FA_CUDA(h->d_pcm.reserve((size_t)(dev + 16) * sizeof(float)));
   const size_t Fz = (size_t)std::max<long long>(F, 1), nz = (size_t)n;
-  if (h->want_spec || h->N == 2048) FA_CUDA(h->d_spec.reserve(Fz * h->M * sizeof(float)));  // also the K1a -> K1b magnitude rows
+  FA_CUDA(h->d_spec.reserve(Fz * h->M * sizeof(float)));  // the K1a -> K1b magnitude rows, turned into dB rows in place
   FA_CUDA(h->d_frames.reserve(Fz * h->B * sizeof(uint32_t)));
   FA_CUDA(h->d_counter.reserve(2 * kMaxSub * sizeof(int)));
   if (h->cfg.output_level >= 3) {
@@ -622,10 +622,10 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
   sp.gain = fa_tab_gain(&c); sp.tau = (float)c.smoothing; sp.omt = (float)(1.0 - c.smoothing);
   sp.inv2N = (float)(1.0 / (2.0 * (double)h->N)); sp.min_db = (float)c.min_db; sp.max_db = (float)c.max_db;
   sp.clamp_db = c.clamp_db;
-  sp.scratch_mag = h->N == 2048;
+  sp.scratch_mag = 1;
   sp.write_db = h->want_spec;
   sp.n_rows = sb.r1 - sb.r0;
-  sp.spec_db = (h->want_spec || sp.scratch_mag) ? h->d_spec.as<float>() : nullptr;
+  sp.spec_db = h->d_spec.as<float>();
   sp.frames = h->d_frames.as<uint32_t>();
   sp.work_counter = h->d_counter.as<int>() + slot;
   FA_CUDA(fa_launch_spectrum(sp, s, &h->launches));
