@@ -39,30 +39,16 @@ __global__ void __launch_bounds__(kPeakThreads) fa_peaks_kernel(const FaPeaksPar
   // bandwidth energy of accumulate_fm @B35952 as ph - pl without touching the frame again)
   unsigned long long pre = 0, pl = 0, ph = 0;
 
+  // Loop fission against divergence: the automaton runs thread-per-frame, so lanes close their peaks at different bins
+  // and everything inside emit() is executed once per lane and peak.  emit() therefore only parks the raw candidate
+  // (two 16-byte stores into its own output slot); the trim of lo / hi to bins >= e[pk]/10 -- data-dependent loops with
+  // loads -- happens after the scan, candidate index by candidate index, all lanes of the warp together.
   auto emit = [&](int last) {
-    int l2 = lo, h2 = hi;
-    // e[i] < e[pk]/10 in doubles  <=>  10*e[i] < e[pk] in integers (both exact)
-    const unsigned long long top = epk;
-    unsigned long long pl2 = pl, ph2 = ph;
-    for (;;) {
-      if (l2 >= pk) break;
-      const uint32_t x = __ldg(e + l2);
-      if (!(10ull * x < top)) break;
-      pl2 += x;
-      l2++;
-    }
-    for (;;) {
-      if (h2 <= pk) break;
-      const uint32_t x = __ldg(e + h2);
-      if (!(10ull * x < top)) break;
-      ph2 -= x;
-      h2--;
-    }
     if (n < maxp) {
       uint4* o4 = reinterpret_cast<uint4*>(out + n);  // two 16-byte stores into one sector
-      o4[0] = make_uint4((uint32_t)l2 | ((uint32_t)h2 << 8) | ((uint32_t)pk << 16) | ((uint32_t)last << 24), epk,
-                         (uint32_t)pl2, (uint32_t)(pl2 >> 32));
-      o4[1] = make_uint4((uint32_t)ph2, (uint32_t)(ph2 >> 32), 0u, 0u);
+      o4[0] = make_uint4((uint32_t)lo | ((uint32_t)hi << 8) | ((uint32_t)pk << 16) | ((uint32_t)last << 24), epk,
+                         (uint32_t)pl, (uint32_t)(pl >> 32));
+      o4[1] = make_uint4((uint32_t)ph, (uint32_t)(ph >> 32), 0u, 0u);
     }
     n++;
   };
@@ -121,6 +107,37 @@ __global__ void __launch_bounds__(kPeakThreads) fa_peaks_kernel(const FaPeaksPar
   }
   p.ncand[f] = n;
   p.gsum[f] = (double)g;
+  // trim (close() @B25717): while lo < pk and e[lo] < e[pk]/10: lo++; while hi > pk and e[hi] < e[pk]/10: hi--.
+  // e[i] < e[pk]/10 in doubles  <=>  10*e[i] < e[pk] in integers (both exact).  The prefix sums follow the bounds.
+  const int nc = n < maxp ? n : maxp;
+  for (int c = 0; c < nc; c++) {
+    uint4* o4 = reinterpret_cast<uint4*>(out + c);
+    const uint4 a4 = o4[0];
+    const uint2 b2 = *reinterpret_cast<const uint2*>(o4 + 1);
+    int l2 = (int)(a4.x & 0xffu), h2 = (int)((a4.x >> 8) & 0xffu);
+    const int pk2 = (int)((a4.x >> 16) & 0xffu);
+    const unsigned long long top = a4.y;
+    unsigned long long pl2 = a4.z | ((unsigned long long)a4.w << 32), ph2 = b2.x | ((unsigned long long)b2.y << 32);
+    const int l0 = l2, h0 = h2;
+    for (;;) {
+      if (l2 >= pk2) break;
+      const uint32_t x = __ldg(e + l2);
+      if (!(10ull * x < top)) break;
+      pl2 += x;
+      l2++;
+    }
+    for (;;) {
+      if (h2 <= pk2) break;
+      const uint32_t x = __ldg(e + h2);
+      if (!(10ull * x < top)) break;
+      ph2 -= x;
+      h2--;
+    }
+    if (l2 != l0 || h2 != h0) {
+      o4[0] = make_uint4((a4.x & 0xffff0000u) | (uint32_t)l2 | ((uint32_t)h2 << 8), a4.y, (uint32_t)pl2, (uint32_t)(pl2 >> 32));
+      *reinterpret_cast<uint2*>(o4 + 1) = make_uint2((uint32_t)ph2, (uint32_t)(ph2 >> 32));
+    }
+  }
 }
 
 }  // namespace
