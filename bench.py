@@ -7,9 +7,11 @@ spectrum + formants output modes, producing the dB spectrum, the formant rows an
 (output_level 5, fftSize 2048, smoothingTimeConstant 0.8).  With --gpus N every rank runs its own 1000-utterance
 batch (sharded by utterance, no data-path collective) => weak scaling.
 
-  value     audio-seconds per second, inputs resident in HBM, CUDA events on the launching stream, max over ranks
-  e2e       the same metric through the C-ABI with HOST buffers: fa_submit_pcm (host memcpy into pinned staging),
-            H2D, kernels, D2H of every result table and of the dB spectrum, inside the timed region
+  value     audio-seconds per second, inputs resident in HBM, CUDA events on the launching stream, max over ranks;
+            --depth batches in flight (one handle + stream per slot), every step one full pass over one batch
+  e2e       the same metric through the C-ABI with HOST buffers: fa_submit_pcm_batch (pinned caller PCM, zero copy),
+            H2D, kernels, D2H of every result table and of the dB spectrum inside the timed region; --depth batches in
+            flight, all batches drained before the clock stops
   roofline  the dominant kernel's algorithmic bytes / its CUDA-event time vs the measured HBM peak
   cpu_baseline  the CPU oracle (a restatement: kind "port") on the host cores, same workload
 
@@ -61,8 +63,10 @@ def ncu_traffic(kernel: str):
     p = os.path.join(ROOT, "profiles", "r1_ncu_kernels.json")
     if not os.path.exists(p):
         return None
-    d = json.load(open(p)).get(kernel)
-    return None if not d else d.get("dram_bytes")
+    for name, d in json.load(open(p)).items():   # kernel names carry template arguments ("void fa_segment_kernel<128>")
+        if kernel in name:
+            return d.get("dram_bytes")
+    return None
 
 
 def measured_peaks():

@@ -111,7 +111,8 @@ struct fa_handle {
   int prio_hi = 0, n_sub_streams = 0;
   bool trace = false;
   int trace_seq = 0;
-  cudaEvent_t tr_ev[kMaxSub][4] = {};  // spectrum-sink D2H, in sub-batch order (fa_set_d2h_stream)
+  cudaEvent_t tr_ev[kMaxSub][4] = {};
+  cudaEvent_t tr_k[kMaxSub][5] = {};   // resident runs: sub-batch start, after spectrum / peaks / segment / features  // spectrum-sink D2H, in sub-batch order (fa_set_d2h_stream)
   bool k3_priority = false;  // FA_K3_PRIO=1: measured slower on C2 (profiles/r1_sweep_overlap.txt), kept as a knob
   cudaEvent_t fork_ev = nullptr;
   bool prepared = false;
@@ -542,6 +543,7 @@ static int ensure_sub_streams(fa_handle* h, int n) {
     FA_CUDA(cudaEventCreateWithFlags(&h->spec_done[i], cudaEventDisableTiming));
     FA_CUDA(cudaEventCreateWithFlags(&h->copy_done[i], cudaEventDisableTiming));
     if (h->trace) for (int k = 0; k < 4; k++) FA_CUDA(cudaEventCreate(&h->tr_ev[i][k]));
+    if (h->trace) for (int k = 0; k < 5; k++) FA_CUDA(cudaEventCreate(&h->tr_k[i][k]));
     h->n_sub_streams = i + 1;
   }
   return FA_OK;
@@ -609,6 +611,8 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
   const long long F = h->total_frames;
   const long long* meta = h->d_meta.as<long long>();
   if (ev) FA_CUDA(cudaEventRecord(ev[0], s));
+  const bool tr = !ev && h->trace;
+  if (tr) FA_CUDA(cudaEventRecord(h->tr_k[slot][0], s));
   FaSpectrumParams sp;
   memset(&sp, 0, sizeof(sp));
   sp.pcm = h->d_pcm.as<float>();
@@ -633,6 +637,7 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
   if (ev) FA_CUDA(cudaEventRecord(ev[1], s));
   if (!ev) FA_CUDA(cudaEventRecord(h->spec_done[slot], s));  // the dB rows of this sub-batch are final
   if (!ev && h->trace) FA_CUDA(cudaEventRecord(h->tr_ev[slot][1], s));
+  if (tr) FA_CUDA(cudaEventRecord(h->tr_k[slot][1], s));
   if (c.output_level >= 3 && sb.r1 > sb.r0) {
     FaPeaksParams pp;
     pp.frames = h->d_frames.as<uint32_t>(); pp.B = h->B; pp.maxp = h->maxp; pp.n_frames = sb.r1 - sb.r0; pp.row_begin = sb.r0;
@@ -641,6 +646,7 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
     if (getenv("FA_DEBUG_SYNC")) FA_CUDA(cudaStreamSynchronize(s));
   }
   if (ev) FA_CUDA(cudaEventRecord(ev[2], s));
+  if (tr) FA_CUDA(cudaEventRecord(h->tr_k[slot][2], s));
   if (s3 != s && c.output_level >= 3) {
     FA_CUDA(cudaEventRecord(h->sub_mid[slot], s));
     FA_CUDA(cudaStreamWaitEvent(s3, h->sub_mid[slot], 0));
@@ -676,6 +682,7 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
     g.n_segs = cnt; g.n_stored = cnt + n; g.n_rows = cnt + 2 * n; g.n_syls = cnt + 3 * n; g.overflow = cnt + 5 * n;
     FA_CUDA(fa_launch_segment(g, s3, &h->launches));
     if (ev) FA_CUDA(cudaEventRecord(ev[3], s));
+    if (tr) FA_CUDA(cudaEventRecord(h->tr_k[slot][3], s3));
     if (c.output_level == 5 || c.output_level == 13) {
       FaFeatureParams fp;
       fp.frame_off = meta + 2 * n; fp.n_utt = n; fp.level = c.output_level;
@@ -684,6 +691,7 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
       fp.features = h->d_features.as<double>(); fp.n_feat = cnt + 4 * n;
       FA_CUDA(fa_launch_features(fp, s3, &h->launches));
     }
+    if (tr) FA_CUDA(cudaEventRecord(h->tr_k[slot][4], s3));
     if (s3 != s) FA_CUDA(cudaEventRecord(h->sub_hi_done[slot], s3));
     if (ev) FA_CUDA(cudaEventRecord(ev[4], s));
   } else if (ev) {
@@ -842,6 +850,18 @@ int fa_sync(fa_handle* h) {
   if (h->ran) {
     for (int i = 0; i < 4; i++) cudaEventElapsedTime(&h->stage_ms[i], h->ev[i], h->ev[i + 1]);
     cudaEventElapsedTime(&h->stage_ms[4], h->ev[0], h->ev[5]);
+    if (h->trace && !h->from_host) {
+      static cudaEvent_t base = nullptr;   // first traced run of the process: the common time origin of all handles
+      if (!base) base = h->ev[0];
+      for (int b = 0; b < h->n_sub_streams; b++) {
+        float t[5];
+        bool ok = true;
+        for (int k = 0; k < 5; k++) ok = ok && cudaEventElapsedTime(&t[k], base, h->tr_k[b][k]) == cudaSuccess;
+        cudaGetLastError();
+        if (ok) fprintf(stderr, "FA_TRACE_K h=%p sub=%d start=%.3f spectrum_end=%.3f peaks_end=%.3f segment_end=%.3f features_end=%.3f\n",
+                        (void*)h, b, t[0], t[1], t[2], t[3], t[4]);
+      }
+    }
     if (h->trace && h->from_host) {
       for (int b = 0; b < h->n_sub_streams; b++) {
         float t[4] = {-1, -1, -1, -1};
