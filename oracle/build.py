@@ -2,8 +2,9 @@
 TEST INFRASTRUCTURE ONLY.  Builds the CPU oracle (oracle/fa_oracle.c) into oracle/_build/libfa_oracle.so.
 
 The reference itself cannot be compiled (`oracle/_ref`): it is browser JavaScript and this image has no
-JS engine (node / deno / bun / qjs absent) -- see DESIGN.md "Oracle".  So there is no oracle/_ref here;
-where `node` exists, oracle/run_reference_modules.js evaluates the reference's own minified modules.
+JS engine (node / deno / bun / qjs absent) -- see DESIGN.md "Oracle".  So there is no oracle/_ref binary; instead
+oracle/minijs executes the reference's own minified modules in the build container (outputs committed as
+tests/golden/ref_js.json), and where `node` exists oracle/run_reference_modules.js does the same.
 """
 from __future__ import annotations
 

@@ -4,17 +4,21 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * build, load or call this file.  The product (webspeechanalyzer_b200/, libfa_b200.so) never does.
  *
- * PARITY STATUS: "parity unpinned".  The reference (tabahi/WebSpeechAnalyzer) ships no tests, no
- * golden vectors and no runnable engine for this path in this image (browser JavaScript, no JS
- * engine here), and its spectrum stage is an un-vendored CDN worklet.  This file restates
+ * PARITY STATUS: stages S2 / S2b / S3 / S3b / S3c / S4 / T / CB are PINNED against outputs of the
+ * reference's own code: its minified segmentor / formants / stats / utterance modules
  *   - segmentor  /root/reference/dist/main.js:2@B23403-B31782 (inner module 3),
  *   - formants   /root/reference/dist/main.js:2@B31782-B38281 (inner module 4),
  *   - stats      /root/reference/dist/main.js:2@B1065-B2714 == /root/reference/src/stats.js:29-64,
- * and a builder-defined AnalyserNode front end (W3C Web Audio API; DESIGN.md "Front-end spec").
- * It is cross-checked against a second, literal transliteration (oracle/literal/refmodules.py),
- * against the invariants the reference does pin (row width 53: src/localstore.js:7; feature
- * ranges: dist/nnmodel/1/cats_emotion/model_meta.json) and, where `node` exists, against the
- * reference's own minified modules through oracle/run_reference_modules.js.
+ *   - utterance  /root/reference/dist/main.js:2@B107866-B110125 (inner module 7),
+ * were EXECUTED in the build container by oracle/minijs (an ECMAScript-subset interpreter written
+ * for this purpose -- the image has no JS engine) on 72 inputs; their outputs are committed as
+ * tests/golden/ref_js.json and tests/test_reference_js.py holds this file to them bit for bit.
+ * Stage S1 / S1b (spectrum + adapter) remains "parity unpinned" BY NECESSITY: the reference's
+ * spectrum stage is an un-vendored CDN worklet (no code, no vectors), so the front end below is a
+ * builder-defined AnalyserNode restatement (W3C Web Audio API; DESIGN.md "Front-end spec").
+ * Further cross-checks: a literal Python transliteration (oracle/literal/refmodules.py), the
+ * invariants the reference pins (row width 53: src/localstore.js:7; feature ranges:
+ * dist/nnmodel/1/cats_emotion/model_meta.json), and oracle/run_reference_modules.js for Node.
  *
  * Build: gcc -O2 -ffp-contract=off -mfma -fPIC -shared -fopenmp (see oracle/build.py).
  * Floating-point contraction MUST be off: every fused multiply-add below is an explicit fmaf().
