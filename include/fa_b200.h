@@ -39,6 +39,7 @@ extern "C" {
 #endif
 
 #define FA_N_FEATURES 53 /* /root/reference/src/localstore.js:7 (levels 5 and 13 -> 53) */
+#define FA_N_UTT_FEATURES 264 /* get_utterance_features, /root/reference/dist/main.js:2@B107983 (level 11) */
 #define FA_ABI_VERSION 1
 
 typedef enum fa_status {
@@ -66,6 +67,7 @@ typedef enum fa_status {
 #define FA_LEVEL_FORMANTS 4
 #define FA_LEVEL_SEG_FEATURES 5
 #define FA_LEVEL_SYL_FORMANTS 10
+#define FA_LEVEL_UTTERANCE 11      /* "Utterance distributions": 264 doubles, cumulative, one row per stored segment */
 #define FA_LEVEL_SYL_FEATURES 13
 
 typedef struct fa_config {
@@ -170,6 +172,14 @@ FA_API int fa_submit_pcm_i16(fa_handle* h, int64_t utt_id, const int16_t* pcm, s
 FA_API int fa_submit_pcm_batch(fa_handle* h, int64_t first_utt_id, const float* pcm, const int64_t* offsets, int n_utt,
                                int sample_rate);
 
+/* The segmentor's own input, for callers that bring their own spectrum stage (e.g. frames captured from a browser
+ * AnalyserNode / the reference's worklet): `n_frames` rows of `bands` uint32, one row per spectrum_push(frame, idx) of the
+ * reference (/root/reference/dist/main.js:2@B30392).  `bands` must equal fa_spec_bands(cfg) -- the reference's own check,
+ * same message ("Error: bins num mismatch").  The spectrum stage (K1a/K1b) is skipped for the batch; a batch holds
+ * either PCM or frames (mixing fails with FA_ERR_INVALID_ARG); output_level must be >= 3.  The frames are copied (pinned
+ * staging).  Returns the utterance index. */
+FA_API int fa_submit_frames(fa_handle* h, int64_t utt_id, const uint32_t* frames, size_t n_frames, int bands);
+
 /* Asynchronously: H2D copy of the staged PCM, stages 1-4 on the handle's stream, D2H of the result
  * tables.  fa_sync waits for it. */
 FA_API int fa_run(fa_handle* h);
@@ -201,6 +211,10 @@ FA_API int fa_copy_formants(fa_handle* h, int64_t utt_id, float* dst, size_t cap
 FA_API int fa_copy_energy(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows);        /* rows of 3 float32 */
 FA_API int fa_copy_syllables(fa_handle* h, int64_t utt_id, fa_syllable* dst, size_t cap_rows);
 FA_API int fa_copy_features(fa_handle* h, int64_t utt_id, double* dst, size_t cap_rows);     /* rows of 53 doubles */
+/* Level 11 (get_utterance_features @B107983, called from P() @B28869): rows of 264 doubles, one per stored segment of the
+ * utterance, row k = the distribution over stores 0..k -- what the reference passes to its callback after store k; the
+ * last row describes the whole utterance.  fa_counts.feature_rows counts these rows at level 11. */
+FA_API int fa_copy_utterance_features(fa_handle* h, int64_t utt_id, double* dst, size_t cap_rows);
 
 /* Stage-level taps for parity tests (candidate peaks of stage 2: packed lo | hi<<8 | pk<<16 | last<<24). */
 FA_API int fa_copy_peak_candidates(fa_handle* h, int64_t utt_id, uint32_t* packed, int32_t* counts, size_t cap_rows,

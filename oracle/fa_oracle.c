@@ -290,6 +290,9 @@ struct fao_result {
   int n_feature_rows;
   /* callback order (P @B28869): indices into seg_ci, in firing order */
   ivec cb_si;
+  /* level 11: one 264-dim row per callback = get_utterance_features(u, h) over the stores that exist at that time */
+  dvec utt_rows;
+  int n_utt_rows;
 };
 typedef struct fao_result fao_result;
 
@@ -764,10 +767,99 @@ static int process_frame(fao_state* st, fao_result* R, const uint32_t* e, int fr
   return fin;
 }
 
+/* ---- level 11: get_utterance_features @B107983 (inner module 7 of the bundle) ------------------------------------
+ * 15 histograms (module-level arrays i,o,l,s,c,u,f,d,h,p,m,g,y,v,x -- sizes below, 264 bins in all) over the segments
+ * and syllables stored so far.  `arr[k]++` with k = NaN or k < 0 does not touch a bin: it creates the named property
+ * "NaN" / "-1" holding NaN, which w() @B109452 then meets in its for-in sum -- the total becomes NaN, `t > 0` fails and
+ * the histogram is returned UN-normalised.  fao_hist.poison models that property. */
+typedef struct { double c[40]; int n, poison; } fao_hist;
+enum { H_I, H_O, H_L, H_S, H_C, H_U, H_F, H_D, H_H, H_P, H_M, H_G, H_Y, H_V, H_X, H_COUNT };
+static const int kHistSize[H_COUNT] = {10, 10, 10, 10, 20, 40, 40, 24, 24, 8, 8, 10, 10, 20, 20};
+
+static void hist_inc(fao_hist* h, double k) {
+  if (k != k || k <= -1.0) { h->poison = 1; return; }   /* named property; (-1, 0) truncates to -0 -> index 0 */
+  int i = (int)k;
+  if (i >= h->n) { h->poison = 1; return; }              /* cannot happen: every index is clamped from above */
+  h->c[i] += 1;
+}
+
+/* _() @B109020: one segment */
+static void utt_segment(fao_hist* H, double seg_len, double n_syl, double gap, double voiced) {
+  double a = fa_js_parse_int(10 * seg_len / 150); if (a >= 10) a = 9; hist_inc(&H[H_I], a);
+  double c = n_syl; if (c >= 10) c = 9; hist_inc(&H[H_O], c);
+  double u = fa_js_parse_int(10 * gap / 150); if (u >= 10) u = 9; hist_inc(&H[H_L], u);
+  double f = fa_js_parse_int(2 * (voiced - .3) * 10); if (f >= 10) f = 9; if (f < 0) f = 0; hist_inc(&H[H_S], f);
+}
+
+/* b() @B109255: one syllable (e len, t/n/a mean f0 bin/energy/span, i sum of f0 steps, o f0 count, l/s/_ the same for f1,
+ * b sum of f1 steps, w f1 count) */
+static void utt_syllable(fao_hist* H, double e, double t, double n, double a, double i, double o, double l, double s,
+                         double u_, double b, double w) {
+  const double r = 40;
+  double T = fa_js_parse_int(e / 2); if (T >= 20) T = 19; hist_inc(&H[H_C], T);
+  double k = fa_js_parse_int(t / 2); if (k >= r) k = r - 1; hist_inc(&H[H_U], k);
+  double M = fa_js_parse_int(l / 2); if (M >= r) M = r - 1; hist_inc(&H[H_F], M);
+  double A = fa_js_parse_int(3 * fa_js_log10(n)); if (A >= 24) A = 23; hist_inc(&H[H_D], A);
+  double S = fa_js_parse_int(4 * fa_js_log10(s)); if (S >= 24) S = 23; hist_inc(&H[H_H], S);
+  double L = fa_js_parse_int(a / 2); if (L >= 8) L = 7; hist_inc(&H[H_P], L);
+  double D = fa_js_parse_int(u_ / 2); if (D >= 8) D = 7; hist_inc(&H[H_M], D);
+  double O = fa_js_parse_int(10 * (e - o) / e); if (O >= 10) O = 9; hist_inc(&H[H_G], O);
+  double C = fa_js_parse_int(10 * (e - w) / e); if (C >= 10) C = 9; hist_inc(&H[H_Y], C);
+  double P = fa_js_parse_int(20 * (i + 50) / 100); if (P >= 20) P = 19; if (P < 0) P = 0; hist_inc(&H[H_V], P);
+  double I = fa_js_parse_int(20 * (b + 50) / 100); if (I >= 20) I = 19; if (I < 0) I = 0; hist_inc(&H[H_X], I);
+}
+
+/* a() @B107983 over the first n_stores stores; store r is paired with seg_ci[r] (NOT with the segment that produced it:
+ * the same misalignment as the time stamps after a dropped segment, quirk 15) */
+static void utterance_features(const fao_result* R, int n_stores, double* out /*[264]*/) {
+  fao_hist H[H_COUNT];
+  memset(H, 0, sizeof(H));
+  for (int q = 0; q < H_COUNT; q++) H[q].n = kHistSize[q];
+  double prev_end = R->seg_start.d[0];
+  for (int r = 0; r < n_stores; r++) {
+    const double seg_len = R->seg_len.d[r];
+    const int nsyl = R->st_nsyl.d[r];
+    double voiced = 0;
+    for (int e = 0; e < nsyl; e++) {
+      const int sy = R->st_first_syl.d[r] + e;
+      const int n = R->syl_len.d[sy];
+      const float* F = R->formants + 9 * (size_t)(R->st_row_off.d[r] + R->syl_start.d[sy]);
+      double a = 0, i = 0, l = 0, s = 0, c = 0, u = 0, f = 0, d = 0, h = 0, p = 0;
+      for (int o = 0; o < n; o++) {
+        const float* x = F + 9 * (size_t)o;
+        if (x[0] > 0) { c++; a += x[0]; i += x[1]; l += x[2]; if (o > 0) s += (double)x[0] - (double)x[-9]; }
+        if (x[3] > 0) { p++; u += x[3]; f += x[4]; d += x[5]; if (o > 0) h += (double)x[3] - (double)x[-9 + 3]; }
+      }
+      a /= c; i /= c; l /= c; u /= p; f /= p; d /= p;
+      utt_syllable(H, n, a, i, l, s, c, u, f, d, h, p);
+      voiced += n;
+    }
+    utt_segment(H, seg_len, nsyl, (double)R->seg_start.d[r] - prev_end, voiced / seg_len);
+    prev_end = (double)R->seg_start.d[r] + (double)R->seg_len.d[r];
+  }
+  for (int q = 0; q < H_COUNT; q++) {        /* w() @B109452 */
+    double t = 0;
+    for (int k = 0; k < H[q].n; k++) t += H[q].c[k];
+    const int norm = !H[q].poison && t > 0;
+    for (int k = 0; k < H[q].n; k++) *out++ = norm ? H[q].c[k] / t : H[q].c[k];
+  }
+}
+
 /* P() @B28869: which seg_ci indices fire a callback, in order.  The stores are indexed by `stored`;
  * the reference indexes seg_ci (u) with the SAME counter, which misaligns after a dropped segment
  * (quirk 15) -- we record the store index and let the host shim reproduce j()/V(). */
 static void fire_callbacks(fao_result* R, int* processed) {
+  if (R->level == 11) {   /* one callback per P() that sees new stores: b(0, label, clip_time, row264) */
+    if (*processed < R->st_len.n) {
+      *processed = R->st_len.n;
+      double row[264];
+      utterance_features(R, R->st_len.n, row);
+      for (int q = 0; q < 264; q++) dvec_push(&R->utt_rows, row[q]);
+      R->n_utt_rows++;
+      ivec_push(&R->cb_si, R->st_len.n - 1);
+    }
+    return;
+  }
   while (*processed < R->st_len.n) {
     int e = (*processed)++;
     int fire = 0;
@@ -829,7 +921,7 @@ FAO_API void fao_free(fao_result* R) {
   free(R->tr_y); free(R->seg_start.d); free(R->seg_len.d); free(R->seg_stored.d); free(R->st_len.d);
   free(R->st_row_off.d); free(R->st_nsyl.d); free(R->st_first_syl.d); free(R->st_y.d); free(R->st_v.d);
   free(R->st_cs.d); free(R->formants); free(R->energy); free(R->syl_seg.d); free(R->syl_start.d);
-  free(R->syl_len.d); free(R->features.d); free(R->cb_si.d);
+  free(R->syl_len.d); free(R->features.d); free(R->cb_si.d); free(R->utt_rows.d);
   free(R);
 }
 
@@ -861,6 +953,10 @@ FAO_API void fao_get_syllables(const fao_result* R, fa_syllable* dst) {
 }
 FAO_API void fao_get_features(const fao_result* R, double* dst) {
   memcpy(dst, R->features.d, sizeof(double) * (size_t)R->features.n);
+}
+FAO_API int fao_utterance_rows(const fao_result* R) { return R->n_utt_rows; }
+FAO_API void fao_get_utterance_features(const fao_result* R, double* dst) {
+  memcpy(dst, R->utt_rows.d, sizeof(double) * (size_t)R->utt_rows.n);
 }
 FAO_API void fao_get_callbacks(const fao_result* R, int* dst) { memcpy(dst, R->cb_si.d, sizeof(int) * (size_t)R->cb_si.n); }
 FAO_API int fao_get_trace(const fao_result* R, int* n, int* p, double* h, double* v, double* y, int* cstart, int* cci,

@@ -35,6 +35,8 @@ _lib.fao_get_formants.argtypes = [C.c_void_p, _f32p, _f32p]
 _lib.fao_get_syllables.argtypes = [C.c_void_p, C.POINTER(FaSyllable)]
 _lib.fao_get_features.argtypes = [C.c_void_p, _f64p]
 _lib.fao_get_callbacks.argtypes = [C.c_void_p, _i32p]
+_lib.fao_utterance_rows.argtypes = [C.c_void_p]
+_lib.fao_get_utterance_features.argtypes = [C.c_void_p, _f64p]
 _lib.fao_get_trace.argtypes = [C.c_void_p, _i32p, _i32p, _f64p, _f64p, _f64p, _i32p, _i32p, _i32p]
 _lib.fao_peak_candidates.argtypes = [_u32p, C.c_int, _u32p, _f64p]
 _lib.fao_run_batch.argtypes = [_cfgp, _f32p, C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
@@ -98,6 +100,7 @@ class Analysis:
     features: np.ndarray            # [rows, 53] float64
     callbacks: np.ndarray           # store indices in firing order
     trace: dict = field(default_factory=dict)
+    utterance: np.ndarray = None    # [callbacks, 264] float64 (level 11)
 
     @property
     def seg_ci(self):
@@ -142,7 +145,11 @@ def analyze_frames(cfg: FaConfig, frames: np.ndarray, trace: bool = False) -> An
             tr.update({k: np.zeros(F, np.float64) for k in ("h", "v", "y")})
             _lib.fao_get_trace(R, _p(tr["n"], _i32p), _p(tr["p"], _i32p), _p(tr["h"], _f64p), _p(tr["v"], _f64p),
                                _p(tr["y"], _f64p), _p(tr["cstart"], _i32p), _p(tr["cci"], _i32p), _p(tr["nofm"], _i32p))
-        return Analysis(F, B, segs, Fm, Eg, syl, feat, cb, tr)
+        nu = _lib.fao_utterance_rows(R)
+        utt = np.zeros((nu, 264), np.float64)
+        if nu:
+            _lib.fao_get_utterance_features(R, _p(utt, _f64p))
+        return Analysis(F, B, segs, Fm, Eg, syl, feat, cb, tr, utt)
     finally:
         _lib.fao_free(R)
 

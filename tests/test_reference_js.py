@@ -60,9 +60,7 @@ def check_against_reference(case, an, level, step):
         mine = [[[int(y["start"]), int(y["len"])] for y in an.syllables[s["first_syllable"]: s["first_syllable"] + s["n_syllables"]]]
                 for s in stored]
         assert mine == case["syl_ci"]
-    if level == 11:
-        return                      # the 264-dim utterance row is checked by test_level11_* below
-    res = UtteranceResult({}, an.segments, an.formants, an.energy, an.syllables, an.features)
+    res = UtteranceResult({}, an.segments, an.formants, an.energy, an.syllables, an.features, getattr(an, "utterance", None))
     calls = api.segment_callbacks(level, step, DOC["labels"], res)
     assert len(calls) == len(case["events"])
     for mine, ref in zip(calls, case["events"]):
@@ -73,6 +71,9 @@ def check_against_reference(case, an, level, step):
             assert all(len(r) == 53 for r in mine[3])
         elif level == 5:
             assert np.array_equal(np.array(mine[3], np.float64), np.array(ref[3], np.float64), equal_nan=True) and len(mine[3]) == 53
+        elif level == 11:
+            # cumulative 264-dim distributions (get_utterance_features @B107983), un-normalised histograms included
+            assert np.array_equal(np.array(mine[3], np.float64), np.array(ref[3], np.float64), equal_nan=True) and len(mine[3]) == 264
         elif level == 4:
             a = np.stack(mine[3]).astype(np.float32)
             assert a.shape[0] == ref[3]["f32_rows"] and sha(a) == ref[3]["sha"]
@@ -102,6 +103,9 @@ def test_fixture_covers_the_quirks():
     assert any(c["syl_ci"] and any(len(s) > 1 for s in c["syl_ci"]) for c in DOC["cases"])
     assert any(not c["kwargs"].get("auto_noise_gate", 1) and c["events"] for c in DOC["cases"])
     assert sum(len(c["seg_ci"]) for c in DOC["cases"]) > 150
+    l11 = [c for c in DOC["cases"] if c["kwargs"]["output_level"] == 11 and c["events"]]
+    assert any(max(np.sum(e[3]) for e in c["events"]) > 15.5 for c in l11)              # a poisoned (raw-count) histogram
+    assert any(len(c["seg_ci"]) > len(c["events"]) for c in l11)                        # level 11 after a dropped segment
 
 
 @pytest.mark.skipif(not run_reference.available(), reason="reference not mounted (GPU box): the committed vectors stand in")

@@ -4,6 +4,7 @@ from __future__ import annotations
 import ctypes as C
 
 N_FEATURES = 53  # /root/reference/src/localstore.js:7
+N_UTT_FEATURES = 264  # get_utterance_features, /root/reference/dist/main.js:2@B107983 (level 11)
 
 
 class FaConfig(C.Structure):

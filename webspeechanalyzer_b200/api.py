@@ -113,6 +113,17 @@ def segment_callbacks(level: int, step_ms: float, labels: list, res) -> list[tup
     segs = res.segments
     stored = [s for s in segs if s["stored"] >= 0]
     out = []
+    if level == 11:
+        # b(0, label, get_clip_timestamps() @B31365, get_utterance_features(u, h) @B107983) after every stored segment;
+        # the clip time sums the lengths of ALL seg_ci entries that exist at that moment (dropped ones included)
+        k = 0
+        for si, s in enumerate(segs):
+            if s["stored"] < 0:
+                continue
+            t = sum(int(x["len"]) for x in segs[: si + 1])
+            out.append((0, labels, [int(segs[0]["start"]) * step, (t + 1) * step], list(map(float, res.utterance[k]))))
+            k += 1
+        return out
     for e, s in enumerate(stored):
         ci = segs[e]
         rows = res.formants[s["row_offset"]: s["row_offset"] + s["len"]]

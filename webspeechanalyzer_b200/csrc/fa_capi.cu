@@ -124,8 +124,11 @@ struct fa_handle {
   DevBuf d_segs, d_syls, d_formants, d_energy, d_features, d_counts, d_off;
   DevBuf g_segs, g_syls, g_formants, g_energy, g_features;
   int n_weights = 0;
-  long long track_total = 0;
+  long long track_total = 0, urow_total = 0;
+  int feat_width() const { return cfg.output_level == FA_LEVEL_UTTERANCE ? FA_N_UTT_FEATURES : FA_N_FEATURES; }
   bool uploaded = false, ran = false, downloaded = false, want_spec = false, from_host = false;
+  bool frames_mode = false;    // the batch was submitted as uint32 frames (fa_submit_frames): the spectrum stage is skipped
+  HostBuf h_frames;            // pinned staging of submitted frames, row order
   long long tot[4] = {0, 0, 0, 0};  // segs, rows, syls, feat
   cudaEvent_t ev[8] = {};
   float stage_ms[5] = {0, 0, 0, 0, 0};
@@ -150,12 +153,12 @@ int fail(fa_handle* h, int code, const char* what, cudaError_t e = cudaSuccess) 
 
 bool level_supported(int lvl) {
   return lvl == FA_LEVEL_BARS || lvl == FA_LEVEL_SPECTRUM || lvl == FA_LEVEL_FORMANTS || lvl == FA_LEVEL_SEG_FEATURES ||
-         lvl == FA_LEVEL_SYL_FORMANTS || lvl == FA_LEVEL_SYL_FEATURES;
+         lvl == FA_LEVEL_SYL_FORMANTS || lvl == FA_LEVEL_UTTERANCE || lvl == FA_LEVEL_SYL_FEATURES;
 }
 
 int validate(const fa_config* c, std::string* why) {
   if (!fa_tab_valid_fft(c->fft_size)) { *why = "fft_size must be a power of two in [256, 16384]"; return FA_ERR_UNSUPPORTED; }
-  if (!level_supported(c->output_level)) { *why = "output_level not supported (levels 1, 2, 4, 5, 10, 13)"; return FA_ERR_UNSUPPORTED; }
+  if (!level_supported(c->output_level)) { *why = "output_level not supported (levels 1, 2, 4, 5, 10, 11, 13)"; return FA_ERR_UNSUPPORTED; }
   if (c->spec_type < 1 || c->spec_type > 3) { *why = "Invalid reset_nodes config"; return FA_ERR_INVALID_ARG; }
   const int B = fa_tab_bands(c);
   if (B < 8 || B > FA_MAX_BANDS) { *why = "Invalid spec_bands"; return FA_ERR_INVALID_ARG; }
@@ -304,7 +307,7 @@ int fa_destroy(fa_handle* h) {
                     &h->d_formants, &h->d_energy, &h->d_features, &h->d_counts, &h->d_off, &h->g_segs, &h->g_syls,
                     &h->g_formants, &h->g_energy, &h->g_features})
     b->release();
-  for (HostBuf* b : {&h->h_pcm, &h->h_meta, &h->h_counts, &h->h_off, &h->h_segs, &h->h_syls, &h->h_formants, &h->h_energy,
+  for (HostBuf* b : {&h->h_pcm, &h->h_frames, &h->h_meta, &h->h_counts, &h->h_off, &h->h_segs, &h->h_syls, &h->h_formants, &h->h_energy,
                      &h->h_features})
     b->release();
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -368,6 +371,7 @@ int fa_reset(fa_handle* h) {
   h->staged = 0;
   h->total_frames = 0;
   h->uploaded = h->ran = h->downloaded = h->prepared = false;
+  h->frames_mode = false;
   return FA_OK;
 }
 
@@ -387,6 +391,7 @@ static int submit_check(fa_handle* h, int sr) {
   if (!h || sr <= 0) return fail(h, FA_ERR_INVALID_ARG, "Invalid audio source");
   cudaSetDevice(h->device);
   if (h->uploaded || h->ran) return fail(h, FA_ERR_BUSY, "Error: Already playing");
+  if (h->frames_mode) return fail(h, FA_ERR_INVALID_ARG, "a batch holds either PCM or frames, not both");
   if (h->utts.empty()) h->sample_rate = sr;
   else if (sr != h->sample_rate) return fail(h, FA_ERR_INVALID_ARG, "all utterances of a batch must share the sample rate");
   return FA_OK;
@@ -458,6 +463,31 @@ int fa_submit_pcm_batch(fa_handle* h, int64_t first_utt_id, const float* pcm, co
   return first;
 }
 
+int fa_submit_frames(fa_handle* h, int64_t utt_id, const uint32_t* frames, size_t n_frames, int bands) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  if (h->uploaded || h->ran) return fail(h, FA_ERR_BUSY, "Error: Already playing");
+  if (!h->frames_mode && !h->utts.empty()) return fail(h, FA_ERR_INVALID_ARG, "a batch holds either PCM or frames, not both");
+  if (h->cfg.output_level < 3) return fail(h, FA_ERR_INVALID_ARG, "frames carry no spectrum: output_level must be >= 3");
+  const int B = fa_tab_bands(&h->cfg);
+  if (bands != B) return fail(h, FA_ERR_INVALID_ARG, "Error: bins num mismatch");   // spectrum_push's own check @B30392
+  if (!frames && n_frames) return fail(h, FA_ERR_INVALID_ARG, "Invalid audio source");
+  if (n_frames > (size_t)INT32_MAX) return fail(h, FA_ERR_CAPACITY, "too many frames");
+  if (h->index.count(utt_id)) return fail(h, FA_ERR_INVALID_ARG, "duplicate utterance id");
+  if (h->sample_rate <= 0) h->sample_rate = 16000;   // only sizes the (unused) spectrum tables
+  const size_t row = (size_t)B * sizeof(uint32_t);
+  const size_t used = (size_t)h->total_frames * row;
+  FA_CUDA(h->h_frames.reserve(used + n_frames * row + 64, used));
+  if (n_frames) memcpy((char*)h->h_frames.p + used, frames, n_frames * row);
+  Utt u;
+  u.id = utt_id; u.region = 0; u.off = 0; u.n = 0; u.frames = (int)n_frames; u.row0 = h->total_frames;
+  h->index[utt_id] = (int)h->utts.size();
+  h->utts.push_back(u);
+  h->total_frames += u.frames;
+  h->frames_mode = true;
+  return (int)h->utts.size() - 1;
+}
+
 // allocate everything a run needs and upload the small tables / metadata (not the PCM)
 static int prepare(fa_handle* h) {
   if (h->utts.empty()) return fail(h, FA_ERR_INVALID_ARG, "Invalid audio source");
@@ -477,10 +507,14 @@ static int prepare(fa_handle* h) {
   }
   h->dev_floats = dev;
   h->abs_off.resize(n);
-  // meta: utt_off[n], utt_len[n], frame_off[n+1], track_base[n+1]
-  FA_CUDA(h->h_meta.reserve(sizeof(long long) * (4 * (size_t)n + 2)));
+  // meta: utt_off[n], utt_len[n], frame_off[n+1], track_base[n+1], urow_base[n+1]
+  FA_CUDA(h->h_meta.reserve(sizeof(long long) * (5 * (size_t)n + 3)));
   long long* m = h->h_meta.as<long long>();
-  long long tb = 0;
+  long long tb = 0, ub = 0;
+  // level 11: a stored segment spans > seg_min_frames voiced frames plus >= seg_breaker pause frames (none for the last one)
+  const double brk = h->cfg.pause_length_ms > 2 * h->cfg.window_step_ms ? h->cfg.pause_length_ms / h->cfg.window_step_ms
+                                                                         : 250 / h->cfg.window_step_ms;
+  const long long seg_span = (long long)fa_js_parse_int(h->cfg.min_seg_length_ms / h->cfg.window_step_ms) + 1 + (long long)ceil(brk);
   for (int i = 0; i < n; i++) {
     const Utt& u = h->utts[i];
     h->abs_off[i] = h->regions[u.region].dev_off + u.off;
@@ -489,12 +523,16 @@ static int prepare(fa_handle* h) {
     m[2 * n + i] = u.row0;
     m[3 * n + 1 + i] = tb;
     tb += (long long)u.frames * 16 + 64;
+    m[4 * n + 2 + i] = ub;
+    ub += u.frames / std::max<long long>(seg_span, 1) + 2;
   }
   m[2 * n + n] = F;
   m[3 * n + 1 + n] = tb;
+  m[4 * n + 2 + n] = ub;
   h->track_total = tb;
-  FA_CUDA(h->d_meta.reserve(sizeof(long long) * (4 * (size_t)n + 2)));
-  FA_CUDA(cudaMemcpyAsync(h->d_meta.p, m, sizeof(long long) * (4 * (size_t)n + 2), cudaMemcpyHostToDevice, s));
+  h->urow_total = ub;
+  FA_CUDA(h->d_meta.reserve(sizeof(long long) * (5 * (size_t)n + 3)));
+  FA_CUDA(cudaMemcpyAsync(h->d_meta.p, m, sizeof(long long) * (5 * (size_t)n + 3), cudaMemcpyHostToDevice, s));
   FA_CUDA(h->d_pcm.reserve((size_t)(dev + 16) * sizeof(float)));
   const size_t Fz = (size_t)std::max<long long>(F, 1), nz = (size_t)n;
   FA_CUDA(h->d_spec.reserve(Fz * h->M * sizeof(float)));  // the K1a -> K1b magnitude rows, turned into dB rows in place
@@ -520,6 +558,10 @@ static int prepare(fa_handle* h) {
     FA_CUDA(h->d_energy.reserve(Fz * 3 * sizeof(float)));
     if (h->cfg.output_level == 5 || h->cfg.output_level == 13)
       FA_CUDA(h->d_features.reserve((Fz + nz) * FA_N_FEATURES * sizeof(double)));
+    if (h->cfg.output_level == FA_LEVEL_UTTERANCE) {
+      FA_CUDA(h->d_features.reserve((size_t)ub * FA_N_UTT_FEATURES * sizeof(double)));
+      FA_CUDA(h->g_features.reserve((size_t)ub * FA_N_UTT_FEATURES * sizeof(double)));
+    }
     FA_CUDA(h->d_counts.reserve(nz * 6 * sizeof(int)));      // n_segs, n_stored, n_rows, n_syls, n_feat, overflow
     FA_CUDA(h->d_off.reserve((nz + 1) * 4 * sizeof(long long)));
     FA_CUDA(h->g_segs.reserve((Fz + nz) * sizeof(fa_segment)));
@@ -580,6 +622,15 @@ static std::vector<SubBatch> plan(const fa_handle* h, bool with_copies) {
 
 // H2D of the PCM of utterances [u0, u1): contiguous runs per region
 static int copy_pcm_range(fa_handle* h, int u0, int u1, cudaStream_t s) {
+  if (h->frames_mode) {   // the input of the batch is the uint32 frames themselves
+    if (u1 <= u0) return FA_OK;
+    const long long r0 = h->utts[u0].row0, r1 = h->utts[u1 - 1].row0 + h->utts[u1 - 1].frames;
+    const size_t row = (size_t)h->B * sizeof(uint32_t);
+    if (r1 > r0)
+      FA_CUDA(cudaMemcpyAsync((char*)h->d_frames.p + (size_t)r0 * row, (const char*)h->h_frames.p + (size_t)r0 * row,
+                              (size_t)(r1 - r0) * row, cudaMemcpyHostToDevice, s));
+    return FA_OK;
+  }
   int i = u0;
   while (i < u1) {
     const int reg = h->utts[i].region;
@@ -632,7 +683,7 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
   sp.spec_db = h->d_spec.as<float>();
   sp.frames = h->d_frames.as<uint32_t>();
   sp.work_counter = h->d_counter.as<int>() + slot;
-  FA_CUDA(fa_launch_spectrum(sp, s, &h->launches));
+  if (!h->frames_mode) FA_CUDA(fa_launch_spectrum(sp, s, &h->launches));
   if (getenv("FA_DEBUG_SYNC")) FA_CUDA(cudaStreamSynchronize(s));
   if (ev) FA_CUDA(cudaEventRecord(ev[1], s));
   if (!ev) FA_CUDA(cudaEventRecord(h->spec_done[slot], s));  // the dB rows of this sub-batch are final
@@ -691,6 +742,13 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
       fp.features = h->d_features.as<double>(); fp.n_feat = cnt + 4 * n;
       FA_CUDA(fa_launch_features(fp, s3, &h->launches));
     }
+    if (c.output_level == FA_LEVEL_UTTERANCE) {
+      FaUtteranceParams up;
+      up.frame_off = meta + 2 * n; up.n_utt = n; up.utt_begin = sb.u0; up.utt_count = sb.u1 - sb.u0;
+      up.segs = g.segs; up.n_segs = g.n_segs; up.syls = g.syls; up.formants = g.formants;
+      up.row_base = meta + 4 * n + 2; up.rows = h->d_features.as<double>(); up.n_feat = cnt + 4 * n; up.overflow = g.overflow;
+      FA_CUDA(fa_launch_utterance(up, s3, &h->launches));
+    }
     if (tr) FA_CUDA(cudaEventRecord(h->tr_k[slot][4], s3));
     if (s3 != s) FA_CUDA(cudaEventRecord(h->sub_hi_done[slot], s3));
     if (ev) FA_CUDA(cudaEventRecord(ev[4], s));
@@ -712,7 +770,7 @@ static int run_device(fa_handle* h, bool with_h2d, bool with_sink) {
   if (c.output_level >= 3) FA_CUDA(cudaMemsetAsync(h->d_counts.p, 0, sizeof(int) * 6 * (size_t)n, s));
   FA_CUDA(cudaEventRecord(h->ev[0], s));
   const std::vector<SubBatch> subs = plan(h, with_h2d || (with_sink && h->spec_sink));
-  const bool sink = with_sink && h->spec_sink && h->want_spec;
+  const bool sink = with_sink && h->spec_sink && h->want_spec && !h->frames_mode;
   if (sink && (size_t)h->total_frames > h->spec_sink_rows) return fail(h, FA_ERR_CAPACITY, "spectrum sink too small");
   if (subs.size() <= 1) {
     SubBatch all{0, n, 0, h->total_frames};
@@ -758,6 +816,8 @@ static int run_device(fa_handle* h, bool with_h2d, bool with_sink) {
   if (c.output_level >= 3) {
     int* cnt = h->d_counts.as<int>();
     FaGatherArgs ga;
+    ga.feat_width = h->feat_width();
+    ga.feat_base = c.output_level == FA_LEVEL_UTTERANCE ? meta + 4 * n + 2 : nullptr;
     ga.frame_off = meta + 2 * n; ga.n_utt = n; ga.n_segs = cnt; ga.n_rows = cnt + 2 * n; ga.n_syls = cnt + 3 * n;
     ga.n_feat = cnt + 4 * n; ga.off = h->d_off.as<long long>();
     ga.segs = h->d_segs.as<fa_segment>(); ga.syls = h->d_syls.as<fa_syllable>();
@@ -815,7 +875,7 @@ int fa_download(fa_handle* h) {
     FA_CUDA(h->h_formants.reserve(std::max<size_t>(16, h->tot[1] * 9 * sizeof(float))));
     FA_CUDA(h->h_energy.reserve(std::max<size_t>(16, h->tot[1] * 3 * sizeof(float))));
     FA_CUDA(h->h_syls.reserve(std::max<size_t>(16, h->tot[2] * sizeof(fa_syllable))));
-    FA_CUDA(h->h_features.reserve(std::max<size_t>(16, h->tot[3] * FA_N_FEATURES * sizeof(double))));
+    FA_CUDA(h->h_features.reserve(std::max<size_t>(16, h->tot[3] * h->feat_width() * sizeof(double))));
     if (h->tot[0]) FA_CUDA(cudaMemcpyAsync(h->h_segs.p, h->g_segs.p, h->tot[0] * sizeof(fa_segment), cudaMemcpyDeviceToHost, s));
     if (h->tot[1]) {
       FA_CUDA(cudaMemcpyAsync(h->h_formants.p, h->g_formants.p, h->tot[1] * 9 * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -823,7 +883,7 @@ int fa_download(fa_handle* h) {
     }
     if (h->tot[2]) FA_CUDA(cudaMemcpyAsync(h->h_syls.p, h->g_syls.p, h->tot[2] * sizeof(fa_syllable), cudaMemcpyDeviceToHost, s));
     if (h->tot[3])
-      FA_CUDA(cudaMemcpyAsync(h->h_features.p, h->g_features.p, h->tot[3] * FA_N_FEATURES * sizeof(double), cudaMemcpyDeviceToHost, s));
+      FA_CUDA(cudaMemcpyAsync(h->h_features.p, h->g_features.p, h->tot[3] * h->feat_width() * sizeof(double), cudaMemcpyDeviceToHost, s));
   }
   FA_CUDA(cudaEventRecord(h->ev[6], s));
   h->downloaded = true;
@@ -966,6 +1026,7 @@ static int copy_rows_device(fa_handle* h, int64_t utt_id, const void* dev, size_
 int fa_copy_spectrum(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows) {
   if (!h) return FA_ERR_INVALID_ARG;
   if (!h->want_spec) return fail(h, FA_ERR_INVALID_ARG, "spectrum not materialised (set want_spectrum or output_level <= 2)");
+  if (h->frames_mode) return fail(h, FA_ERR_INVALID_ARG, "spectrum not materialised (the batch was submitted as frames)");
   return copy_rows_device(h, utt_id, h->d_spec.p, (size_t)h->M * sizeof(float), dst, cap_rows);
 }
 
@@ -1013,7 +1074,15 @@ int fa_copy_syllables(fa_handle* h, int64_t utt_id, fa_syllable* dst, size_t cap
 }
 int fa_copy_features(fa_handle* h, int64_t utt_id, double* dst, size_t cap) {
   if (!h) return FA_ERR_INVALID_ARG;
+  if (h->cfg.output_level == FA_LEVEL_UTTERANCE)
+    return fail(h, FA_ERR_INVALID_ARG, "level 11 rows have 264 entries: use fa_copy_utterance_features");
   return copy_dense(h, utt_id, 3, h->h_features.p, FA_N_FEATURES * sizeof(double), dst, cap);
+}
+
+int fa_copy_utterance_features(fa_handle* h, int64_t utt_id, double* dst, size_t cap) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  if (h->cfg.output_level != FA_LEVEL_UTTERANCE) return fail(h, FA_ERR_INVALID_ARG, "utterance distributions need output_level 11");
+  return copy_dense(h, utt_id, 3, h->h_features.p, FA_N_UTT_FEATURES * sizeof(double), dst, cap);
 }
 
 int fa_copy_peak_candidates(fa_handle* h, int64_t utt_id, uint32_t* packed, int32_t* counts, size_t cap_rows,

@@ -246,9 +246,10 @@ __global__ void __launch_bounds__(128) fa_gather_kernel(const FaGatherArgs g) {
   {
     const int n = g.n_feat[u];
     const long long o = off[3 * N1 + u];
-    const double* s = g.features + (size_t)sb * FA_N_FEATURES;
-    double* d = g.d_features + (size_t)o * FA_N_FEATURES;
-    for (int i = tid; i < n * FA_N_FEATURES; i += 128) d[i] = s[i];
+    const int W = g.feat_width;
+    const double* s = g.features + (size_t)(g.feat_base ? g.feat_base[u] : sb) * W;
+    double* d = g.d_features + (size_t)o * W;
+    for (int i = tid; i < n * W; i += 128) d[i] = s[i];
   }
 }
 

@@ -5,6 +5,7 @@
 //   K2 fa_peaks        S2        candidate peak scan of D() @B25863 (v-independent part)
 //   K3 fa_segment      S2b/S3/S3b/S3c  D()/C()/O() @B25717/@B28506/@B27088, accumulate_fm @B35952, straighten @B35074, sep_syllables @B34757
 //   K4 fa_features     S4        formant_features @B32369 + stats (src/stats.js:29-64)
+//   K6 fa_utterance    (f)1      get_utterance_features @B107983 (level 11: 264-dim distributions)
 //   K5 fa_compact      gathers the per-utterance tables into dense arrays for one D2H copy
 #pragma once
 
@@ -106,9 +107,25 @@ struct FaFeatureParams {
   int* n_feat;                        // [n_utt]
 };
 
+// K6 (level 11): cumulative 264-dim utterance distributions, one row per stored segment
+struct FaUtteranceParams {
+  const long long* frame_off;
+  int n_utt;
+  int utt_begin, utt_count;
+  const fa_segment* segs; const int* n_segs;
+  const fa_syllable* syls;
+  const float* formants;
+  const long long* row_base;          // [n_utt + 1] first 264-row of every utterance in `rows` (capacity = difference)
+  double* rows;
+  int* n_feat;                        // [n_utt] rows written
+  int* overflow;                      // [n_utt]
+};
+
 struct FaGatherArgs {
   const long long* frame_off;
   int n_utt;
+  int feat_width;                     // doubles per feature row: 53 (levels 5, 13) or 264 (level 11)
+  const long long* feat_base;         // level 11: first row of every utterance in `features`; nullptr: frame_off[u] + u
   const int *n_segs, *n_rows, *n_syls, *n_feat;
   long long* off;  // [4][n_utt + 1] exclusive prefixes: segs, rows, syls, feat
   const fa_segment* segs; const fa_syllable* syls; const float* formants; const float* energy; const double* features;
@@ -119,5 +136,6 @@ cudaError_t fa_launch_spectrum(const FaSpectrumParams& p, cudaStream_t s, int* l
 cudaError_t fa_launch_peaks(const FaPeaksParams& p, cudaStream_t s, int* launches);
 cudaError_t fa_launch_segment(const FaSegmentParams& p, cudaStream_t s, int* launches);
 cudaError_t fa_launch_features(const FaFeatureParams& p, cudaStream_t s, int* launches);
+cudaError_t fa_launch_utterance(const FaUtteranceParams& p, cudaStream_t s, int* launches);
 cudaError_t fa_launch_prefix(const FaGatherArgs& a, cudaStream_t s, int* launches);
 cudaError_t fa_launch_gather(const FaGatherArgs& a, cudaStream_t s, int* launches);

@@ -8,7 +8,7 @@ import numpy as np
 
 from . import _capi
 from ._capi import FaError
-from ._ctypes_defs import FaConfig, FaCounts, N_FEATURES
+from ._ctypes_defs import FaConfig, FaCounts, N_FEATURES, N_UTT_FEATURES
 
 SEG_DTYPE = np.dtype([("start", "<i4"), ("len", "<i4"), ("stored", "<i4"), ("n_syllables", "<i4"),
                       ("first_syllable", "<i4"), ("row_offset", "<i4"), ("ymax", "<f8"), ("vmin", "<f8"),
@@ -24,6 +24,7 @@ class UtteranceResult:
     energy: np.ndarray        # [rows, 3] float32
     syllables: np.ndarray     # SYL_DTYPE
     features: np.ndarray      # [rows, 53] float64
+    utterance: np.ndarray | None = None   # [stored segments, 264] float64, cumulative (level 11)
 
     @property
     def seg_ci(self):
@@ -89,6 +90,12 @@ class Engine:
             return self._check(self._lib.fa_submit_pcm_i16(self._h, utt_id, pcm.ctypes.data, pcm.size, sample_rate))
         pcm = np.ascontiguousarray(pcm, np.float32)
         return self._check(self._lib.fa_submit_pcm(self._h, utt_id, pcm.ctypes.data, pcm.size, sample_rate))
+
+    def submit_frames(self, utt_id: int, frames: np.ndarray) -> int:
+        """The segmentor's own input (spectrum_push @B30392): [n_frames, bands] uint32; the spectrum stage is skipped."""
+        frames = np.ascontiguousarray(frames, np.uint32)
+        assert frames.ndim == 2
+        return self._check(self._lib.fa_submit_frames(self._h, utt_id, frames.ctypes.data, frames.shape[0], frames.shape[1]))
 
     def submit_batch(self, first_utt_id: int, pcm: np.ndarray, offsets: np.ndarray, sample_rate: int) -> int:
         """Whole batch in one float32 buffer; zero-copy when `pcm` is page-locked (keep it alive until sync())."""
@@ -178,5 +185,8 @@ class Engine:
         fm = self._rows(L.fa_copy_formants, utt_id, c["formant_rows"], (9,), np.float32)
         en = self._rows(L.fa_copy_energy, utt_id, c["formant_rows"], (3,), np.float32)
         sy = self._rows(L.fa_copy_syllables, utt_id, c["syllables"], (), SYL_DTYPE)
+        if self.cfg.output_level == 11:
+            ut = self._rows(L.fa_copy_utterance_features, utt_id, c["feature_rows"], (N_UTT_FEATURES,), np.float64)
+            return UtteranceResult(c, segs, fm, en, sy, np.zeros((0, N_FEATURES)), ut)
         ft = self._rows(L.fa_copy_features, utt_id, c["feature_rows"], (N_FEATURES,), np.float64)
         return UtteranceResult(c, segs, fm, en, sy, ft)
