@@ -61,7 +61,7 @@ def test_to_fixed3_matches_js():
 
 
 def as_result(an) -> UtteranceResult:
-    return UtteranceResult({}, an.segments, an.formants, an.energy, an.syllables, an.features)
+    return UtteranceResult({}, an.segments, an.formants, an.energy, an.syllables, an.features, getattr(an, "utterance", None))
 
 
 @pytest.mark.parametrize("level,step", [(13, 15.0), (5, 25.0), (4, 25.0), (10, 15.0)])
@@ -125,3 +125,54 @@ def test_dropped_segment_misaligns_times_like_the_reference():
     # store 0 belongs to seg_ci[1] but is stamped with seg_ci[0]'s time, exactly like the reference
     assert calls[0][2] == S.events[0][2] == [8 * 0.025, (3 + 1) * 0.025]
     assert calls[0][3][0] == 12.0
+
+
+# ------------------------------------------------------------------ export in the web app's storage format
+def test_export_rows_json_csv_follow_localstore():
+    from webspeechanalyzer_b200 import export
+    assert export.js_number(101.0) == "101" and export.js_number(0.1 + 0.2) == "0.30000000000000004"
+    assert export.js_number(1.5e-7) == "1.5e-7" and export.js_number(1e21) == "1e+21" and export.js_number(float("nan")) == "NaN"
+    sr = 16000
+    pcm = synth_speech(5 * sr, sr, 1, 0)
+    # level 13: one stored row per syllable, key "<db>#<file>#<si + ph/100>" (src/index.js:53, src/localstore.js:41-42)
+    cfg = FaConfig.default(output_level=13, window_step_ms=15.0)
+    _, an = oracle.analyze_pcm(cfg, pcm, sr)
+    calls = api.segment_callbacks(13, 15.0, ["f.wav"], as_result(an))
+    rows = export.stored_rows(13, 7, "f.wav", calls)
+    assert len(rows) == an.features.shape[0] > 0 and rows[0]["key"] == "7#f.wav#0" and all(len(r["features"]) == 53 for r in rows)
+    multi = [c for c in calls if len(c[3]) > 1]
+    if multi:
+        assert f"7#f.wav#{export.js_number(multi[0][0] + 0.01)}" in [r["key"] for r in rows]
+    import json
+    doc = json.loads(export.to_json(rows, origin=["f.wav"]))
+    assert set(doc[0]) == {"file", "seg", "time", "features", "origin", "true", "pred"}        # localstore.js:883
+    assert doc[0]["file"] == "f.wav" and doc[0]["seg"] == "0" and doc[0]["time"] == calls[0][2][0]  # toFixed(3) strings
+    got = np.array([[np.nan if v is None else v for v in d["features"]] for d in doc])
+    assert np.array_equal(got, an.features, equal_nan=True)                                   # repr round-trips the doubles
+    csv = export.to_csv(rows).split("\r\n")
+    assert csv[0] == "file,seg,t0,td," + "".join(f"x{i}," for i in range(53))                  # localstore.js:900, 934
+    assert csv[1].startswith(f"f.wav,0,{calls[0][2][0][0]},{calls[0][2][0][1]},") and csv[1].count(",") == 4 + 53
+    # level 5: one row per segment, numeric time stamps
+    cfg = FaConfig.default(output_level=5)
+    _, an = oracle.analyze_pcm(cfg, pcm, sr)
+    rows = export.stored_rows(5, "db", "f.wav", api.segment_callbacks(5, 25.0, [], as_result(an)))
+    assert [r["seg"] for r in rows] == [str(i) for i in range(len(rows))] and len(rows) == an.features.shape[0]
+    assert export.to_csv(rows).split("\r\n")[1].split(",")[2] == export.js_number(an.seg_ci[0][0] * 0.025)
+    # level 10: float32 mean of the syllable's rows (src/index.js:74-86); level 11: the last cumulative row, segment 0
+    cfg = FaConfig.default(output_level=10, window_step_ms=15.0)
+    _, an = oracle.analyze_pcm(cfg, pcm, sr)
+    calls = api.segment_callbacks(10, 15.0, [], as_result(an))
+    rows = export.stored_rows(10, 1, "f.wav", calls)
+    fr = np.stack(calls[0][3][0]).astype(np.float32)
+    acc = fr[0].copy()
+    for r in fr[1:]:
+        acc += r
+    assert len(rows[0]["features"]) == 9 and np.array_equal(np.array(rows[0]["features"], np.float32),
+                                                            np.where(acc != 0, acc / np.float32(len(fr)), acc))
+    cfg = FaConfig.default(output_level=11, window_step_ms=15.0)
+    _, an = oracle.analyze_pcm(cfg, pcm, sr)
+    rows = export.stored_rows(11, 1, "f.wav", api.segment_callbacks(11, 15.0, [], as_result(an)))
+    assert len(rows) == 1 and rows[0]["seg"] == "0" and np.array_equal(rows[0]["features"], an.utterance[-1])
+    # level 4 is not stored by the app; rows of the wrong width are refused
+    assert export.stored_rows(4, 1, "f.wav", [(0, [], [0.0, 1.0], [np.zeros(9, np.float32)])]) == []
+    assert export.stored_rows(5, 1, "f.wav", [(0, [], [0.0, 1.0], [1.0] * 52)]) == []

@@ -105,7 +105,7 @@ typedef struct {
   fa_handle* h;
   const float* pcm;
   size_t n;
-  int sr, rc, want_spec, fft_half;
+  int sr, rc, want_spec, fft_half, feat_width, is_frames;
   char err[256];
   fa_counts counts;
   fa_segment* segs;
@@ -119,7 +119,9 @@ static void job_execute(napi_env env, void* data) {
   job_t* j = (job_t*)data;
   fa_handle* h = j->h;
   int rc = fa_reset(h);
-  if (rc == FA_OK) rc = fa_submit_pcm(h, 0, j->pcm, j->n, j->sr);
+  if (rc == FA_OK)
+    rc = j->is_frames ? (j->sr > 0 ? fa_submit_frames(h, 0, (const uint32_t*)j->pcm, j->n / (size_t)j->sr, j->sr) : FA_ERR_INVALID_ARG)
+                      : fa_submit_pcm(h, 0, j->pcm, j->n, j->sr);
   if (rc >= 0) rc = fa_run(h);
   if (rc == FA_OK) rc = fa_sync(h);
   if (rc == FA_OK) rc = fa_result_counts(h, 0, &j->counts);
@@ -129,12 +131,14 @@ static void job_execute(napi_env env, void* data) {
     j->syls = (fa_syllable*)malloc(sizeof(fa_syllable) * (size_t)(c->syllables + 1));
     j->formants = (float*)malloc(sizeof(float) * 9 * (size_t)(c->formant_rows + 1));
     j->energy = (float*)malloc(sizeof(float) * 3 * (size_t)(c->formant_rows + 1));
-    j->features = (double*)malloc(sizeof(double) * FA_N_FEATURES * (size_t)(c->feature_rows + 1));
+    /* level 11 rows are the 264-dim utterance distributions (cumulative, one per stored segment) */
+    j->features = (double*)malloc(sizeof(double) * (size_t)j->feat_width * (size_t)(c->feature_rows + 1));
     rc = fa_copy_segments(h, 0, j->segs, (size_t)c->segments);
     if (rc >= 0) rc = fa_copy_syllables(h, 0, j->syls, (size_t)c->syllables);
     if (rc >= 0) rc = fa_copy_formants(h, 0, j->formants, (size_t)c->formant_rows);
     if (rc >= 0) rc = fa_copy_energy(h, 0, j->energy, (size_t)c->formant_rows);
-    if (rc >= 0) rc = fa_copy_features(h, 0, j->features, (size_t)c->feature_rows);
+    if (rc >= 0) rc = j->feat_width == FA_N_UTT_FEATURES ? fa_copy_utterance_features(h, 0, j->features, (size_t)c->feature_rows)
+                                                         : fa_copy_features(h, 0, j->features, (size_t)c->feature_rows);
     if (rc >= 0 && j->want_spec) {
       j->spectrum = (float*)malloc(sizeof(float) * (size_t)j->fft_half * (size_t)(c->frames + 1));
       rc = fa_copy_spectrum(h, 0, j->spectrum, (size_t)c->frames);
@@ -200,7 +204,7 @@ static void job_complete(napi_env env, napi_status status, void* data) {
     napi_set_named_property(env, res, "syllables", syls);
     napi_set_named_property(env, res, "formants", make_f32(env, j->formants, 9 * (size_t)c->formant_rows));
     napi_set_named_property(env, res, "energy", make_f32(env, j->energy, 3 * (size_t)c->formant_rows));
-    napi_set_named_property(env, res, "features", make_f64(env, j->features, FA_N_FEATURES * (size_t)c->feature_rows));
+    napi_set_named_property(env, res, "features", make_f64(env, j->features, (size_t)j->feat_width * (size_t)c->feature_rows));
     if (j->want_spec) napi_set_named_property(env, res, "spectrum", make_f32(env, j->spectrum, (size_t)j->fft_half * (size_t)c->frames));
     napi_resolve_deferred(env, j->deferred, res);
   }
@@ -210,10 +214,11 @@ static void job_complete(napi_env env, napi_status status, void* data) {
   free(j);
 }
 
-/* analyze(handle, Float32Array pcm, sampleRate, wantSpectrum, fftSize) -> Promise */
+/* analyze(handle, Float32Array pcm, sampleRate, wantSpectrum, fftSize, outputLevel) -> Promise
+ * analyze(handle, Uint32Array frames, bands, false, fftSize, outputLevel)       -> Promise (frames = spectrum_push input) */
 static napi_value Analyze(napi_env env, napi_callback_info info) {
-  size_t argc = 5;
-  napi_value argv[5], promise, name;
+  size_t argc = 6;
+  napi_value argv[6], promise, name;
   CHECK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
   if (argc < 3) { napi_throw_error(env, NULL, "Invalid audio source"); return NULL; }
   job_t* j = (job_t*)calloc(1, sizeof(job_t));
@@ -223,7 +228,8 @@ static napi_value Analyze(napi_env env, napi_callback_info info) {
   size_t len = 0;
   bool is_ta = false;
   if (napi_get_value_external(env, argv[0], &hp) != napi_ok || !hp || napi_is_typedarray(env, argv[1], &is_ta) != napi_ok || !is_ta ||
-      napi_get_typedarray_info(env, argv[1], &tt, &len, &pdata, NULL, NULL) != napi_ok || tt != napi_float32_array) {
+      napi_get_typedarray_info(env, argv[1], &tt, &len, &pdata, NULL, NULL) != napi_ok ||
+      (tt != napi_float32_array && tt != napi_uint32_array)) {
     free(j);
     napi_throw_error(env, NULL, "Invalid audio source");
     return NULL;
@@ -232,7 +238,11 @@ static napi_value Analyze(napi_env env, napi_callback_info info) {
   napi_get_value_int32(env, argv[2], &sr);
   if (argc >= 4) { bool b = false; if (napi_get_value_bool(env, argv[3], &b) == napi_ok) ws = b; }
   if (argc >= 5) napi_get_value_int32(env, argv[4], &fft);
+  int32_t level = 0;
+  if (argc >= 6) napi_get_value_int32(env, argv[5], &level);
   j->h = (fa_handle*)hp; j->pcm = (const float*)pdata; j->n = len; j->sr = sr; j->want_spec = ws; j->fft_half = fft / 2;
+  j->feat_width = level == FA_LEVEL_UTTERANCE ? FA_N_UTT_FEATURES : FA_N_FEATURES;
+  j->is_frames = tt == napi_uint32_array;   /* Uint32Array = the segmentor's own frames (spectrum_push); argv[2] = bands */
   CHECK(napi_create_reference(env, argv[1], 1, &j->pcm_ref)); /* keep the PCM alive while the pool thread reads it */
   CHECK(napi_create_promise(env, &j->deferred, &promise));
   CHECK(napi_create_string_utf8(env, "fa_b200.analyze", NAPI_AUTO_LENGTH, &name));

@@ -94,6 +94,18 @@ function engine() {
 function segmentCallbacks(level, res, labels) {
   const step = a.window_step / 1e3, calls = [];
   const stored = res.segments.filter((s) => s.stored >= 0);
+  if (level === 11) {
+    // b(0, label, get_clip_timestamps() @B31365, get_utterance_features(u, h) @B107983) after every stored segment
+    let k = 0;
+    res.segments.forEach((s, si) => {
+      if (s.stored < 0) return;
+      let t = 0;
+      for (let n = 0; n <= si; n++) t += res.segments[n].len;
+      calls.push([0, labels, [res.segments[0].start * step, (t + 1) * step], Array.from(res.features.subarray(264 * k, 264 * (k + 1)))]);
+      k++;
+    });
+    return calls;
+  }
   stored.forEach((s, e) => {
     const ci = res.segments[e];
     const rows = [];
@@ -139,7 +151,7 @@ function LaunchAudioNodes(context_source, source_obj = null, callback = null, fi
     const level = a.output_level;
     let eng;
     try { eng = engine(); } catch (e) { state.playing = false; return reject(String(e.message || e)); }
-    native.analyze(eng, pcm, src.sampleRate, level <= 2, a.fftSize).then((res) => {
+    native.analyze(eng, pcm, src.sampleRate, level <= 2, a.fftSize, level).then((res) => {
       if (level <= 2) {
         if (!test_play && callback) callback(0, file_labels, [0, res.counts.frames * a.window_step / 1e3], res.spectrum);
       } else {
