@@ -11,7 +11,7 @@
  *   - stats      /root/reference/dist/main.js:2@B1065-B2714 == /root/reference/src/stats.js:29-64,
  *   - utterance  /root/reference/dist/main.js:2@B107866-B110125 (inner module 7),
  * were EXECUTED in the build container by oracle/minijs (an ECMAScript-subset interpreter written
- * for this purpose -- the image has no JS engine) on 72 inputs; their outputs are committed as
+ * for this purpose -- the image has no JS engine) on 83 inputs; their outputs are committed as
  * tests/golden/ref_js.json and tests/test_reference_js.py holds this file to them bit for bit.
  * Stage S1 / S1b (spectrum + adapter) remains "parity unpinned" BY NECESSITY: the reference's
  * spectrum stage is an un-vendored CDN worklet (no code, no vectors), so the front end below is a

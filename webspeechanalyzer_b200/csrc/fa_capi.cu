@@ -122,6 +122,11 @@ struct fa_handle {
   DevBuf d_win, d_tw, d_tws, d_ws, d_bmi, d_bmw, d_emph;
   DevBuf d_spill, d_trkbase, d_trk_i, d_trk_d, d_trk_slot, d_pt_i, d_pt_e, d_rows, d_rowlist;
   DevBuf d_segs, d_syls, d_formants, d_energy, d_features, d_counts, d_off;
+  DevBuf d_frctl, d_frv, d_epochs, d_work, d_k3q;   // K3 mode 1: per-frame control record, epoch table, work list, queue counters
+  int k3_cfg = -1;       // FA_K3_MODE: 0 = serial one-warp-per-utterance kernel, 1 = control scan + epoch-parallel tracking,
+                         // unset = automatic (prepare): long utterances / streams take mode 1, short ones mode 0
+  int k3_mode = 0;
+  int k3_workers = 0;    // warps of the epoch-tracking grid
   DevBuf g_segs, g_syls, g_formants, g_energy, g_features;
   int n_weights = 0;
   long long track_total = 0, urow_total = 0;
@@ -283,6 +288,9 @@ int fa_create(const fa_config* cfg, int device, fa_handle** out) {
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lowest = greatest priority
   if (const char* ev = getenv("FA_K3_PRIO")) h->k3_priority = atoi(ev) != 0;
   if (const char* ev = getenv("FA_TRACE")) h->trace = atoi(ev) != 0;
+  if (const char* ev = getenv("FA_K3_MODE")) h->k3_cfg = atoi(ev) != 0;
+  h->k3_workers = prop.multiProcessorCount * 14;   // 7 CTAs x 2 warps per SM (shared memory bound)
+  if (const char* ev = getenv("FA_K3_WORKERS")) { const int v = atoi(ev); if (v >= 32 && v <= 1 << 16) h->k3_workers = v; }
 
   // Streams are created on first use (ensure_sub_streams): the device has at most 32 hardware work queues
   // (CUDA_DEVICE_MAX_CONNECTIONS, default 8) and streams beyond that alias onto the same queue, where a stream that waits
@@ -305,7 +313,7 @@ int fa_destroy(fa_handle* h) {
                     &h->d_win, &h->d_tw, &h->d_tws, &h->d_ws, &h->d_bmi, &h->d_bmw, &h->d_emph, &h->d_spill, &h->d_trkbase, &h->d_trk_i,
                     &h->d_trk_d, &h->d_trk_slot, &h->d_pt_i, &h->d_pt_e, &h->d_rows, &h->d_rowlist, &h->d_segs, &h->d_syls,
                     &h->d_formants, &h->d_energy, &h->d_features, &h->d_counts, &h->d_off, &h->g_segs, &h->g_syls,
-                    &h->g_formants, &h->g_energy, &h->g_features})
+                    &h->g_formants, &h->g_energy, &h->g_features, &h->d_frctl, &h->d_frv, &h->d_epochs, &h->d_work, &h->d_k3q})
     b->release();
   for (HostBuf* b : {&h->h_pcm, &h->h_frames, &h->h_meta, &h->h_counts, &h->h_off, &h->h_segs, &h->h_syls, &h->h_formants, &h->h_energy,
                      &h->h_features})
@@ -498,6 +506,10 @@ static int prepare(fa_handle* h) {
   const int n = (int)h->utts.size();
   const long long F = h->total_frames;
   cudaStream_t s = h->stream;
+  // K3 mode: the split costs one extra (cheap) sequential pass per frame and pays off when an utterance holds many
+  // segments -- measured on B200: C2 (200 frames, 1.75 segments per utterance) 1.18 ms serial vs 1.38 ms split, the
+  // one-hour stream (144 000 frames, 541 segments) 641 ms serial vs 124 ms split
+  h->k3_mode = h->k3_cfg >= 0 ? h->k3_cfg : (F / std::max(n, 1) >= 1000 ? 1 : 0);
   // device layout of the PCM: [staging | caller buffers ...], each region 16-byte aligned
   long long dev = 0;
   h->regions[0].n = h->staged;
@@ -522,7 +534,9 @@ static int prepare(fa_handle* h) {
     m[n + i] = u.n;
     m[2 * n + i] = u.row0;
     m[3 * n + 1 + i] = tb;
-    tb += (long long)u.frames * 16 + 64;
+    // track table: mode 0 (serial) 16 per frame; mode 1 gives every epoch its own frame range of `maxp` entries per frame
+    // (tracks <= points <= accepted peaks <= maxp per frame), so no epoch can overflow its slice
+    tb += h->k3_mode == 1 ? (long long)u.frames * h->maxp + 64 : (long long)u.frames * 16 + 64;
     m[4 * n + 2 + i] = ub;
     ub += u.frames / std::max<long long>(seg_span, 1) + 2;
   }
@@ -551,7 +565,14 @@ static int prepare(fa_handle* h) {
     FA_CUDA(h->d_pt_e.reserve(P * sizeof(double)));
     FA_CUDA(h->d_rows.reserve((Fz + nz) * 2 * sizeof(int)));
     FA_CUDA(h->d_rowlist.reserve(P * sizeof(int)));
-    FA_CUDA(h->d_spill.reserve(nz * 6 * 128 * sizeof(unsigned long long)));
+    FA_CUDA(h->d_spill.reserve(std::max<size_t>(nz, (size_t)h->k3_workers) * 6 * 128 * sizeof(unsigned long long)));
+    if (h->k3_mode == 1) {
+      FA_CUDA(h->d_frctl.reserve(Fz * sizeof(unsigned)));
+      FA_CUDA(h->d_frv.reserve(Fz * sizeof(double)));
+      FA_CUDA(h->d_epochs.reserve((Fz + nz) * sizeof(FaEpoch)));
+      FA_CUDA(h->d_work.reserve((Fz + nz) * sizeof(int2)));
+      FA_CUDA(h->d_k3q.reserve(2 * kMaxSub * sizeof(int)));
+    }
     FA_CUDA(h->d_segs.reserve((Fz + nz) * sizeof(fa_segment)));
     FA_CUDA(h->d_syls.reserve((Fz + nz) * sizeof(fa_syllable)));
     FA_CUDA(h->d_formants.reserve(Fz * 9 * sizeof(float)));
@@ -727,6 +748,13 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
     g.row_count = h->d_rows.as<int>(); g.row_off = g.row_count + R; g.row_list = h->d_rowlist.as<int>();
     g.cs_spill = h->d_spill.as<unsigned long long>();
     g.finalize_in_smem = getenv("FA_K3_FINALIZE_HBM") ? 0 : 1;
+    g.mode = h->k3_mode;
+    if (g.mode == 1) {
+      g.fr_ctl = h->d_frctl.as<unsigned>(); g.fr_v = h->d_frv.as<double>(); g.epochs = h->d_epochs.as<FaEpoch>();
+      g.work = h->d_work.as<int2>() + (sb.r0 + sb.u0);      // the sub-batch's slice (capacity: its frames + utterances)
+      g.work_count = h->d_k3q.as<int>() + 2 * slot;
+      g.n_workers = h->k3_workers;
+    }
     g.segs = h->d_segs.as<fa_segment>(); g.syls = h->d_syls.as<fa_syllable>();
     g.formants = h->d_formants.as<float>(); g.energy = h->d_energy.as<float>();
     int* cnt = h->d_counts.as<int>();
@@ -740,6 +768,8 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
       fp.utt_begin = sb.u0; fp.utt_count = sb.u1 - sb.u0;
       fp.segs = g.segs; fp.n_segs = g.n_segs; fp.syls = g.syls; fp.n_syls = g.n_syls; fp.formants = g.formants;
       fp.features = h->d_features.as<double>(); fp.n_feat = cnt + 4 * n;
+      // rows of one utterance are spread over `row_slices` CTAs (a one-hour stream has ~2000 rows in ONE utterance)
+      fp.row_slices = (int)std::min<long long>(64, std::max<long long>(1, (sb.r1 - sb.r0) / std::max(1, sb.u1 - sb.u0) / 256));
       FA_CUDA(fa_launch_features(fp, s3, &h->launches));
     }
     if (c.output_level == FA_LEVEL_UTTERANCE) {
@@ -768,6 +798,7 @@ static int run_device(fa_handle* h, bool with_h2d, bool with_sink) {
   const long long* meta = h->d_meta.as<long long>();
   h->launches = 0;
   if (c.output_level >= 3) FA_CUDA(cudaMemsetAsync(h->d_counts.p, 0, sizeof(int) * 6 * (size_t)n, s));
+  if (c.output_level >= 3 && h->k3_mode == 1) FA_CUDA(cudaMemsetAsync(h->d_k3q.p, 0, 2 * kMaxSub * sizeof(int), s));
   FA_CUDA(cudaEventRecord(h->ev[0], s));
   const std::vector<SubBatch> subs = plan(h, with_h2d || (with_sink && h->spec_sink));
   const bool sink = with_sink && h->spec_sink && h->want_spec && !h->frames_mode;

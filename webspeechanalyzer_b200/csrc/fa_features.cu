@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kFeatThreads) fa_features_kernel(const FaFeatu
   }
   __syncthreads();
   const int R = s_rows;
-  for (int row = warp; row < R; row += kFeatThreads / 32) {
+  for (int row = warp + (int)blockIdx.y * (kFeatThreads / 32); row < R; row += (kFeatThreads / 32) * (int)gridDim.y) {
     const float* F;
     int len;
     const fa_segment* sg;
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(128) fa_gather_kernel(const FaGatherArgs g) {
 
 cudaError_t fa_launch_features(const FaFeatureParams& p, cudaStream_t s, int* launches) {
   if (p.utt_count <= 0) return cudaSuccess;
-  fa_features_kernel<<<p.utt_count, kFeatThreads, 0, s>>>(p);
+  fa_features_kernel<<<dim3(p.utt_count, p.row_slices > 0 ? p.row_slices : 1), kFeatThreads, 0, s>>>(p);
   if (launches) (*launches)++;
   return cudaGetLastError();
 }

@@ -66,7 +66,16 @@ struct FaPeaksParams {
   double* gsum;                  // [F_total] sum e[1..B-1]
 };
 
-// per-utterance scan state that survives across time chunks (reserved for the stream stitcher)
+// One finalisation of the control scan (K3a -> K3b): the frames of the track epoch that ends in it and the scalar state
+// O() @B27088 reads.  Index in the per-utterance table = index in seg_ci.
+struct __align__(16) FaEpoch {
+  int first;                     // first frame of the epoch (frame index inside the utterance): tracks were cleared before it
+  int last;                      // last frame to replay (the frame that triggered the finalisation; F - 1 for segment_truncate)
+  int n_arg, no_fm_segs, current_frame, c_ci;
+  int trk_off, trk_cap;          // the epoch's slice of the utterance's track table (capacity = accepted peaks of the epoch)
+  double y, v;                   // thresholds at finalisation
+};
+
 struct FaSegmentParams {
   const FaCand* cand;            // [F_total][maxp]
   const int* ncand;
@@ -87,6 +96,14 @@ struct FaSegmentParams {
   int* row_list;                      // [F_total * maxp]
   unsigned long long* cs_spill;       // [n_utt][6][128] candidate scores beyond the three kept in shared memory
   int finalize_in_smem;               // 1: segments that fit are finalised in shared memory (0 forces the HBM path: tests)
+  // mode 1: control scan (K3a, warp per utterance) + epoch-parallel tracking / finalisation (K3b, warp per epoch) + fix-up (K3c)
+  int mode;
+  unsigned* fr_ctl;                   // [F_total] bit 31: the frame reaches accumulate_fm; low bits: its (stale) label c_ci
+  double* fr_v;                       // [F_total] gate threshold v after the frame (= v at the start of the next frame)
+  FaEpoch* epochs;                    // [F_total + n_utt] per-utterance tables at base frame_off[u] + u
+  int2* work;                         // epoch work list of this sub-batch: (utterance, seg_ci index)
+  int* work_count;                    // [2]: entries in the list, next entry to take
+  int n_workers;                      // warps of the K3b grid (cs_spill has one slice per worker in mode 1)
   // outputs (per utterance tables at base frame_off[u] + u, capacity F_u + 1)
   fa_segment* segs; int* n_segs; int* n_stored;
   float* formants;                    // [F_total][9]   rows of utterance u start at frame_off[u]
@@ -103,6 +120,7 @@ struct FaFeatureParams {
   const fa_segment* segs; const int* n_segs;
   const fa_syllable* syls; const int* n_syls;
   const float* formants;
+  int row_slices;                     // CTAs per utterance (grid.y): rows are dealt round-robin over slices x warps
   double* features;                   // [(F_total + n_utt)][53] per-utterance rows at base frame_off[u] + u
   int* n_feat;                        // [n_utt]
 };

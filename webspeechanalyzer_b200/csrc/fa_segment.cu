@@ -83,8 +83,10 @@ struct Bases {
   long long row0;   // first frame row of the utterance
   long long tb;     // track table base
   long long pb;     // point pool base
-  long long sb;     // segment / syllable / row-scratch base (row0 + u)
+  long long sb;     // segment / syllable base (row0 + u)
+  long long rb;     // row-scratch base (row_count / row_off)
   int F, tcap, u;
+  int spill;        // slice of cs_spill (utterance in the serial kernel, worker warp in the epoch-parallel one)
 };
 
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
@@ -130,12 +132,18 @@ __device__ __forceinline__ void seg_reset(ScanState& st, WarpShared& S, int star
   __syncwarp();
 }
 
-// C() @B28506
-__device__ __forceinline__ void noise_gate(ScanState& st, WarpShared& S, double e, const int lane) {
+// C() @B28506 without the track reset: returns true when the gate asks for L(0).
+// Only reached with the automatic gate, where e, y, x, v, v0, T are integer-valued doubles far below 2^53 (amplitudes are
+// uint32, every update is a parseInt) -- so the reference's quotient tests are decided exactly by integer-exact products
+// instead of FP64 divisions (a correctly rounded q = a/b with |a/b - c| >= 1/b >> ulp(c) compares with c like a/b does):
+//   e > x/100  <=>  100 e > x        T/k < 30 v  <=>  T < 30 v k        v > v0/10  <=>  10 v > v0
+//   parseInt(v0/20) = floor(v0/20)   (v0 < 2^32: unsigned division by a constant)
+__device__ __forceinline__ bool gate_update(ScanState& st, double e) {
+  bool reset = false;
   st.w++;
   if (e > st.y || (st.w > 40 && e > 2 * st.v)) {
     if (e >= st.y) { st.w = 0; st.x = st.y = e; }
-    else if (e > st.x / 100) { st.y -= fa_js_parse_int(st.y / 8); st.w = 35; }
+    else if (100 * e > st.x) { st.y -= fa_js_parse_int(st.y / 8); st.w = 35; }
     const double t = fa_js_log10(st.y);
     if (t > 7) st.v = fa_js_parse_int(fa_js_pow(10, t - 3) / 20);
     else if (t > 6) st.v = fa_js_parse_int(fa_js_pow(10, t - 3) / 2);
@@ -144,13 +152,19 @@ __device__ __forceinline__ void noise_gate(ScanState& st, WarpShared& S, double 
     else if (t > 1) st.v = fa_js_parse_int(st.y / 10);
     else st.v = 1;
     st.v0 = st.v;
-    if (st.k > 0 && st.T / (double)st.k < 30 * st.v) { seg_reset(st, S, 0, lane); st.k = 0; st.T = 0; }
+    if (st.k > 0 && st.T < 30 * st.v * (double)st.k) { reset = true; st.k = 0; st.T = 0; }
     st.T += st.y;
     st.k += 1;
-  } else if (st.v > 10 && st.v > st.v0 / 10 && st.w > 20) {
-    st.v -= fa_js_parse_int(st.v0 / 20);
+  } else if (st.v > 10 && 10 * st.v > st.v0 && st.w > 20) {
+    st.v -= (double)((unsigned)st.v0 / 20u);
     if (st.v < 10) st.v = 10;
   }
+  return reset;
+}
+
+// C() @B28506
+__device__ __forceinline__ void noise_gate(ScanState& st, WarpShared& S, double e, const int lane) {
+  if (gate_update(st, e)) seg_reset(st, S, 0, lane);
 }
 
 // accumulate_fm @B35952
@@ -163,7 +177,7 @@ __device__ __forceinline__ void accumulate_fm(const FaSegmentParams& p, WarpShar
   int B = p.B;
   asm volatile("" : "+r"(B));
   const int n_slots = st.n_slots;
-  unsigned long long* spill = p.cs_spill + (size_t)bs.u * ((CMAX - CSM) * ACAP);  // > 3 scoring candidates in a window: rare
+  unsigned long long* spill = p.cs_spill + (size_t)bs.spill * ((CMAX - CSM) * ACAP);  // > 3 scoring candidates in a window: rare
   // (1) lane per track slot: expire, window of candidate peaks, scores, arg-max per peak (atomicMax on the bits)
   bool bad = false;
   for (int r0 = 0; r0 < n_slots; r0 += 32) {
@@ -619,8 +633,8 @@ __device__ __noinline__ int finalize_segment(const FaSegmentParams p, ScanState&
   st.n_segs++;
 
   // rows: which points land on which frame row
-  int* rc = p.row_count + bs.sb;
-  int* ro = p.row_off + bs.sb;
+  int* rc = p.row_count + bs.rb;
+  int* ro = p.row_off + bs.rb;
   for (int r = lane; r < len; r += 32) rc[r] = 0;
   __syncwarp();
   bool thrown = false;
@@ -778,7 +792,9 @@ __global__ void __launch_bounds__(kBound) fa_segment_kernel(const FaSegmentParam
   asm volatile("" : "+r"(maxp));  // keep it in an ordinary register (ptxas uniform-register hazard, see fa_peaks.cu)
   bs.pb = bs.row0 * maxp;
   bs.sb = bs.row0 + u;
+  bs.rb = bs.sb;
   bs.u = u;
+  bs.spill = u;
   const unsigned lt = (1u << lane) - 1u;
 
   ScanState st;
@@ -863,15 +879,20 @@ __global__ void __launch_bounds__(kBound) fa_segment_kernel(const FaSegmentParam
     if (n > PCAP) { st.overflow = 1; break; }
     __syncwarp();
     const double d = (double)dsum;
+    // exact integer forms of the reference's quotient tests (see gate_update and fa_segctl_kernel)
+    const unsigned long long gi = (unsigned long long)g;
+    const bool weak = gi > dsum && 10ull * dsum < gi - dsum;       // d / (g - d) < 0.1
 
     int fin = -2;
     if (st.c_started < 0) {
-      const double ratio = d > h ? h * (double)(n - 1) / (d - h) : 0;
-      if (n > 0 && pbin > 7 && pbin < p.max_voiced_bin && n > 4 && ratio > 4) { seg_reset(st, S, 0, lane); st.c_started = 0; }
+      bool strong;                                                  // h (n - 1) / (d - h) > 4
+      if (p.auto_gate) strong = d > h && h * (double)(n - 1) > 4 * (d - h);
+      else strong = (d > h ? h * (double)(n - 1) / (d - h) : 0) > 4;
+      if (n > 0 && pbin > 7 && pbin < p.max_voiced_bin && n > 4 && strong) { seg_reset(st, S, 0, lane); st.c_started = 0; }
       else st.no_fm_segs++;
     }
     if (st.c_started >= 0) {
-      if (n == 0 || pbin < 7 || pbin >= p.max_voiced_bin || (n > 3 && d / (g - d) < 0.1)) {
+      if (n == 0 || pbin < 7 || pbin >= p.max_voiced_bin || (n > 3 && weak)) {
         st.no_fm_segs++;
         if (st.c_started < 2) st.c_started--;
         else if ((double)st.no_fm_segs >= p.seg_breaker) fin = finalize_copy(p, S, st, bs, st.c_ci + 1, lane);
@@ -902,16 +923,360 @@ __global__ void __launch_bounds__(kBound) fa_segment_kernel(const FaSegmentParam
   }
 }
 
+
+// =====================================================================================================================
+// Mode 1: the scan split in three.  Only the CONTROL state is sequential in time -- the start / pause tests, c_started,
+// no_fm_segs, c_ci and the adaptive gate (y, v, ...) depend on the frame's (n, d, h, p, g) and on each other, never on
+// the tracks: accumulate_fm has no way back into D() (its only outputs are the track table and the c/s energies read at
+// finalisation).  And every finalisation reads tracks that were cleared at a known frame (L(0) / L(-1) / L(1) all end in
+// clear_fm).  So:
+//   K3a fa_segctl_kernel   warp per utterance, registers only: the control scan.  Per frame it records whether the frame
+//                          reaches accumulate_fm, with which (stale) label, and the gate threshold after the frame; per
+//                          finalisation attempt that passes O()'s length test it emits one FaEpoch and queues it.
+//   K3b fa_segtrack_kernel warp per EPOCH (work queue over the sub-batch): replays the epoch's voiced frames through the
+//                          same accumulate_fm and finalises with the recorded scalars.  Segments of one utterance -- and the
+//                          541 segments of a one-hour stream -- are tracked in parallel; pauses and abandoned starts cost
+//                          nothing here.  Rows / syllables go to provisional places inside the epoch's own frame range.
+//   K3c fa_segfix_kernel   warp per utterance: stored indices, dense row / syllable offsets, rows moved down in place.
+// Same arithmetic on the same operands in the same order as the serial kernel => identical bits.
+// =====================================================================================================================
+constexpr int kCtlWarps = 4;
+
+__global__ void __launch_bounds__(kCtlWarps * 32) fa_segctl_kernel(const FaSegmentParams p) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int ui = blockIdx.x * kCtlWarps + wib;
+  if (ui >= p.utt_count) return;
+  const int u = p.utt_begin + ui;
+  const long long row0 = p.frame_off[u], sb = row0 + u;
+  const int F = (int)(p.frame_off[u + 1] - row0);
+  int maxp = p.maxp;
+  asm volatile("" : "+r"(maxp));
+  ScanState st;
+  st.current_frame = 0; st.no_fm_segs = 0; st.c_ci = 0; st.c_started = -1; st.w = 0; st.k = 0;
+  st.y = p.y0; st.v = p.v0; st.x = p.y0; st.v0 = p.v0; st.T = 0; st.s_energy = 0; st.c_energy = 0;
+  st.n_tr = 0; st.n_pts = 0; st.n_slots = 0; st.n_segs = 0; st.n_stored = 0; st.n_rows = 0; st.n_syls = 0;
+  st.overflow = 0;
+  int epoch_first = 0;
+
+  // The frame inputs (count, g, first 32 candidates) are fetched kGroup frames at a time, one group ahead: the scan's
+  // dependent chain per frame is a few hundred cycles, about the latency of ONE L2 / HBM round trip, so a prefetch
+  // distance of one frame would leave the loop memory-latency bound.
+  constexpr int kGroup = 4;
+  uint32_t pkd_n[kGroup], amp_n[kGroup];
+  int nc_n[kGroup];
+  double g_n[kGroup];
+  auto prefetch_group = [&](const int t0) {
+#pragma unroll
+    for (int k = 0; k < kGroup; k++) {
+      const int t = t0 + k;
+      pkd_n[k] = 0u; amp_n[k] = 0u; nc_n[k] = 0; g_n[k] = 0.0;
+      if (t < F) {
+        const size_t row = (size_t)(row0 + t);
+        nc_n[k] = __ldg(p.ncand + row);
+        g_n[k] = __ldg(p.gsum + row);
+        if (lane < maxp) {
+          const uint2 a = __ldg(reinterpret_cast<const uint2*>(p.cand + row * maxp + lane));
+          pkd_n[k] = a.x; amp_n[k] = a.y;
+        }
+      }
+    }
+  };
+  // O()'s acceptance test; an accepted attempt becomes seg_ci[n_segs] and one unit of work for K3b
+  auto attempt = [&](const int n_arg, const int last) {
+    const int len = n_arg - st.no_fm_segs;
+    if (!(len > p.seg_min_frames && st.c_started >= 2)) return;
+    if (lane == 0) {
+      FaEpoch e;
+      e.first = epoch_first; e.last = last; e.n_arg = n_arg; e.no_fm_segs = st.no_fm_segs;
+      // tracks <= points <= accepted peaks <= maxp per frame: the epoch's frame range of the track table always suffices
+      e.current_frame = st.current_frame; e.c_ci = st.c_ci; e.trk_off = epoch_first * maxp; e.trk_cap = (last - epoch_first + 1) * maxp;
+      e.y = st.y; e.v = st.v;
+      p.epochs[sb + st.n_segs] = e;
+      const int w = atomicAdd(p.work_count, 1);
+      p.work[w] = make_int2(u, st.n_segs);
+    }
+    st.n_segs++;
+  };
+  prefetch_group(0);
+  for (int t0 = 0; t0 < F && !st.overflow; t0 += kGroup) {
+   uint32_t pkd_c[kGroup], amp_c[kGroup];
+   int nc_c[kGroup];
+   double g_c[kGroup];
+#pragma unroll
+   for (int k = 0; k < kGroup; k++) { pkd_c[k] = pkd_n[k]; amp_c[k] = amp_n[k]; nc_c[k] = nc_n[k]; g_c[k] = g_n[k]; }
+   prefetch_group(t0 + kGroup);
+#pragma unroll
+   for (int k = 0; k < kGroup; k++) {
+    const int t = t0 + k;
+    if (t >= F || st.overflow) break;
+    st.current_frame++;
+    const uint32_t pkd0 = pkd_c[k], amp0 = amp_c[k];
+    const int nc = min(nc_c[k], maxp);
+    if (nc_c[k] > maxp) st.overflow = 1;
+    const double g = g_c[k];
+    const double v = st.v;
+    const int t_stale = st.c_ci;
+    int n = 0, pbin = 0;
+    unsigned long long dsum = 0;
+    double h = 2 * v;
+    auto filter = [&](const int c0, const uint32_t pkd, const uint32_t amp) {
+      const bool acc = c0 + lane < nc && (double)amp > v;
+      const unsigned m = __ballot_sync(FULL, acc);
+      if (m == 0u) return;
+      const int pk = (pkd >> 16) & 0xff;
+      n += __popc(m);
+      const uint32_t a = acc ? amp : 0u;
+      dsum += (unsigned long long)__reduce_add_sync(FULL, a & 0xffffu) +
+              ((unsigned long long)__reduce_add_sync(FULL, a >> 16) << 16);
+      const bool hp = acc && !((pkd >> 24) & 1u);
+      const uint32_t mx = __reduce_max_sync(FULL, hp ? amp : 0u);
+      const unsigned who = __ballot_sync(FULL, hp && amp == mx);
+      if (who && (double)mx > h) {
+        h = (double)mx;
+        pbin = __shfl_sync(FULL, pk, __ffs(who) - 1);
+      }
+    };
+    filter(0, pkd0, amp0);
+    for (int c0 = 32; c0 < nc; c0 += 32) {
+      uint2 a = make_uint2(0u, 0u);
+      if (c0 + lane < nc) a = __ldg(reinterpret_cast<const uint2*>(p.cand + (size_t)(row0 + t) * maxp + c0 + lane));
+      filter(c0, a.x, a.y);
+    }
+    if (n > PCAP) { st.overflow = 1; break; }
+    const double d = (double)dsum;
+    // d and g are exact integers (sums of uint32): d/(g-d) < 0.1 <=> 10 d < g - d, and with the automatic gate h is an
+    // integer too: h (n-1)/(d-h) > 4 <=> h (n-1) > 4 (d-h)   (same argument as in gate_update; d/0 = inf fails both ways)
+    const unsigned long long gi = (unsigned long long)g;
+    const bool weak = gi > dsum && 10ull * dsum < gi - dsum;
+    bool voiced = false, finalised = false;
+    auto clear = [&](const int started) {   // L(started): the tracks are cleared, a new epoch starts with this frame
+      st.c_ci = 0; st.c_started = started; st.no_fm_segs = 0;
+      epoch_first = t;
+    };
+    if (st.c_started < 0) {
+      bool strong;
+      if (p.auto_gate) strong = d > h && h * (double)(n - 1) > 4 * (d - h);
+      else strong = (d > h ? h * (double)(n - 1) / (d - h) : 0) > 4;   // fixed gate: h = 2 v need not be an integer
+      if (n > 0 && pbin > 7 && pbin < p.max_voiced_bin && n > 4 && strong) clear(0);
+      else st.no_fm_segs++;
+    }
+    if (st.c_started >= 0) {
+      if (n == 0 || pbin < 7 || pbin >= p.max_voiced_bin || (n > 3 && weak)) {
+        st.no_fm_segs++;
+        if (st.c_started < 2) st.c_started--;
+        else if ((double)st.no_fm_segs >= p.seg_breaker) { attempt(st.c_ci + 1, t); finalised = true; }
+        else if (p.auto_gate) { if (gate_update(st, h)) clear(0); }
+      } else {
+        if (p.auto_gate) { if (gate_update(st, h)) clear(0); }
+        voiced = true;
+        if (st.c_started < 2) st.c_started++; else st.no_fm_segs = 0;
+      }
+    }
+    st.c_ci++;
+    if (finalised) { st.c_ci = 0; st.c_started = -1; st.no_fm_segs = 0; epoch_first = t + 1; }
+    if (lane == 0) {
+      p.fr_ctl[row0 + t] = voiced ? (0x80000000u | (unsigned)t_stale) : 0u;
+      p.fr_v[row0 + t] = st.v;
+    }
+   }
+  }
+  if (!st.overflow) attempt(st.c_ci, F - 1);   // segment_truncate @B30800
+  if (lane == 0) {
+    p.n_segs[u] = st.n_segs;
+    p.overflow[u] = st.overflow;
+  }
+}
+
+template <int kBound>
+__global__ void __launch_bounds__(kBound) fa_segtrack_kernel(const FaSegmentParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WarpShared* sh = reinterpret_cast<WarpShared*>(smem_raw);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  WarpShared& S = sh[wib];
+  const int worker = blockIdx.x * (int)(blockDim.x >> 5) + wib;
+  int maxp = p.maxp;
+  asm volatile("" : "+r"(maxp));
+  const unsigned lt = (1u << lane) - 1u;
+  const int n_work = *reinterpret_cast<volatile int*>(p.work_count);
+  for (;;) {
+    int wi = 0;
+    if (lane == 0) wi = atomicAdd(p.work_count + 1, 1);
+    wi = __shfl_sync(FULL, wi, 0);
+    if (wi >= n_work) break;
+    const int2 wk = p.work[wi];
+    const int u = wk.x;
+    Bases bs;
+    bs.row0 = p.frame_off[u];
+    bs.F = (int)(p.frame_off[u + 1] - bs.row0);
+    bs.sb = bs.row0 + u;
+    const FaEpoch E = p.epochs[bs.sb + wk.y];
+    bs.tb = p.track_base[u] + E.trk_off;
+    bs.tcap = E.trk_cap;
+    bs.pb = (bs.row0 + E.first) * maxp;     // the epoch's own frame range of the point pool
+    bs.rb = bs.sb + E.first;                // ... and of the row scratch
+    bs.u = u;
+    bs.spill = worker;
+    ScanState st;
+    st.current_frame = E.current_frame; st.no_fm_segs = E.no_fm_segs; st.c_ci = E.c_ci; st.c_started = 2;
+    st.w = 0; st.k = 0; st.y = E.y; st.v = E.v; st.x = E.y; st.v0 = E.v; st.T = 0; st.s_energy = 0; st.c_energy = 0;
+    st.n_tr = 0; st.n_pts = 0; st.n_slots = 0;
+    st.n_segs = wk.y;         // -> segs[sb + seg_ci index]
+    st.n_stored = 0;          // provisional: K3c numbers the stores
+    st.n_rows = E.first;      // provisional row offset: rows land inside the epoch's frame range (len <= its frames)
+    st.n_syls = E.first;      // provisional syllable offset, same argument
+    st.overflow = 0;
+    for (int r = lane; r < ACAP; r += 32) S.t_id[r] = -1;
+    if (lane <= FA_MAX_BANDS / 32) S.pmask[lane] = 0u;
+    __syncwarp();
+    // software prefetch of the next frame's control record, thresholds, count, g and first 32 candidates
+    unsigned ctl_n = 0u;
+    double v_n = 0, vmin_n = 0, g_n = 0;
+    int nc_n = 0;
+    uint4 a_n = make_uint4(0u, 0u, 0u, 0u), b_n = a_n;
+    auto prefetch = [&](const int t) {
+      const size_t row = (size_t)(bs.row0 + t);
+      ctl_n = __ldg(p.fr_ctl + row);
+      v_n = t > 0 ? __ldg(p.fr_v + row - 1) : p.v0;   // the gate at the start of the frame
+      vmin_n = __ldg(p.fr_v + row);                   // ... and after C(h): what accumulate_fm receives
+      nc_n = __ldg(p.ncand + row);
+      g_n = __ldg(p.gsum + row);
+      if (lane < maxp) {
+        const uint4* c4 = reinterpret_cast<const uint4*>(p.cand + row * maxp + lane);
+        a_n = __ldg(c4); b_n = __ldg(c4 + 1);
+      }
+    };
+    if (E.first <= E.last) prefetch(E.first);
+    for (int t = E.first; t <= E.last && !st.overflow; t++) {
+      const size_t row = (size_t)(bs.row0 + t);
+      const unsigned ctl = ctl_n;
+      const double v = v_n, vmin = vmin_n, g = g_n;
+      const int nc = min(nc_n, maxp);
+      const uint4 a0 = a_n, b0 = b_n;
+      if (t < E.last) prefetch(t + 1);
+      if (!(ctl >> 31)) continue;
+      int n = 0;
+      for (int c0 = 0; c0 < nc; c0 += 32) {
+        uint4 a = a0, b = b0;
+        if (c0 > 0) {
+          a = make_uint4(0u, 0u, 0u, 0u); b = a;
+          if (c0 + lane < nc) {
+            const uint4* c4 = reinterpret_cast<const uint4*>(p.cand + row * maxp + c0 + lane);
+            a = __ldg(c4); b = __ldg(c4 + 1);
+          }
+        }
+        const uint32_t pkd = a.x, amp = a.y;
+        const bool acc = c0 + lane < nc && (double)amp > v;
+        const unsigned m = __ballot_sync(FULL, acc);
+        if (m == 0u) continue;
+        if (acc) {
+          const int pk = (pkd >> 16) & 0xff;
+          const int pos = n + __popc(m & lt);
+          if (pos < PCAP) {
+            S.pa[pos] = make_uint2(pkd, amp);
+            S.plh[pos] = make_ulonglong2(a.z | ((unsigned long long)a.w << 32), b.x | ((unsigned long long)b.y << 32));
+            S.best[pos] = 0ull; S.owner[pos] = BIG;
+            S.pidx[pk] = (unsigned char)pos;
+            atomicOr(&S.pmask[pk >> 5], 1u << (pk & 31));
+          }
+        }
+        n += __popc(m);
+      }
+      if (n > PCAP) { st.overflow = 1; break; }
+      __syncwarp();
+      accumulate_fm(p, S, st, bs, n, (int)(ctl & 0x7fffffffu), g, vmin, lane);
+      __syncwarp();
+      if (lane <= FA_MAX_BANDS / 32) S.pmask[lane] = 0u;
+      __syncwarp();
+    }
+    if (!st.overflow) {
+      const int len = E.n_arg - st.no_fm_segs;
+      int r = -3;
+      if (p.finalize_in_smem && finalize_fits(st, len)) r = finalize_fast(p, S, st, bs, E.n_arg, lane);
+      if (r == -3) r = finalize_segment(p, st, bs, E.n_arg, lane);
+    }
+    if (st.overflow && lane == 0) p.overflow[u] = 1;
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kCtlWarps * 32) fa_segfix_kernel(const FaSegmentParams p) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int ui = blockIdx.x * kCtlWarps + wib;
+  if (ui >= p.utt_count) return;
+  const int u = p.utt_begin + ui;
+  const long long row0 = p.frame_off[u], sb = row0 + u;
+  const int nseg = p.n_segs[u];
+  int k = 0, rows = 0, nsyl = 0;
+  if (!p.overflow[u]) {
+    for (int si = 0; si < nseg; si++) {
+      fa_segment sg = p.segs[sb + si];
+      if (sg.stored < 0) continue;       // dropped by the throw: seg_ci keeps it, nothing was stored
+      const int src = sg.row_offset, ssrc = sg.first_syllable;
+      if (src != rows) {                 // rows move down in place: dst < src, ascending chunks, reads before writes
+        float* Fm = p.formants + (size_t)row0 * 9;
+        for (int e0 = 0; e0 < sg.len * 9; e0 += 32) {
+          const int e = e0 + lane;
+          float x = 0.f;
+          if (e < sg.len * 9) x = Fm[(size_t)src * 9 + e];
+          __syncwarp();
+          if (e < sg.len * 9) Fm[(size_t)rows * 9 + e] = x;
+          __syncwarp();
+        }
+        float* Eg = p.energy + (size_t)row0 * 3;
+        for (int e0 = 0; e0 < sg.len * 3; e0 += 32) {
+          const int e = e0 + lane;
+          float x = 0.f;
+          if (e < sg.len * 3) x = Eg[(size_t)src * 3 + e];
+          __syncwarp();
+          if (e < sg.len * 3) Eg[(size_t)rows * 3 + e] = x;
+          __syncwarp();
+        }
+      }
+      for (int j0 = 0; j0 < sg.n_syllables; j0 += 32) {
+        const int j = j0 + lane;
+        fa_syllable sy;
+        if (j < sg.n_syllables) { sy = p.syls[sb + ssrc + j]; sy.stored_seg = k; }
+        __syncwarp();
+        if (j < sg.n_syllables) p.syls[sb + nsyl + j] = sy;
+        __syncwarp();
+      }
+      if (lane == 0) {
+        sg.stored = k; sg.row_offset = rows; sg.first_syllable = nsyl;
+        p.segs[sb + si] = sg;
+      }
+      k++; rows += sg.len; nsyl += sg.n_syllables;
+    }
+  }
+  if (lane == 0) { p.n_stored[u] = k; p.n_rows[u] = rows; p.n_syls[u] = nsyl; }
+}
+
 }  // namespace
 
 cudaError_t fa_launch_segment(const FaSegmentParams& p, cudaStream_t s, int* launches) {
   if (p.utt_count <= 0) return cudaSuccess;
   int kw = kWarps;
   if (const char* ev = getenv("FA_K3_WARPS")) { const int v = atoi(ev); if (v >= 1 && v <= 4) kw = v; }  // tuning knob
-  const int grid = (p.utt_count + kw - 1) / kw;
   const int bytes = (int)sizeof(WarpShared) * kw;
   static int regs = -1;
   if (regs < 0) { const char* ev = getenv("FA_K3_REGS"); regs = ev ? atoi(ev) : 128; }
+  if (p.mode == 1) {
+    fa_segctl_kernel<<<(p.utt_count + kCtlWarps - 1) / kCtlWarps, kCtlWarps * 32, 0, s>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int grid = (p.n_workers + kw - 1) / kw;
+    auto launch = [&](auto kernel) -> cudaError_t {
+      cudaError_t e2 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (e2 != cudaSuccess) return e2;
+      kernel<<<grid, kw * 32, bytes, s>>>(p);
+      return cudaGetLastError();
+    };
+    e = regs <= 64 ? launch(fa_segtrack_kernel<1024>) : regs <= 96 ? launch(fa_segtrack_kernel<640>) : launch(fa_segtrack_kernel<128>);
+    if (e != cudaSuccess) return e;
+    fa_segfix_kernel<<<(p.utt_count + kCtlWarps - 1) / kCtlWarps, kCtlWarps * 32, 0, s>>>(p);
+    if (launches) (*launches) += 3;
+    return cudaGetLastError();
+  }
+  const int grid = (p.utt_count + kw - 1) / kw;
   auto launch = [&](auto kernel) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
