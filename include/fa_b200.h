@@ -217,6 +217,26 @@ FA_API int fa_copy_features(fa_handle* h, int64_t utt_id, double* dst, size_t ca
 FA_API int fa_copy_utterance_features(fa_handle* h, int64_t utt_id, double* dst, size_t cap_rows);
 
 /* Stage-level taps for parity tests (candidate peaks of stage 2: packed lo | hi<<8 | pk<<16 | last<<24). */
+/* ---- batched MLP inference on feature rows (the web app's emotion classifier) -------------------
+ * Replaces ml5 classifyMultiple on a tf.js Sequential of Dense layers (/root/reference/src/neuralmodel.js:540-585, models
+ * under /root/reference/dist/nnmodel/<db>/cats_<label>/): kernels are row-major [in][out] float32 as in model.weights.bin,
+ * inputs are min-max normalised with the ranges of model_meta.json ((x - min) / (max - min), in double, then float32).
+ * fa_mlp_classify takes host rows (n_rows x dims[0] doubles) and writes n_rows x dims[n_layers] float32 outputs;
+ * fa_mlp_classify_features classifies the feature rows of a finished handle where they are (device), one utterance
+ * (utt_id >= 0) or the whole batch (utt_id < 0), and returns the number of rows.  No CPU path: FA_ERR_NO_DEVICE without a B200. */
+#define FA_MLP_MAX_LAYERS 8
+#define FA_MLP_LINEAR 0
+#define FA_MLP_RELU 1
+#define FA_MLP_SIGMOID 2
+#define FA_MLP_SOFTMAX 3
+typedef struct fa_mlp fa_mlp;
+FA_API int fa_mlp_create(int n_layers, const int* dims /* n_layers + 1 */, const int* activations, const float* const* kernels,
+                         const float* const* biases, const double* in_min, const double* in_max, int device, fa_mlp** out);
+FA_API int fa_mlp_destroy(fa_mlp* m);
+FA_API const char* fa_mlp_last_error(const fa_mlp* m);
+FA_API int fa_mlp_classify(fa_mlp* m, const double* rows, size_t n_rows, float* probs);
+FA_API int fa_mlp_classify_features(fa_mlp* m, fa_handle* h, int64_t utt_id, float* probs, size_t cap_rows);
+
 FA_API int fa_copy_peak_candidates(fa_handle* h, int64_t utt_id, uint32_t* packed, int32_t* counts, size_t cap_rows,
                             int32_t* max_per_frame);
 

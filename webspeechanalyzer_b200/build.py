@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfa_b200.so")
-SOURCES = ["fa_spectrum.cu", "fa_peaks.cu", "fa_segment.cu", "fa_features.cu", "fa_utterance.cu", "fa_capi.cu", "fa_synth.cpp"]
+SOURCES = ["fa_spectrum.cu", "fa_peaks.cu", "fa_segment.cu", "fa_features.cu", "fa_utterance.cu", "fa_mlp.cu", "fa_capi.cu", "fa_synth.cpp"]
 HEADERS = [os.path.join(CSRC, "fa_internal.cuh")] + [os.path.join(ROOT, "include", h)
                                                       for h in ("fa_b200.h", "fa_jsmath.h", "fa_tables.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -1116,6 +1116,32 @@ int fa_copy_utterance_features(fa_handle* h, int64_t utt_id, double* dst, size_t
   return copy_dense(h, utt_id, 3, h->h_features.p, FA_N_UTT_FEATURES * sizeof(double), dst, cap);
 }
 
+int fa_mlp_classify_features(fa_mlp* m, fa_handle* h, int64_t utt_id, float* probs, size_t cap_rows) {
+  if (!m || !h) return FA_ERR_INVALID_ARG;
+  const int lvl = h->cfg.output_level;
+  if (lvl != FA_LEVEL_SEG_FEATURES && lvl != FA_LEVEL_SYL_FEATURES && lvl != FA_LEVEL_UTTERANCE)
+    return fail(h, FA_ERR_INVALID_ARG, "no feature rows at this output_level");
+  if (fa_mlp_in_dim(m) != h->feat_width()) return fail(h, FA_ERR_INVALID_ARG, "model input width != feature row width");
+  int rc = need_results(h);
+  if (rc != FA_OK) return rc;
+  const int n = (int)h->utts.size();
+  const long long* off = h->h_off.as<long long>() + (size_t)3 * (n + 1);
+  long long r0 = 0, nr = off[n];
+  if (utt_id >= 0) {
+    Utt* u = find_utt(h, utt_id);
+    if (!u) return fail(h, FA_ERR_UNKNOWN_UTT, "unknown utterance id");
+    const int i = (int)(u - h->utts.data());
+    r0 = off[i]; nr = off[i + 1] - off[i];
+  }
+  if ((size_t)nr > cap_rows) return fail(h, FA_ERR_CAPACITY, "destination too small");
+  if (nr == 0) return 0;
+  if (!probs) return FA_ERR_INVALID_ARG;
+  // the dense feature table is still on the device (g_features): classify it in place, only the class scores come back
+  rc = fa_mlp_run_device(m, h->g_features.as<double>() + (size_t)r0 * h->feat_width(), (int)nr, probs, h->stream);
+  if (rc < 0) return fail(h, rc, fa_mlp_last_error(m));
+  return (int)nr;
+}
+
 int fa_copy_peak_candidates(fa_handle* h, int64_t utt_id, uint32_t* packed, int32_t* counts, size_t cap_rows,
                             int32_t* max_per_frame) {
   if (!h) return FA_ERR_INVALID_ARG;
