@@ -322,6 +322,63 @@ def main():
                "path": "per batch: fa_reset + fa_submit_pcm_batch (pinned host PCM) + fa_set_spectrum_sink (pinned) + fa_run "
                        "(async) ... fa_sync + fa_copy_{segments,formants,energy,syllables,features}; one handle per batch slot"}
 
+    # ---- the same end-to-end loop for the FEATURE modes alone (Segment Features, no spectrum output), 16-bit PCM in ----
+    # What a WAV-file workload looks like: int16 samples cross PCIe as they are (fa_submit_pcm_i16_batch, converted on the
+    # device) and only the result tables come back.  Reported beside `e2e`; the headline `e2e` above keeps the spectrum.
+    e2e_feat = None
+    if not args.no_e2e:
+        from webspeechanalyzer_b200 import FaConfig
+        cfg2 = FaConfig.default(output_level=5, want_spectrum=0)
+        engs2, pcm16_hosts = [], []
+        for j in range(depth):
+            e = Engine(cfg2, device=local)
+            e.set_stream(streams[j].cuda_stream)
+            e.set_pipeline(1 if args.serial else args.e2e_pipeline)
+            engs2.append(e)
+            ph = torch.empty(int(offs[-1]), dtype=torch.int16, pin_memory=True).numpy()
+            for i, p in enumerate(pcms):
+                ph[offs[i]: offs[i + 1]] = np.clip(np.rint(p * 32768.0), -32768, 32767).astype(np.int16)
+            pcm16_hosts.append(ph)
+        seen2 = []
+
+        def launch2(j):
+            engs2[j].reset()
+            engs2[j].submit_batch(0, pcm16_hosts[j], offs, SR)
+            engs2[j].run()
+
+        def collect2(j):
+            engs2[j].sync()
+            r = engs2[j].result(None)
+            seen2.append(r.segments.nbytes + r.formants.nbytes + r.energy.nbytes + r.features.nbytes + r.syllables.nbytes)
+
+        def steps2(k_steps):
+            inflight = []
+            for k in range(k_steps):
+                j = k % depth
+                if len(inflight) == depth:
+                    collect2(inflight.pop(0))
+                launch2(j)
+                inflight.append(j)
+            while inflight:
+                collect2(inflight.pop(0))
+
+        steps2(2 * depth)
+        barrier()
+        t0 = time.perf_counter()
+        steps2(args.steps)
+        torch.cuda.synchronize()
+        dt2 = time.perf_counter() - t0
+        tt2 = torch.tensor([dt2], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt2, op=dist.ReduceOp.MAX)
+        e2e_feat = {"value": world * audio_per_step * args.steps / float(tt2.item()), "unit": "audio-s/s",
+                    "h2d_bytes_per_step": int(pcm16_hosts[0].nbytes), "d2h_bytes_per_step": int(seen2[-1]),
+                    "ms_per_step": 1e3 * float(tt2.item()) / args.steps, "batches_in_flight": depth,
+                    "path": "Segment Features only (output_level 5, no spectrum output): fa_reset + fa_submit_pcm_i16_batch (pinned int16 "
+                            "PCM, converted on the device) + fa_run ... fa_sync + fa_copy_{segments,formants,energy,syllables,features}"}
+        for e in engs2:
+            e.close()
+
     clocks = sampler.stop()
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -350,7 +407,7 @@ def main():
             "config": {"workload": WORKLOAD, "utterances_per_gpu": n_utt, "parallelism": f"shard-by-utterance x{world}",
                        "batches_in_flight": depth,
                        "l2": "inputs (320 MB PCM + 819 MB spectrum rows per step) exceed the 126 MB L2; no flush needed"},
-            "roofline": {"bound": "hbm", "kernel": {"spectrum": "fa_spectrum_2048_kernel", "peaks": "fa_peaks_kernel",
+            "roofline": {"bound": "hbm", "kernel": {"spectrum": "fa_fftmag_2048_kernel", "peaks": "fa_peaks_kernel",
                                                     "segment": "fa_segment_kernel", "features": "fa_features_kernel"}[top],
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic({"spectrum": "fa_fftmag_2048_kernel", "peaks": "fa_peaks_kernel",
@@ -359,6 +416,7 @@ def main():
                          "note": "segment scan / features are latency bound (sequential state machine), spectrum is FP32-issue bound; see DESIGN.md"},
             "stages": stages,
             "e2e": e2e,
+            "e2e_feature_modes": e2e_feat,
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "results": {"segments": tot["segments"], "feature_rows": tot["feature_rows"], "formant_rows": tot["formant_rows"],

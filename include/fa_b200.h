@@ -172,6 +172,12 @@ FA_API int fa_submit_pcm_i16(fa_handle* h, int64_t utt_id, const int16_t* pcm, s
 FA_API int fa_submit_pcm_batch(fa_handle* h, int64_t first_utt_id, const float* pcm, const int64_t* offsets, int n_utt,
                                int sample_rate);
 
+/* The same for 16-bit PCM (what a WAV file holds): with page-locked caller memory the int16 samples cross PCIe as they are
+ * -- half the bytes of float32 -- and are converted on the device ((float)x * 2^-15, exact, identical to fa_submit_pcm_i16).
+ * Pageable memory is converted on the host and staged like fa_submit_pcm_i16. */
+FA_API int fa_submit_pcm_i16_batch(fa_handle* h, int64_t first_utt_id, const int16_t* pcm, const int64_t* offsets, int n_utt,
+                                   int sample_rate);
+
 /* The segmentor's own input, for callers that bring their own spectrum stage (e.g. frames captured from a browser
  * AnalyserNode / the reference's worklet): `n_frames` rows of `bands` uint32, one row per spectrum_push(frame, idx) of the
  * reference (/root/reference/dist/main.js:2@B30392).  `bands` must equal fa_spec_bands(cfg) -- the reference's own check,

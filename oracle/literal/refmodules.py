@@ -67,7 +67,7 @@ def only_std_NZ(arr):
     mean = array_mean_NZ(arr)
     acc = 0.0
     for v in arr:
-        acc += (v - mean) ** 2
+        acc += jspow(v - mean, 2)   # (x - t) ** 2 is Math.pow in V8: fdlibm returns x * x exactly, glibc pow may be 1 ulp off
     return math.sqrt(acc / len(arr)) if len(arr) else math.nan
 
 
@@ -75,7 +75,7 @@ def mean_std_NZ(arr):
     mean = array_mean_NZ(arr)
     acc = 0.0
     for v in arr:
-        acc += (v - mean) ** 2
+        acc += jspow(v - mean, 2)   # (x - t) ** 2 is Math.pow in V8: fdlibm returns x * x exactly, glibc pow may be 1 ulp off
     return [mean, math.sqrt(acc / len(arr)) if len(arr) else math.nan]
 
 

@@ -76,6 +76,7 @@ struct Region {
   const float* host;   // nullptr for region 0 (resolved at upload: the staging buffer may move while it grows)
   long long n;         // floats
   long long dev_off;   // first float in d_pcm (multiple of 4)
+  const int16_t* host16 = nullptr;  // caller-owned int16 PCM (zero copy): crosses PCIe as int16, converted on the device
 };
 
 struct SubBatch { int u0, u1; long long r0, r1; };
@@ -118,6 +119,7 @@ struct fa_handle {
   bool prepared = false;
   long long total_frames = 0;
   HostBuf h_pcm, h_meta, h_counts, h_off, h_segs, h_syls, h_formants, h_energy, h_features;
+  DevBuf d_pcm16;   // int16 PCM of caller regions, same element index as d_pcm
   DevBuf d_pcm, d_meta, d_spec, d_frames, d_cand, d_ncand, d_gsum, d_counter;
   DevBuf d_win, d_tw, d_tws, d_ws, d_bmi, d_bmw, d_emph;
   DevBuf d_spill, d_trkbase, d_trk_i, d_trk_d, d_trk_slot, d_pt_i, d_pt_e, d_rows, d_rowlist;
@@ -309,7 +311,7 @@ int fa_destroy(fa_handle* h) {
   cudaStreamSynchronize(h->stream);
   for (int i = 0; i < kMaxSub; i++) if (h->sub_stream[i]) cudaStreamSynchronize(h->sub_stream[i]);
   for (int i = 0; i < kMaxSub; i++) if (h->sub_hi[i]) cudaStreamSynchronize(h->sub_hi[i]);
-  for (DevBuf* b : {&h->d_pcm, &h->d_meta, &h->d_spec, &h->d_frames, &h->d_cand, &h->d_ncand, &h->d_gsum, &h->d_counter,
+  for (DevBuf* b : {&h->d_pcm16, &h->d_pcm, &h->d_meta, &h->d_spec, &h->d_frames, &h->d_cand, &h->d_ncand, &h->d_gsum, &h->d_counter,
                     &h->d_win, &h->d_tw, &h->d_tws, &h->d_ws, &h->d_bmi, &h->d_bmw, &h->d_emph, &h->d_spill, &h->d_trkbase, &h->d_trk_i,
                     &h->d_trk_d, &h->d_trk_slot, &h->d_pt_i, &h->d_pt_e, &h->d_rows, &h->d_rowlist, &h->d_segs, &h->d_syls,
                     &h->d_formants, &h->d_energy, &h->d_features, &h->d_counts, &h->d_off, &h->g_segs, &h->g_syls,
@@ -471,6 +473,39 @@ int fa_submit_pcm_batch(fa_handle* h, int64_t first_utt_id, const float* pcm, co
   return first;
 }
 
+int fa_submit_pcm_i16_batch(fa_handle* h, int64_t first_utt_id, const int16_t* pcm, const int64_t* offsets, int n_utt, int sr) {
+  int rc = submit_check(h, sr);
+  if (rc != FA_OK) return rc;
+  if (!pcm || !offsets || n_utt <= 0) return fail(h, FA_ERR_INVALID_ARG, "Invalid audio source");
+  for (int i = 0; i < n_utt; i++)
+    if (offsets[i + 1] < offsets[i] || offsets[0] < 0) return fail(h, FA_ERR_INVALID_ARG, "offsets must be non-decreasing");
+  for (int i = 0; i < n_utt; i++)
+    if (h->index.count(first_utt_id + i)) return fail(h, FA_ERR_INVALID_ARG, "duplicate utterance id");
+  cudaPointerAttributes attr;
+  const bool pinned = cudaPointerGetAttributes(&attr, pcm) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  const int first = (int)h->utts.size();
+  if (pinned) {
+    Region r;
+    r.host = nullptr;
+    r.host16 = pcm + offsets[0];
+    r.n = offsets[n_utt] - offsets[0];
+    r.dev_off = 0;
+    h->regions.push_back(r);
+    const int ri = (int)h->regions.size() - 1;
+    for (int i = 0; i < n_utt; i++) {
+      rc = add_utt(h, first_utt_id + i, ri, offsets[i] - offsets[0], (size_t)(offsets[i + 1] - offsets[i]), sr);
+      if (rc < 0) return rc;
+    }
+  } else {
+    for (int i = 0; i < n_utt; i++) {
+      rc = fa_submit_pcm_i16(h, first_utt_id + i, pcm + offsets[i], (size_t)(offsets[i + 1] - offsets[i]), sr);
+      if (rc < 0) return rc;
+    }
+  }
+  return first;
+}
+
 int fa_submit_frames(fa_handle* h, int64_t utt_id, const uint32_t* frames, size_t n_frames, int bands) {
   if (!h) return FA_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
@@ -548,6 +583,11 @@ static int prepare(fa_handle* h) {
   FA_CUDA(h->d_meta.reserve(sizeof(long long) * (5 * (size_t)n + 3)));
   FA_CUDA(cudaMemcpyAsync(h->d_meta.p, m, sizeof(long long) * (5 * (size_t)n + 3), cudaMemcpyHostToDevice, s));
   FA_CUDA(h->d_pcm.reserve((size_t)(dev + 16) * sizeof(float)));
+  {
+    bool any16 = false;
+    for (const auto& r : h->regions) any16 = any16 || r.host16;
+    if (any16) FA_CUDA(h->d_pcm16.reserve((size_t)(dev + 16) * sizeof(int16_t)));
+  }
   const size_t Fz = (size_t)std::max<long long>(F, 1), nz = (size_t)n;
   FA_CUDA(h->d_spec.reserve(Fz * h->M * sizeof(float)));  // the K1a -> K1b magnitude rows, turned into dB rows in place
   FA_CUDA(h->d_frames.reserve(Fz * h->B * sizeof(uint32_t)));
@@ -664,7 +704,11 @@ static int copy_pcm_range(fa_handle* h, int u0, int u1, cudaStream_t s) {
     const Region& r = h->regions[reg];
     const float* host = reg == 0 ? h->h_pcm.as<float>() : r.host;
     hi = std::min(hi, reg == 0 ? h->staged : r.n);
-    if (hi > lo)
+    if (hi > lo && r.host16) {
+      int16_t* d16 = h->d_pcm16.as<int16_t>() + r.dev_off + lo;
+      FA_CUDA(cudaMemcpyAsync(d16, r.host16 + lo, (size_t)(hi - lo) * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+      FA_CUDA(fa_launch_pcm_i16(d16, h->d_pcm.as<float>() + r.dev_off + lo, hi - lo, s, &h->launches));
+    } else if (hi > lo)
       FA_CUDA(cudaMemcpyAsync(h->d_pcm.as<float>() + r.dev_off + lo, host + lo, (size_t)(hi - lo) * sizeof(float),
                               cudaMemcpyHostToDevice, s));
     i = j;

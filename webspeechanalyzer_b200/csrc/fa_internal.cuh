@@ -150,6 +150,7 @@ struct FaGatherArgs {
   fa_segment* d_segs; fa_syllable* d_syls; float* d_formants; float* d_energy; double* d_features;
 };
 
+cudaError_t fa_launch_pcm_i16(const int16_t* src, float* dst, long long n, cudaStream_t s, int* launches);
 cudaError_t fa_launch_spectrum(const FaSpectrumParams& p, cudaStream_t s, int* launches);
 cudaError_t fa_launch_peaks(const FaPeaksParams& p, cudaStream_t s, int* launches);
 cudaError_t fa_launch_segment(const FaSegmentParams& p, cudaStream_t s, int* launches);

@@ -99,9 +99,12 @@ class Engine:
 
     def submit_batch(self, first_utt_id: int, pcm: np.ndarray, offsets: np.ndarray, sample_rate: int) -> int:
         """Whole batch in one float32 buffer; zero-copy when `pcm` is page-locked (keep it alive until sync())."""
-        assert pcm.dtype == np.float32 and pcm.flags.c_contiguous
+        assert pcm.dtype in (np.float32, np.int16) and pcm.flags.c_contiguous
         offsets = np.ascontiguousarray(offsets, np.int64)
         self._keep = (pcm, offsets)
+        if pcm.dtype == np.int16:      # crosses PCIe as int16 (half the bytes), converted on the device
+            return self._check(self._lib.fa_submit_pcm_i16_batch(self._h, first_utt_id, pcm.ctypes.data, offsets.ctypes.data,
+                                                                 offsets.size - 1, sample_rate))
         return self._check(self._lib.fa_submit_pcm_batch(self._h, first_utt_id, pcm.ctypes.data, offsets.ctypes.data,
                                                          offsets.size - 1, sample_rate))
 
