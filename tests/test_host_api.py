@@ -98,19 +98,12 @@ def test_callback_shapes_and_order_equal_literal_P(level, step):
 def test_dropped_segment_misaligns_times_like_the_reference():
     """Quirk 15: straighten_formants throws when a track point's frame index >= len; seg_ci keeps the entry but the
     stores do not, so later callbacks pair store e with seg_ci[e]."""
+    import sys
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    from framegen import dropped_segment_frames
     B = 128
-    bins = np.arange(B)
-
-    def voiced(c, amps):
-        e = np.zeros(B)
-        for a, cc in zip(amps, c):
-            e += a * np.exp(-0.5 * ((bins - cc) / 1.5) ** 2)
-        return np.rint(e).astype(np.uint32)
-
-    v = voiced([12, 30, 50, 70, 85], [8000, 40000, 8000, 8000, 8000])
-    z = np.zeros(B, np.uint32)
-    # voiced, pause, voiced, voiced, then a long pause -> len 3 but a track point sits at frame 3
-    frames = [v, z, v, v] + [z] * 10 + [v] * 12 + [z] * 10
+    frames = list(dropped_segment_frames(B))
     cfg = FaConfig.default(output_level=5)
     an = oracle.analyze_frames(cfg, np.stack(frames))
     S = Segmentor(5, B, 200, 25.0, 200, 50, True, 100, 10, None, True, [])

@@ -2,13 +2,17 @@
 modules (oracle/literal/refmodules.py) and against the invariants the reference pins."""
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
-from conftest import sha
+from conftest import GOLDEN, sha
 from hypothesis import given, settings, strategies as st
 
-from oracle import oracle
+sys.path.insert(0, GOLDEN)
+from framegen import adversarial_frames, voiced_random_frames  # noqa: E402
+
+from oracle import oracle  # noqa: E402
 from oracle.literal.refmodules import Segmentor, toFixed3
 from webspeechanalyzer_b200 import FaConfig, synth_speech
 
@@ -123,18 +127,9 @@ frames_strategy = st.integers(0, 2 ** 31).flatmap(lambda seed: st.just(seed))
 @given(seed=st.integers(0, 2 ** 31), B=st.sampled_from([32, 128, 256]), F=st.integers(1, 120),
        auto=st.booleans(), level=st.sampled_from([4, 5, 13]))
 def test_oracle_equals_literal_on_random_frames(seed, B, F, auto, level):
-    """Adversarial frames: smooth random spectra with moving bumps, silences and huge / tiny amplitudes."""
-    rng = np.random.default_rng(seed)
-    bins = np.arange(B)
-    fr = np.zeros((F, B))
-    centres = rng.uniform(8, 0.65 * B, size=6)
-    for t in range(F):
-        centres += rng.normal(0, 0.7, size=6)
-        amp = rng.choice([0.0, 1.0, 1.0, 1.0]) * 10 ** rng.uniform(1, 6)
-        for c in centres:
-            fr[t] += amp * rng.uniform(0.2, 1) * np.exp(-0.5 * ((bins - c) / rng.uniform(0.8, 3)) ** 2)
-        fr[t] += rng.uniform(0, 3, size=B)
-    frames = np.rint(fr).astype(np.uint32)
+    """Adversarial frames: smooth random spectra with moving bumps, silences and huge / tiny amplitudes (and, every other
+    example, runs of voiced frames that do open and close segments)."""
+    frames = voiced_random_frames(seed, B, F) if seed % 2 else adversarial_frames(seed, B, F)
     cfg = FaConfig.default(output_level=level, auto_noise_gate=int(auto), voiced_max_db=100.0, voiced_min_db=30.0)
     cfg.n_mel_bins = B
     an = oracle.analyze_frames(cfg, frames)
