@@ -124,6 +124,13 @@ struct fa_handle {
   DevBuf d_win, d_tw, d_tws, d_ws, d_bmi, d_bmw, d_emph;
   DevBuf d_spill, d_trkbase, d_trk_i, d_trk_d, d_trk_slot, d_pt_i, d_pt_e, d_rows, d_rowlist;
   DevBuf d_segs, d_syls, d_formants, d_energy, d_features, d_counts, d_off;
+  // K1b stream mode: chunk work list (utt[], idx[], base[n+1]), speculated entry / true exit states, separate dB rows, fix-up count
+  DevBuf d_chunks, d_state, d_specdb, d_fix;
+  int chunk_frames = 0, warm_frames = 0;
+  long long total_chunks = 0;
+  std::vector<long long> chunk_base;   // host copy of base[]
+  int fixups = -1;                      // chunks recomputed in the last run (fetched lazily)
+  float* spec_rows() const { return (chunk_frames > 0 && want_spec) ? d_specdb.as<float>() : d_spec.as<float>(); }
   DevBuf d_frctl, d_frv, d_epochs, d_work, d_k3q;   // K3 mode 1: per-frame control record, epoch table, work list, queue counters
   int k3_cfg = -1;       // FA_K3_MODE: 0 = serial one-warp-per-utterance kernel, 1 = control scan + epoch-parallel tracking,
                          // unset = automatic (prepare): long utterances / streams take mode 1, short ones mode 0
@@ -315,7 +322,7 @@ int fa_destroy(fa_handle* h) {
                     &h->d_win, &h->d_tw, &h->d_tws, &h->d_ws, &h->d_bmi, &h->d_bmw, &h->d_emph, &h->d_spill, &h->d_trkbase, &h->d_trk_i,
                     &h->d_trk_d, &h->d_trk_slot, &h->d_pt_i, &h->d_pt_e, &h->d_rows, &h->d_rowlist, &h->d_segs, &h->d_syls,
                     &h->d_formants, &h->d_energy, &h->d_features, &h->d_counts, &h->d_off, &h->g_segs, &h->g_syls,
-                    &h->g_formants, &h->g_energy, &h->g_features, &h->d_frctl, &h->d_frv, &h->d_epochs, &h->d_work, &h->d_k3q})
+                    &h->g_formants, &h->g_energy, &h->g_features, &h->d_chunks, &h->d_state, &h->d_specdb, &h->d_fix, &h->d_frctl, &h->d_frv, &h->d_epochs, &h->d_work, &h->d_k3q})
     b->release();
   for (HostBuf* b : {&h->h_pcm, &h->h_frames, &h->h_meta, &h->h_counts, &h->h_off, &h->h_segs, &h->h_syls, &h->h_formants, &h->h_energy,
                      &h->h_features})
@@ -545,6 +552,23 @@ static int prepare(fa_handle* h) {
   // segments -- measured on B200: C2 (200 frames, 1.75 segments per utterance) 1.18 ms serial vs 1.38 ms split, the
   // one-hour stream (144 000 frames, 541 segments) 641 ms serial vs 124 ms split
   h->k3_mode = h->k3_cfg >= 0 ? h->k3_cfg : (F / std::max(n, 1) >= 1000 ? 1 : 0);
+  // K1b stream mode for the same long utterances: chunks of 2048 frames, warm-up long enough for tau^W << 2^-24 plus a
+  // margin for the last-ulp coalescence (FA_K1B_CHUNK=0 disables, FA_K1B_WARMUP overrides W -- the tests force W = 8 to
+  // exercise the fix-up pass); tau close to 1 would need a warm-up as long as a chunk: one pass per utterance then
+  {
+    int ch = (F / std::max(n, 1) >= 1000 && !h->frames_mode) ? 2048 : 0;
+    if (const char* ev = getenv("FA_K1B_CHUNK")) ch = atoi(ev);
+    int warm = 0;
+    if (ch > 0) {
+      const double tau = h->cfg.smoothing;
+      warm = tau <= 0.0 ? 8 : (int)ceil(40.0 * log(2.0) / -log(tau)) + 64;
+      if (const char* ev = getenv("FA_K1B_WARMUP")) warm = atoi(ev);
+      warm = std::max(8, (warm + 7) & ~7);
+      ch = std::max(64, (ch + 7) & ~7);
+      if (!(tau < 1.0) || warm > ch / 2) ch = 0;
+    }
+    h->chunk_frames = ch; h->warm_frames = ch ? warm : 0;
+  }
   // device layout of the PCM: [staging | caller buffers ...], each region 16-byte aligned
   long long dev = 0;
   h->regions[0].n = h->staged;
@@ -631,6 +655,26 @@ static int prepare(fa_handle* h) {
     FA_CUDA(h->g_energy.reserve(Fz * 3 * sizeof(float)));
     if (h->cfg.output_level == 5 || h->cfg.output_level == 13)
       FA_CUDA(h->g_features.reserve((Fz + nz) * FA_N_FEATURES * sizeof(double)));
+  }
+  if (h->chunk_frames > 0) {
+    const int CH = h->chunk_frames;
+    h->chunk_base.assign((size_t)n + 1, 0);
+    for (int i = 0; i < n; i++) h->chunk_base[i + 1] = h->chunk_base[i] + std::max(1, (h->utts[i].frames + CH - 1) / CH);
+    h->total_chunks = h->chunk_base[n];
+    const size_t tc = (size_t)h->total_chunks;
+    std::vector<int> lists(2 * tc);
+    for (int i = 0; i < n; i++)
+      for (long long c = h->chunk_base[i]; c < h->chunk_base[i + 1]; c++) { lists[c] = i; lists[tc + c] = (int)(c - h->chunk_base[i]); }
+    const size_t bytes = 2 * tc * sizeof(int) + ((size_t)n + 1) * sizeof(long long) + 16;
+    FA_CUDA(h->d_chunks.reserve(bytes));
+    // layout: base[n+1] (long long) | utt[tc] | idx[tc]
+    FA_CUDA(cudaMemcpyAsync(h->d_chunks.p, h->chunk_base.data(), ((size_t)n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
+    FA_CUDA(cudaMemcpyAsync((char*)h->d_chunks.p + ((size_t)n + 1) * sizeof(long long), lists.data(), 2 * tc * sizeof(int),
+                            cudaMemcpyHostToDevice, s));
+    FA_CUDA(cudaStreamSynchronize(s));   // `lists` dies at scope exit
+    FA_CUDA(h->d_state.reserve(2 * tc * (size_t)h->M * sizeof(float)));
+    FA_CUDA(h->d_fix.reserve(16));
+    if (h->want_spec) FA_CUDA(h->d_specdb.reserve(Fz * h->M * sizeof(float)));
   }
   h->prepared = true;
   return FA_OK;
@@ -748,6 +792,17 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
   sp.spec_db = h->d_spec.as<float>();
   sp.frames = h->d_frames.as<uint32_t>();
   sp.work_counter = h->d_counter.as<int>() + slot;
+  if (h->chunk_frames > 0) {
+    const size_t tc = (size_t)h->total_chunks;
+    const long long* base = h->d_chunks.as<long long>();
+    const int* utt_list = reinterpret_cast<const int*>(base + n + 1);
+    const long long c0 = h->chunk_base[sb.u0], c1 = h->chunk_base[sb.u1];
+    sp.chunk_frames = h->chunk_frames; sp.warm_frames = h->warm_frames;
+    sp.chunk_base = base; sp.chunk_utt = utt_list + c0; sp.chunk_idx = utt_list + tc + c0; sp.n_chunks = (int)(c1 - c0);
+    sp.st_entry = h->d_state.as<float>(); sp.st_exit = sp.st_entry + tc * h->M;
+    sp.spec_out = h->want_spec ? h->d_specdb.as<float>() : nullptr;
+    sp.fixups = h->d_fix.as<int>();
+  }
   if (!h->frames_mode) FA_CUDA(fa_launch_spectrum(sp, s, &h->launches));
   if (getenv("FA_DEBUG_SYNC")) FA_CUDA(cudaStreamSynchronize(s));
   if (ev) FA_CUDA(cudaEventRecord(ev[1], s));
@@ -843,6 +898,8 @@ static int run_device(fa_handle* h, bool with_h2d, bool with_sink) {
   h->launches = 0;
   if (c.output_level >= 3) FA_CUDA(cudaMemsetAsync(h->d_counts.p, 0, sizeof(int) * 6 * (size_t)n, s));
   if (c.output_level >= 3 && h->k3_mode == 1) FA_CUDA(cudaMemsetAsync(h->d_k3q.p, 0, 2 * kMaxSub * sizeof(int), s));
+  if (h->chunk_frames > 0) FA_CUDA(cudaMemsetAsync(h->d_fix.p, 0, sizeof(int), s));
+  h->fixups = -1;
   FA_CUDA(cudaEventRecord(h->ev[0], s));
   const std::vector<SubBatch> subs = plan(h, with_h2d || (with_sink && h->spec_sink));
   const bool sink = with_sink && h->spec_sink && h->want_spec && !h->frames_mode;
@@ -853,7 +910,7 @@ static int run_device(fa_handle* h, bool with_h2d, bool with_sink) {
     const int rc = launch_sub(h, all, 0, s, h->ev);
     if (rc != FA_OK) return rc;
     if (sink && h->total_frames)
-      FA_CUDA(cudaMemcpyAsync(h->spec_sink, h->d_spec.p, (size_t)h->total_frames * h->M * sizeof(float), cudaMemcpyDeviceToHost, s));
+      FA_CUDA(cudaMemcpyAsync(h->spec_sink, h->spec_rows(), (size_t)h->total_frames * h->M * sizeof(float), cudaMemcpyDeviceToHost, s));
   } else {
     { const int rc = ensure_sub_streams(h, (int)subs.size()); if (rc != FA_OK) return rc; }
     if (sink && !h->copy_stream) {
@@ -874,7 +931,7 @@ static int run_device(fa_handle* h, bool with_h2d, bool with_sink) {
         // the copy stream: FIFO over sub-batches -- and over batches when several handles share one copy stream
         FA_CUDA(cudaStreamWaitEvent(h->copy_stream, h->spec_done[b], 0));
         if (h->trace) FA_CUDA(cudaEventRecord(h->tr_ev[b][2], h->copy_stream));
-        FA_CUDA(cudaMemcpyAsync(h->spec_sink + (size_t)subs[b].r0 * h->M, h->d_spec.as<float>() + (size_t)subs[b].r0 * h->M,
+        FA_CUDA(cudaMemcpyAsync(h->spec_sink + (size_t)subs[b].r0 * h->M, h->spec_rows() + (size_t)subs[b].r0 * h->M,
                                 (size_t)(subs[b].r1 - subs[b].r0) * h->M * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
         FA_CUDA(cudaEventRecord(h->copy_done[b], h->copy_stream));
         if (h->trace) FA_CUDA(cudaEventRecord(h->tr_ev[b][3], h->copy_stream));
@@ -1027,6 +1084,20 @@ int fa_stage_times(fa_handle* h, float ms[5]) {
 }
 
 int fa_launch_count(fa_handle* h) { return h ? h->launches : FA_ERR_INVALID_ARG; }
+
+int fa_stream_fixups(fa_handle* h) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  if (!h->ran) return fail(h, FA_ERR_NOT_RUN, "no run yet");
+  if (h->chunk_frames <= 0) return 0;
+  if (h->fixups < 0) {
+    cudaSetDevice(h->device);
+    int v = 0;
+    FA_CUDA(cudaMemcpyAsync(&v, h->d_fix.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    FA_CUDA(cudaStreamSynchronize(h->stream));
+    h->fixups = v;
+  }
+  return h->fixups;
+}
 int fa_num_utterances(const fa_handle* h) { return h ? (int)h->utts.size() : FA_ERR_INVALID_ARG; }
 
 static int need_results(fa_handle* h) {
@@ -1102,7 +1173,7 @@ int fa_copy_spectrum(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows) 
   if (!h) return FA_ERR_INVALID_ARG;
   if (!h->want_spec) return fail(h, FA_ERR_INVALID_ARG, "spectrum not materialised (set want_spectrum or output_level <= 2)");
   if (h->frames_mode) return fail(h, FA_ERR_INVALID_ARG, "spectrum not materialised (the batch was submitted as frames)");
-  return copy_rows_device(h, utt_id, h->d_spec.p, (size_t)h->M * sizeof(float), dst, cap_rows);
+  return copy_rows_device(h, utt_id, h->spec_rows(), (size_t)h->M * sizeof(float), dst, cap_rows);
 }
 
 int fa_copy_frames(fa_handle* h, int64_t utt_id, uint32_t* dst, size_t cap_rows) {

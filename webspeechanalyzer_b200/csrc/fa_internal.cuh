@@ -45,6 +45,19 @@ struct FaSpectrumParams {
   long long n_rows;              // frames of the sub-batch
   uint32_t* frames;              // [F_total][B] or nullptr
   int* work_counter;             // dynamic utterance queue
+  // K1b stream mode (long utterances): the smoothing recursion is run per CHUNK of `chunk_frames` frames, every chunk but
+  // the first from a SPECULATED entry state (a warm-up over the `warm_frames` frames before it, started from zero), and a
+  // verification pass compares each chunk's true exit state with the next chunk's speculated entry bit for bit,
+  // recomputing the (rare) chunks whose warm-up had not converged.  chunk_frames == 0: one pass per utterance.
+  int chunk_frames, warm_frames;
+  const int* chunk_utt;          // [n_chunks] work items of this launch: utterance ...
+  const int* chunk_idx;          // ... and chunk inside it
+  const long long* chunk_base;   // [n_utt + 1] first state slot of every utterance
+  int n_chunks;
+  float* st_entry;               // [total chunks][M]
+  float* st_exit;                // [total chunks][M]
+  float* spec_out;               // dB rows in stream mode (the magnitudes must survive until verified); nullptr: in place
+  int* fixups;                   // chunks recomputed by the verification pass
 };
 
 // one candidate peak of a frame (K2 -> K3), 32 bytes = one DRAM sector

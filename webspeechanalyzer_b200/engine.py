@@ -141,6 +141,11 @@ class Engine:
         return dict(zip(("spectrum", "peaks", "segment", "features", "total"), [float(x) for x in ms]))
 
     @property
+    def stream_fixups(self) -> int:
+        """Chunks the verification pass of the chunk-parallel smoothing had to recompute in the last run (stream mode)."""
+        return self._check(self._lib.fa_stream_fixups(self._h))
+
+    @property
     def launches(self) -> int:
         return self._lib.fa_launch_count(self._h)
 
