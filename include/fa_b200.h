@@ -203,10 +203,10 @@ FA_API int fa_download(fa_handle* h);
 FA_API int fa_stage_times(fa_handle* h, float ms[5]);
 /* Number of kernel launches issued by the last run. */
 FA_API int fa_launch_count(fa_handle* h);
-/* Stream mode (utterances of >= 1000 frames on average): the smoothing recursion runs chunk-parallel from speculated
- * entry states that a verification pass checks bit for bit; returns how many chunks the last run had to recompute
- * (0 in practice; > 0 only means extra work, never a different result). */
-FA_API int fa_stream_fixups(fa_handle* h);
+/* Stream mode (utterances of >= 1000 frames on average): the smoothing recursion (stage 0) and the segmentor's control
+ * scan (stage 1) run chunk-parallel from speculated entry states that a verification pass checks exactly; returns how many
+ * chunks of that stage the last run had to redo (> 0 only means extra work, never a different result). */
+FA_API int fa_stream_fixups(fa_handle* h, int stage);
 
 FA_API int fa_num_utterances(const fa_handle* h);
 FA_API int fa_result_counts(fa_handle* h, int64_t utt_id, fa_counts* out);

@@ -67,8 +67,9 @@ def lib() -> C.CDLL:
     L.fa_submit_frames.argtypes = [H, C.c_int64, C.c_void_p, C.c_size_t, C.c_int]
     L.fa_set_pipeline.argtypes = [H, C.c_int]
     L.fa_set_spectrum_sink.argtypes = [H, C.c_void_p, C.c_size_t]
-    for n in ("fa_run", "fa_sync", "fa_upload", "fa_run_resident", "fa_download", "fa_launch_count", "fa_stream_fixups", "fa_num_utterances"):
+    for n in ("fa_run", "fa_sync", "fa_upload", "fa_run_resident", "fa_download", "fa_launch_count", "fa_num_utterances"):
         getattr(L, n).argtypes = [H]
+    L.fa_stream_fixups.argtypes = [H, C.c_int]
     L.fa_stage_times.argtypes = [H, C.POINTER(C.c_float)]
     L.fa_result_counts.argtypes = [H, C.c_int64, C.POINTER(FaCounts)]
     L.fa_total_counts.argtypes = [H, C.POINTER(FaCounts)]

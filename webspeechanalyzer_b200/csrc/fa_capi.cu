@@ -129,7 +129,12 @@ struct fa_handle {
   int chunk_frames = 0, warm_frames = 0;
   long long total_chunks = 0;
   std::vector<long long> chunk_base;   // host copy of base[]
-  int fixups = -1;                      // chunks recomputed in the last run (fetched lazily)
+  int fixups[2] = {-1, -1};             // chunks recomputed in the last run by K1b / K3a (fetched lazily)
+  // K3a stream mode: chunk work list, speculated entry / exit control states, T / k record of the gate's tests
+  DevBuf d_cchunks, d_cstate, d_frT, d_frk, d_frthr;
+  int ctl_chunk = 0, ctl_warm = 0;
+  long long total_cchunks = 0;
+  std::vector<long long> cchunk_base;
   float* spec_rows() const { return (chunk_frames > 0 && want_spec) ? d_specdb.as<float>() : d_spec.as<float>(); }
   DevBuf d_frctl, d_frv, d_epochs, d_work, d_k3q;   // K3 mode 1: per-frame control record, epoch table, work list, queue counters
   int k3_cfg = -1;       // FA_K3_MODE: 0 = serial one-warp-per-utterance kernel, 1 = control scan + epoch-parallel tracking,
@@ -322,7 +327,7 @@ int fa_destroy(fa_handle* h) {
                     &h->d_win, &h->d_tw, &h->d_tws, &h->d_ws, &h->d_bmi, &h->d_bmw, &h->d_emph, &h->d_spill, &h->d_trkbase, &h->d_trk_i,
                     &h->d_trk_d, &h->d_trk_slot, &h->d_pt_i, &h->d_pt_e, &h->d_rows, &h->d_rowlist, &h->d_segs, &h->d_syls,
                     &h->d_formants, &h->d_energy, &h->d_features, &h->d_counts, &h->d_off, &h->g_segs, &h->g_syls,
-                    &h->g_formants, &h->g_energy, &h->g_features, &h->d_chunks, &h->d_state, &h->d_specdb, &h->d_fix, &h->d_frctl, &h->d_frv, &h->d_epochs, &h->d_work, &h->d_k3q})
+                    &h->g_formants, &h->g_energy, &h->g_features, &h->d_chunks, &h->d_state, &h->d_specdb, &h->d_fix, &h->d_cchunks, &h->d_cstate, &h->d_frT, &h->d_frk, &h->d_frthr, &h->d_frctl, &h->d_frv, &h->d_epochs, &h->d_work, &h->d_k3q})
     b->release();
   for (HostBuf* b : {&h->h_pcm, &h->h_frames, &h->h_meta, &h->h_counts, &h->h_off, &h->h_segs, &h->h_syls, &h->h_formants, &h->h_energy,
                      &h->h_features})
@@ -569,6 +574,17 @@ static int prepare(fa_handle* h) {
     }
     h->chunk_frames = ch; h->warm_frames = ch ? warm : 0;
   }
+  // K3a stream mode: chunks of 4096 frames scanned from a speculated state (warm-up 1024 frames: a few segments, so that both
+  // the gate -- renewed by every frame louder than y -- and the segment state -- renewed by every finalisation -- have been
+  // through a renewal); FA_K3_CHUNK=0 disables, FA_K3_WARM overrides (tests force a useless warm-up)
+  {
+    int ch = (h->k3_mode == 1 && F / std::max(n, 1) >= 1000) ? 4096 : 0;
+    if (const char* ev = getenv("FA_K3_CHUNK")) ch = h->k3_mode == 1 ? atoi(ev) : 0;
+    int warm = 1024;
+    if (const char* ev = getenv("FA_K3_WARM")) warm = atoi(ev);
+    h->ctl_chunk = ch > 0 ? std::max(16, ch) : 0;
+    h->ctl_warm = std::max(0, warm);
+  }
   // device layout of the PCM: [staging | caller buffers ...], each region 16-byte aligned
   long long dev = 0;
   h->regions[0].n = h->staged;
@@ -656,6 +672,26 @@ static int prepare(fa_handle* h) {
     if (h->cfg.output_level == 5 || h->cfg.output_level == 13)
       FA_CUDA(h->g_features.reserve((Fz + nz) * FA_N_FEATURES * sizeof(double)));
   }
+  if (h->ctl_chunk > 0 && h->cfg.output_level >= 3) {
+    const int CH = h->ctl_chunk;
+    h->cchunk_base.assign((size_t)n + 1, 0);
+    for (int i = 0; i < n; i++) h->cchunk_base[i + 1] = h->cchunk_base[i] + std::max(1, (h->utts[i].frames + CH - 1) / CH);
+    h->total_cchunks = h->cchunk_base[n];
+    const size_t tc = (size_t)h->total_cchunks;
+    std::vector<int> lists(2 * tc);
+    for (int i = 0; i < n; i++)
+      for (long long c = h->cchunk_base[i]; c < h->cchunk_base[i + 1]; c++) { lists[c] = i; lists[tc + c] = (int)(c - h->cchunk_base[i]); }
+    FA_CUDA(h->d_cchunks.reserve(2 * tc * sizeof(int) + ((size_t)n + 1) * sizeof(long long) + 16));
+    FA_CUDA(cudaMemcpyAsync(h->d_cchunks.p, h->cchunk_base.data(), ((size_t)n + 1) * sizeof(long long), cudaMemcpyHostToDevice, s));
+    FA_CUDA(cudaMemcpyAsync((char*)h->d_cchunks.p + ((size_t)n + 1) * sizeof(long long), lists.data(), 2 * tc * sizeof(int),
+                            cudaMemcpyHostToDevice, s));
+    FA_CUDA(cudaStreamSynchronize(s));
+    FA_CUDA(h->d_cstate.reserve(2 * tc * sizeof(FaCtlState)));
+    FA_CUDA(h->d_frT.reserve(Fz * sizeof(double)));
+    FA_CUDA(h->d_frk.reserve(Fz * sizeof(int)));
+    FA_CUDA(h->d_frthr.reserve(Fz * sizeof(double)));
+  }
+  FA_CUDA(h->d_fix.reserve(16));
   if (h->chunk_frames > 0) {
     const int CH = h->chunk_frames;
     h->chunk_base.assign((size_t)n + 1, 0);
@@ -673,7 +709,6 @@ static int prepare(fa_handle* h) {
                             cudaMemcpyHostToDevice, s));
     FA_CUDA(cudaStreamSynchronize(s));   // `lists` dies at scope exit
     FA_CUDA(h->d_state.reserve(2 * tc * (size_t)h->M * sizeof(float)));
-    FA_CUDA(h->d_fix.reserve(16));
     if (h->want_spec) FA_CUDA(h->d_specdb.reserve(Fz * h->M * sizeof(float)));
   }
   h->prepared = true;
@@ -853,6 +888,17 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
       g.work = h->d_work.as<int2>() + (sb.r0 + sb.u0);      // the sub-batch's slice (capacity: its frames + utterances)
       g.work_count = h->d_k3q.as<int>() + 2 * slot;
       g.n_workers = h->k3_workers;
+      if (h->ctl_chunk > 0) {
+        const size_t tc = (size_t)h->total_cchunks;
+        const long long* base = h->d_cchunks.as<long long>();
+        const int* lst = reinterpret_cast<const int*>(base + n + 1);
+        const long long c0 = h->cchunk_base[sb.u0], c1 = h->cchunk_base[sb.u1];
+        g.ctl_chunk = h->ctl_chunk; g.ctl_warm = h->ctl_warm;
+        g.cchunk_base = base; g.cchunk_utt = lst + c0; g.cchunk_idx = lst + tc + c0; g.n_cchunks = (int)(c1 - c0);
+        g.ctl_entry = h->d_cstate.as<FaCtlState>(); g.ctl_exit = g.ctl_entry + tc;
+        g.fr_T = h->d_frT.as<double>(); g.fr_k = h->d_frk.as<int>(); g.fr_thr = h->d_frthr.as<double>();
+        g.ctl_fixups = h->d_fix.as<int>() + 1;
+      }
     }
     g.segs = h->d_segs.as<fa_segment>(); g.syls = h->d_syls.as<fa_syllable>();
     g.formants = h->d_formants.as<float>(); g.energy = h->d_energy.as<float>();
@@ -867,6 +913,7 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
       fp.utt_begin = sb.u0; fp.utt_count = sb.u1 - sb.u0;
       fp.segs = g.segs; fp.n_segs = g.n_segs; fp.syls = g.syls; fp.n_syls = g.n_syls; fp.formants = g.formants;
       fp.features = h->d_features.as<double>(); fp.n_feat = cnt + 4 * n;
+      fp.epochs = h->k3_mode == 1 ? h->d_epochs.as<FaEpoch>() : nullptr;
       // rows of one utterance are spread over `row_slices` CTAs (a one-hour stream has ~2000 rows in ONE utterance)
       fp.row_slices = (int)std::min<long long>(64, std::max<long long>(1, (sb.r1 - sb.r0) / std::max(1, sb.u1 - sb.u0) / 256));
       FA_CUDA(fa_launch_features(fp, s3, &h->launches));
@@ -875,6 +922,7 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
       FaUtteranceParams up;
       up.frame_off = meta + 2 * n; up.n_utt = n; up.utt_begin = sb.u0; up.utt_count = sb.u1 - sb.u0;
       up.segs = g.segs; up.n_segs = g.n_segs; up.syls = g.syls; up.formants = g.formants;
+      up.epochs = h->k3_mode == 1 ? h->d_epochs.as<FaEpoch>() : nullptr;
       up.row_base = meta + 4 * n + 2; up.rows = h->d_features.as<double>(); up.n_feat = cnt + 4 * n; up.overflow = g.overflow;
       FA_CUDA(fa_launch_utterance(up, s3, &h->launches));
     }
@@ -898,8 +946,8 @@ static int run_device(fa_handle* h, bool with_h2d, bool with_sink) {
   h->launches = 0;
   if (c.output_level >= 3) FA_CUDA(cudaMemsetAsync(h->d_counts.p, 0, sizeof(int) * 6 * (size_t)n, s));
   if (c.output_level >= 3 && h->k3_mode == 1) FA_CUDA(cudaMemsetAsync(h->d_k3q.p, 0, 2 * kMaxSub * sizeof(int), s));
-  if (h->chunk_frames > 0) FA_CUDA(cudaMemsetAsync(h->d_fix.p, 0, sizeof(int), s));
-  h->fixups = -1;
+  FA_CUDA(cudaMemsetAsync(h->d_fix.p, 0, 2 * sizeof(int), s));
+  h->fixups[0] = h->fixups[1] = -1;
   FA_CUDA(cudaEventRecord(h->ev[0], s));
   const std::vector<SubBatch> subs = plan(h, with_h2d || (with_sink && h->spec_sink));
   const bool sink = with_sink && h->spec_sink && h->want_spec && !h->frames_mode;
@@ -949,6 +997,8 @@ static int run_device(fa_handle* h, bool with_h2d, bool with_sink) {
     int* cnt = h->d_counts.as<int>();
     FaGatherArgs ga;
     ga.feat_width = h->feat_width();
+    ga.epochs = h->k3_mode == 1 ? h->d_epochs.as<FaEpoch>() : nullptr;
+    ga.row_slices = (int)std::min<long long>(64, std::max<long long>(1, h->total_frames / std::max(1, n) / 256));
     ga.feat_base = c.output_level == FA_LEVEL_UTTERANCE ? meta + 4 * n + 2 : nullptr;
     ga.frame_off = meta + 2 * n; ga.n_utt = n; ga.n_segs = cnt; ga.n_rows = cnt + 2 * n; ga.n_syls = cnt + 3 * n;
     ga.n_feat = cnt + 4 * n; ga.off = h->d_off.as<long long>();
@@ -1085,18 +1135,17 @@ int fa_stage_times(fa_handle* h, float ms[5]) {
 
 int fa_launch_count(fa_handle* h) { return h ? h->launches : FA_ERR_INVALID_ARG; }
 
-int fa_stream_fixups(fa_handle* h) {
-  if (!h) return FA_ERR_INVALID_ARG;
+int fa_stream_fixups(fa_handle* h, int stage) {
+  if (!h || stage < 0 || stage > 1) return FA_ERR_INVALID_ARG;
   if (!h->ran) return fail(h, FA_ERR_NOT_RUN, "no run yet");
-  if (h->chunk_frames <= 0) return 0;
-  if (h->fixups < 0) {
+  if (h->fixups[0] < 0) {
     cudaSetDevice(h->device);
-    int v = 0;
-    FA_CUDA(cudaMemcpyAsync(&v, h->d_fix.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    int v[2] = {0, 0};
+    FA_CUDA(cudaMemcpyAsync(v, h->d_fix.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     FA_CUDA(cudaStreamSynchronize(h->stream));
-    h->fixups = v;
+    h->fixups[0] = v[0]; h->fixups[1] = v[1];
   }
-  return h->fixups;
+  return h->fixups[stage];
 }
 int fa_num_utterances(const fa_handle* h) { return h ? (int)h->utts.size() : FA_ERR_INVALID_ARG; }
 

@@ -143,13 +143,13 @@ __global__ void __launch_bounds__(kFeatThreads) fa_features_kernel(const FaFeatu
       int s = 0;
       while (p.segs[sb + s].stored != sy.stored_seg) s++;  // stored indices increase in seg_ci order
       sg = &p.segs[sb + s];
-      F = p.formants + (size_t)(row0 + sg->row_offset + sy.start) * 9;
+      F = p.formants + (size_t)(row0 + (p.epochs ? p.epochs[sb + s].first : sg->row_offset) + sy.start) * 9;
       len = sy.len;
     } else {
       int s = 0, c = -1;
       for (;; s++) { if (p.segs[sb + s].stored >= 0 && ++c == row) break; }
       sg = &p.segs[sb + s];
-      F = p.formants + (size_t)(row0 + sg->row_offset) * 9;
+      F = p.formants + (size_t)(row0 + (p.epochs ? p.epochs[sb + s].first : sg->row_offset)) * 9;
       len = sg->len;
     }
     double* out = p.features + (size_t)(sb + row) * FA_N_FEATURES;
@@ -226,7 +226,22 @@ __global__ void __launch_bounds__(128) fa_gather_kernel(const FaGatherArgs g) {
     uint32_t* d = reinterpret_cast<uint32_t*>(g.d_segs + o);
     for (int i = tid; i < words; i += 128) d[i] = s[i];
   }
-  {
+  if (g.epochs) {   // stream mode: segment by segment from the epochs' frame ranges, segments dealt over the row slices
+    const long long o = off[N1 + u];
+    const int nseg = g.n_segs[u];
+    for (int sgi = blockIdx.y; sgi < nseg; sgi += gridDim.y) {
+      const fa_segment sg = g.segs[sb + sgi];
+      if (sg.stored < 0) continue;
+      const size_t src = (size_t)(row0 + g.epochs[sb + sgi].first), dst = (size_t)(o + sg.row_offset);
+      const float* s = g.formants + src * 9;
+      float* d = g.d_formants + dst * 9;
+      for (int i = tid; i < sg.len * 9; i += 128) d[i] = s[i];
+      const float* s2 = g.energy + src * 3;
+      float* d2 = g.d_energy + dst * 3;
+      for (int i = tid; i < sg.len * 3; i += 128) d2[i] = s2[i];
+    }
+    if (blockIdx.y != 0) return;
+  } else {
     const int n = g.n_rows[u];
     const long long o = off[N1 + u];
     const float* s = g.formants + (size_t)row0 * 9;
@@ -271,7 +286,7 @@ cudaError_t fa_launch_prefix(const FaGatherArgs& a, cudaStream_t s, int* launche
 
 cudaError_t fa_launch_gather(const FaGatherArgs& a, cudaStream_t s, int* launches) {
   if (a.n_utt <= 0) return cudaSuccess;
-  fa_gather_kernel<<<a.n_utt, 128, 0, s>>>(a);
+  fa_gather_kernel<<<dim3(a.n_utt, a.epochs && a.row_slices > 1 ? a.row_slices : 1), 128, 0, s>>>(a);
   if (launches) (*launches)++;
   return cudaGetLastError();
 }

@@ -89,6 +89,15 @@ struct __align__(16) FaEpoch {
   double y, v;                   // thresholds at finalisation
 };
 
+// the control state that crosses a chunk boundary of the control scan (K3a stream mode)
+struct __align__(8) FaCtlState {
+  int c_started, no_fm_segs, c_ci, w, k, epoch_first;
+  int n_epochs;                  // accepted finalisations inside the chunk
+  int fired;                     // the gate's T/k reset fired inside the chunk
+  int overflow, n_events;        // n_events: reset tests recorded for the chunk
+  double y, v, x, v0, T;
+};
+
 struct FaSegmentParams {
   const FaCand* cand;            // [F_total][maxp]
   const int* ncand;
@@ -117,6 +126,16 @@ struct FaSegmentParams {
   int2* work;                         // epoch work list of this sub-batch: (utterance, seg_ci index)
   int* work_count;                    // [2]: entries in the list, next entry to take
   int n_workers;                      // warps of the K3b grid (cs_spill has one slice per worker in mode 1)
+  // K3a chunked (long utterances): every chunk of `ctl_chunk` frames is scanned from a SPECULATED entry state (a warm-up over
+  // the `ctl_warm` frames before it, from the initial state); a verification pass walks the chain, accepts a chunk when its
+  // speculated entry equals the true exit of its predecessor (T, k up to a replay of the gate's tests) and rescans it otherwise
+  int ctl_chunk, ctl_warm;
+  const int* cchunk_utt; const int* cchunk_idx; const long long* cchunk_base; int n_cchunks;
+  FaCtlState* ctl_entry; FaCtlState* ctl_exit;   // [total chunks]
+  // the gate's reset tests of a chunk, in order, at [frame_off[u] + a + i]: T and k in front of the test (k bit 31: it fired)
+  // and the threshold factor 30 v
+  double* fr_T; int* fr_k; double* fr_thr;
+  int* ctl_fixups;
   // outputs (per utterance tables at base frame_off[u] + u, capacity F_u + 1)
   fa_segment* segs; int* n_segs; int* n_stored;
   float* formants;                    // [F_total][9]   rows of utterance u start at frame_off[u]
@@ -134,6 +153,8 @@ struct FaFeatureParams {
   const fa_syllable* syls; const int* n_syls;
   const float* formants;
   int row_slices;                     // CTAs per utterance (grid.y): rows are dealt round-robin over slices x warps
+  const FaEpoch* epochs;              // K3 stream mode: the rows of segment s sit at the epoch's first frame (not compacted);
+                                      // nullptr: at fa_segment.row_offset
   double* features;                   // [(F_total + n_utt)][53] per-utterance rows at base frame_off[u] + u
   int* n_feat;                        // [n_utt]
 };
@@ -146,6 +167,7 @@ struct FaUtteranceParams {
   const fa_segment* segs; const int* n_segs;
   const fa_syllable* syls;
   const float* formants;
+  const FaEpoch* epochs;              // see FaFeatureParams
   const long long* row_base;          // [n_utt + 1] first 264-row of every utterance in `rows` (capacity = difference)
   double* rows;
   int* n_feat;                        // [n_utt] rows written
@@ -155,6 +177,9 @@ struct FaUtteranceParams {
 struct FaGatherArgs {
   const long long* frame_off;
   int n_utt;
+  const FaEpoch* epochs;              // K3 stream mode: formant / energy rows are gathered segment by segment from the
+                                      // epochs' frame ranges, several CTAs per utterance (row_slices); nullptr: contiguous
+  int row_slices;
   int feat_width;                     // doubles per feature row: 53 (levels 5, 13) or 264 (level 11)
   const long long* feat_base;         // level 11: first row of every utterance in `features`; nullptr: frame_off[u] + u
   const int *n_segs, *n_rows, *n_syls, *n_feat;

@@ -138,8 +138,9 @@ __device__ __forceinline__ void seg_reset(ScanState& st, WarpShared& S, int star
 // instead of FP64 divisions (a correctly rounded q = a/b with |a/b - c| >= 1/b >> ulp(c) compares with c like a/b does):
 //   e > x/100  <=>  100 e > x        T/k < 30 v  <=>  T < 30 v k        v > v0/10  <=>  10 v > v0
 //   parseInt(v0/20) = floor(v0/20)   (v0 < 2^32: unsigned division by a constant)
-__device__ __forceinline__ bool gate_update(ScanState& st, double e) {
-  bool reset = false;
+// flags: bit 0 = the T/k test asked for L(0), bit 1 = the test was evaluated; Tb, kb = T and k in front of the test
+__device__ __forceinline__ int gate_update_rec(ScanState& st, double e, double& Tb, int& kb) {
+  int flags = 0;
   st.w++;
   if (e > st.y || (st.w > 40 && e > 2 * st.v)) {
     if (e >= st.y) { st.w = 0; st.x = st.y = e; }
@@ -152,14 +153,22 @@ __device__ __forceinline__ bool gate_update(ScanState& st, double e) {
     else if (t > 1) st.v = fa_js_parse_int(st.y / 10);
     else st.v = 1;
     st.v0 = st.v;
-    if (st.k > 0 && st.T < 30 * st.v * (double)st.k) { reset = true; st.k = 0; st.T = 0; }
+    Tb = st.T; kb = st.k;
+    flags = 2;
+    if (st.k > 0 && st.T < 30 * st.v * (double)st.k) { flags = 3; st.k = 0; st.T = 0; }
     st.T += st.y;
     st.k += 1;
   } else if (st.v > 10 && 10 * st.v > st.v0 && st.w > 20) {
     st.v -= (double)((unsigned)st.v0 / 20u);
     if (st.v < 10) st.v = 10;
   }
-  return reset;
+  return flags;
+}
+
+__device__ __forceinline__ bool gate_update(ScanState& st, double e) {
+  double Tb;
+  int kb;
+  return gate_update_rec(st, e, Tb, kb) & 1;
 }
 
 // C() @B28506
@@ -937,30 +946,60 @@ __global__ void __launch_bounds__(kBound) fa_segment_kernel(const FaSegmentParam
 //                          same accumulate_fm and finalises with the recorded scalars.  Segments of one utterance -- and the
 //                          541 segments of a one-hour stream -- are tracked in parallel; pauses and abandoned starts cost
 //                          nothing here.  Rows / syllables go to provisional places inside the epoch's own frame range.
-//   K3c fa_segfix_kernel   warp per utterance: stored indices, dense row / syllable offsets, rows moved down in place.
+//   K3c fa_segfix_kernel   warp per utterance: stored indices, dense row / syllable offsets (rows themselves stay put).
 // Same arithmetic on the same operands in the same order as the serial kernel => identical bits.
 // =====================================================================================================================
 constexpr int kCtlWarps = 4;
+constexpr unsigned kCtlVoiced = 0x80000000u, kCtlGate = 0x40000000u, kCtlFired = 0x20000000u, kCtlLabel = 0x1fffffffu;
 
-__global__ void __launch_bounds__(kCtlWarps * 32) fa_segctl_kernel(const FaSegmentParams p) {
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int ui = blockIdx.x * kCtlWarps + wib;
-  if (ui >= p.utt_count) return;
-  const int u = p.utt_begin + ui;
-  const long long row0 = p.frame_off[u], sb = row0 + u;
-  const int F = (int)(p.frame_off[u + 1] - row0);
-  int maxp = p.maxp;
-  asm volatile("" : "+r"(maxp));
-  ScanState st;
+__device__ __forceinline__ void ctl_init(const FaSegmentParams& p, ScanState& st) {
   st.current_frame = 0; st.no_fm_segs = 0; st.c_ci = 0; st.c_started = -1; st.w = 0; st.k = 0;
   st.y = p.y0; st.v = p.v0; st.x = p.y0; st.v0 = p.v0; st.T = 0; st.s_energy = 0; st.c_energy = 0;
   st.n_tr = 0; st.n_pts = 0; st.n_slots = 0; st.n_segs = 0; st.n_stored = 0; st.n_rows = 0; st.n_syls = 0;
   st.overflow = 0;
-  int epoch_first = 0;
+}
 
-  // The frame inputs (count, g, first 32 candidates) are fetched kGroup frames at a time, one group ahead: the scan's
-  // dependent chain per frame is a few hundred cycles, about the latency of ONE L2 / HBM round trip, so a prefetch
-  // distance of one frame would leave the loop memory-latency bound.
+__device__ __forceinline__ void ctl_save(const ScanState& st, const int epoch_first, const int fired, const int n_events,
+                                         FaCtlState& o) {
+  o.c_started = st.c_started; o.no_fm_segs = st.no_fm_segs; o.c_ci = st.c_ci; o.w = st.w; o.k = st.k; o.epoch_first = epoch_first;
+  o.n_epochs = st.n_segs; o.fired = fired; o.overflow = st.overflow; o.n_events = n_events;
+  o.y = st.y; o.v = st.v; o.x = st.x; o.v0 = st.v0; o.T = st.T;
+}
+
+__device__ __forceinline__ void ctl_load(const FaCtlState& o, ScanState& st, int& epoch_first) {
+  st.c_started = o.c_started; st.no_fm_segs = o.no_fm_segs; st.c_ci = o.c_ci; st.w = o.w; st.k = o.k; epoch_first = o.epoch_first;
+  st.y = o.y; st.v = o.v; st.x = o.x; st.v0 = o.v0; st.T = o.T;
+}
+
+// O()'s acceptance test at a finalisation; an accepted attempt is written to epochs[slot] (slot = seg_ci index, or a
+// provisional place while the chunk is speculative) and, when `queue`, becomes one unit of work for K3b
+__device__ __forceinline__ void ctl_attempt(const FaSegmentParams& p, ScanState& st, const int epoch_first, const int n_arg,
+                                            const int last, const int maxp, const long long slot_base, const int u,
+                                            const bool emit, const bool queue, const int lane) {
+  const int len = n_arg - st.no_fm_segs;
+  if (!(len > p.seg_min_frames && st.c_started >= 2)) return;
+  if (emit && lane == 0) {
+    FaEpoch e;
+    e.first = epoch_first; e.last = last; e.n_arg = n_arg; e.no_fm_segs = st.no_fm_segs;
+    // tracks <= points <= accepted peaks <= maxp per frame: the epoch's frame range of the track table always suffices
+    e.current_frame = st.current_frame; e.c_ci = st.c_ci; e.trk_off = epoch_first * maxp; e.trk_cap = (last - epoch_first + 1) * maxp;
+    e.y = st.y; e.v = st.v;
+    p.epochs[slot_base + st.n_segs] = e;
+    if (queue) {
+      const int w = atomicAdd(p.work_count, 1);
+      p.work[w] = make_int2(u, st.n_segs);
+    }
+  }
+  if (emit) st.n_segs++;
+}
+
+// frames [t_begin, t_end) of the control scan of utterance u.  outputs: write the per-frame control record (and the T / k
+// record of the gate's test when `record`); emit / queue: see ctl_attempt; fired: set when the gate's T/k reset fires.
+__device__ __forceinline__ void segctl_range(const FaSegmentParams& p, const int u, const long long row0, const int t_begin,
+                                             const int t_end, ScanState& st, int& epoch_first, int& fired, int& n_events,
+                                             const bool outputs, const bool record, const long long slot_base, const bool queue,
+                                             const int maxp, const int lane) {
+  // The frame inputs (count, g, first 32 candidates) are fetched kGroup frames at a time, one group ahead
   constexpr int kGroup = 4;
   uint32_t pkd_n[kGroup], amp_n[kGroup];
   int nc_n[kGroup];
@@ -970,7 +1009,7 @@ __global__ void __launch_bounds__(kCtlWarps * 32) fa_segctl_kernel(const FaSegme
     for (int k = 0; k < kGroup; k++) {
       const int t = t0 + k;
       pkd_n[k] = 0u; amp_n[k] = 0u; nc_n[k] = 0; g_n[k] = 0.0;
-      if (t < F) {
+      if (t < t_end) {
         const size_t row = (size_t)(row0 + t);
         nc_n[k] = __ldg(p.ncand + row);
         g_n[k] = __ldg(p.gsum + row);
@@ -981,24 +1020,8 @@ __global__ void __launch_bounds__(kCtlWarps * 32) fa_segctl_kernel(const FaSegme
       }
     }
   };
-  // O()'s acceptance test; an accepted attempt becomes seg_ci[n_segs] and one unit of work for K3b
-  auto attempt = [&](const int n_arg, const int last) {
-    const int len = n_arg - st.no_fm_segs;
-    if (!(len > p.seg_min_frames && st.c_started >= 2)) return;
-    if (lane == 0) {
-      FaEpoch e;
-      e.first = epoch_first; e.last = last; e.n_arg = n_arg; e.no_fm_segs = st.no_fm_segs;
-      // tracks <= points <= accepted peaks <= maxp per frame: the epoch's frame range of the track table always suffices
-      e.current_frame = st.current_frame; e.c_ci = st.c_ci; e.trk_off = epoch_first * maxp; e.trk_cap = (last - epoch_first + 1) * maxp;
-      e.y = st.y; e.v = st.v;
-      p.epochs[sb + st.n_segs] = e;
-      const int w = atomicAdd(p.work_count, 1);
-      p.work[w] = make_int2(u, st.n_segs);
-    }
-    st.n_segs++;
-  };
-  prefetch_group(0);
-  for (int t0 = 0; t0 < F && !st.overflow; t0 += kGroup) {
+  prefetch_group(t_begin);
+  for (int t0 = t_begin; t0 < t_end && !st.overflow; t0 += kGroup) {
    uint32_t pkd_c[kGroup], amp_c[kGroup];
    int nc_c[kGroup];
    double g_c[kGroup];
@@ -1008,8 +1031,8 @@ __global__ void __launch_bounds__(kCtlWarps * 32) fa_segctl_kernel(const FaSegme
 #pragma unroll
    for (int k = 0; k < kGroup; k++) {
     const int t = t0 + k;
-    if (t >= F || st.overflow) break;
-    st.current_frame++;
+    if (t >= t_end || st.overflow) break;
+    st.current_frame = t + 1;
     const uint32_t pkd0 = pkd_c[k], amp0 = amp_c[k];
     const int nc = min(nc_c[k], maxp);
     if (nc_c[k] > maxp) st.overflow = 1;
@@ -1049,6 +1072,8 @@ __global__ void __launch_bounds__(kCtlWarps * 32) fa_segctl_kernel(const FaSegme
     const unsigned long long gi = (unsigned long long)g;
     const bool weak = gi > dsum && 10ull * dsum < gi - dsum;
     bool voiced = false, finalised = false;
+    int gflags = 0, kb = 0;
+    double Tb = 0;
     auto clear = [&](const int started) {   // L(started): the tracks are cleared, a new epoch starts with this frame
       st.c_ci = 0; st.c_started = started; st.no_fm_segs = 0;
       epoch_first = t;
@@ -1064,26 +1089,168 @@ __global__ void __launch_bounds__(kCtlWarps * 32) fa_segctl_kernel(const FaSegme
       if (n == 0 || pbin < 7 || pbin >= p.max_voiced_bin || (n > 3 && weak)) {
         st.no_fm_segs++;
         if (st.c_started < 2) st.c_started--;
-        else if ((double)st.no_fm_segs >= p.seg_breaker) { attempt(st.c_ci + 1, t); finalised = true; }
-        else if (p.auto_gate) { if (gate_update(st, h)) clear(0); }
+        else if ((double)st.no_fm_segs >= p.seg_breaker) {
+          ctl_attempt(p, st, epoch_first, st.c_ci + 1, t, maxp, slot_base, u, outputs, queue, lane);
+          finalised = true;
+        } else if (p.auto_gate) { gflags = gate_update_rec(st, h, Tb, kb); if (gflags & 1) clear(0); }
       } else {
-        if (p.auto_gate) { if (gate_update(st, h)) clear(0); }
+        if (p.auto_gate) { gflags = gate_update_rec(st, h, Tb, kb); if (gflags & 1) clear(0); }
         voiced = true;
         if (st.c_started < 2) st.c_started++; else st.no_fm_segs = 0;
       }
     }
     st.c_ci++;
     if (finalised) { st.c_ci = 0; st.c_started = -1; st.no_fm_segs = 0; epoch_first = t + 1; }
-    if (lane == 0) {
-      p.fr_ctl[row0 + t] = voiced ? (0x80000000u | (unsigned)t_stale) : 0u;
+    if (gflags & 1) fired = 1;
+    if (outputs && lane == 0) {
+      p.fr_ctl[row0 + t] = (voiced ? (kCtlVoiced | ((unsigned)t_stale & kCtlLabel)) : 0u) | ((gflags & 2) ? kCtlGate : 0u) |
+                           ((gflags & 1) ? kCtlFired : 0u);
       p.fr_v[row0 + t] = st.v;
+      if (record && (gflags & 2)) {      // the chunk's next reset-test record
+        const long long ei = row0 + t_begin + n_events;
+        p.fr_T[ei] = Tb; p.fr_k[ei] = kb | ((gflags & 1) ? (int)0x80000000 : 0); p.fr_thr[ei] = 30 * st.v;
+      }
     }
+    if (record && (gflags & 2)) n_events++;
    }
   }
-  if (!st.overflow) attempt(st.c_ci, F - 1);   // segment_truncate @B30800
+}
+
+// utterance mode of the control scan: one warp, all frames
+__global__ void __launch_bounds__(kCtlWarps * 32) fa_segctl_kernel(const FaSegmentParams p) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int ui = blockIdx.x * kCtlWarps + wib;
+  if (ui >= p.utt_count) return;
+  const int u = p.utt_begin + ui;
+  const long long row0 = p.frame_off[u], sb = row0 + u;
+  const int F = (int)(p.frame_off[u + 1] - row0);
+  int maxp = p.maxp;
+  asm volatile("" : "+r"(maxp));
+  ScanState st;
+  ctl_init(p, st);
+  int epoch_first = 0, fired = 0;
+  int n_events = 0;
+  segctl_range(p, u, row0, 0, F, st, epoch_first, fired, n_events, true, false, sb, true, maxp, lane);
+  st.current_frame = F;
+  if (!st.overflow) ctl_attempt(p, st, epoch_first, st.c_ci, F - 1, maxp, sb, u, true, true, lane);   // segment_truncate @B30800
   if (lane == 0) {
     p.n_segs[u] = st.n_segs;
     p.overflow[u] = st.overflow;
+  }
+}
+
+// stream mode, pass 1: warp per chunk.  Chunk 0 starts from the initial state (exact); chunk j > 0 warms up over the
+// ctl_warm frames in front of it (no outputs), notes the state it arrives with (its SPECULATED entry) and scans its frames
+// with all outputs; accepted finalisations go to provisional slots at the chunk's own first frame.
+__global__ void __launch_bounds__(kCtlWarps * 32) fa_segctl_chunk_kernel(const FaSegmentParams p) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int wi = blockIdx.x * kCtlWarps + wib;
+  if (wi >= p.n_cchunks) return;
+  const int u = p.cchunk_utt[wi], j = p.cchunk_idx[wi];
+  const long long row0 = p.frame_off[u], sb = row0 + u;
+  const int F = (int)(p.frame_off[u + 1] - row0);
+  int maxp = p.maxp;
+  asm volatile("" : "+r"(maxp));
+  const int a = j * p.ctl_chunk, b = min(F, a + p.ctl_chunk);
+  const long long slot = p.cchunk_base[u] + j;
+  ScanState st;
+  ctl_init(p, st);
+  int epoch_first = 0, fired = 0;
+  if (j > 0) {
+    int none = 0;
+    segctl_range(p, u, row0, max(0, a - p.ctl_warm), a, st, epoch_first, fired, none, false, false, 0, false, maxp, lane);
+    st.n_segs = 0;
+    fired = 0;
+    if (lane == 0) ctl_save(st, epoch_first, 0, 0, p.ctl_entry[slot]);
+  }
+  int n_events = 0;
+  segctl_range(p, u, row0, a, b, st, epoch_first, fired, n_events, true, true, sb + a, false, maxp, lane);
+  if (lane == 0) ctl_save(st, epoch_first, fired, n_events, p.ctl_exit[slot]);
+}
+
+// stream mode, pass 2: warp per utterance walks the chain of chunks.
+__global__ void __launch_bounds__(kCtlWarps * 32) fa_segctl_verify_kernel(const FaSegmentParams p) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int ui = blockIdx.x * kCtlWarps + wib;
+  if (ui >= p.utt_count) return;
+  const int u = p.utt_begin + ui;
+  const long long row0 = p.frame_off[u], sb = row0 + u;
+  const int F = (int)(p.frame_off[u + 1] - row0);
+  int maxp = p.maxp;
+  asm volatile("" : "+r"(maxp));
+  const int nc = (int)(p.cchunk_base[u + 1] - p.cchunk_base[u]);
+  ScanState st;          // the TRUE state at the current chunk boundary
+  ctl_init(p, st);
+  int epoch_first = 0, n_segs = 0, overflow = 0;
+  for (int j = 0; j < nc && !overflow; j++) {
+    const int a = j * p.ctl_chunk, b = min(F, a + p.ctl_chunk);
+    const long long slot = p.cchunk_base[u] + j;
+    const FaCtlState X = p.ctl_exit[slot];
+    bool ok = true;
+    double dT = 0;
+    int dk = 0;
+    if (j > 0) {
+      const FaCtlState G = p.ctl_entry[slot];
+      ok = G.c_started == st.c_started && G.no_fm_segs == st.no_fm_segs && G.c_ci == st.c_ci && G.w == st.w &&
+           G.epoch_first == epoch_first && G.y == st.y && G.v == st.v && G.x == st.x && G.v0 == st.v0;
+      dT = st.T - G.T;
+      dk = st.k - G.k;
+      if (ok && (dT != 0 || dk != 0)) {
+        // T and k are running sums since the gate's last reset: the speculated ones differ from the true ones by a constant
+        // until the first reset inside the chunk.  Replay the reset test of every frame up to (and including) that one with
+        // the true sums; the chunk stands iff every outcome is what the speculative scan saw.
+        const long long e0 = row0 + a;
+        int first = 0x7fffffff;
+        for (int i = lane; i < X.n_events; i += 32)
+          if (p.fr_k[e0 + i] < 0) { first = i; break; }
+        first = __reduce_min_sync(FULL, first);
+        bool bad = false;
+        for (int i = lane; i < X.n_events && i <= first; i += 32) {
+          const int kr = p.fr_k[e0 + i];
+          const double Tt = p.fr_T[e0 + i] + dT;
+          const int kt = (kr & 0x7fffffff) + dk;
+          const bool fire = kt > 0 && Tt < p.fr_thr[e0 + i] * (double)kt;
+          bad |= fire != (kr < 0);
+        }
+        ok = !__any_sync(FULL, bad);
+      }
+    }
+    if (ok) {
+      // accept: move the chunk's finalisations from their provisional slots (at frame a) to their seg_ci indices and queue them
+      if (a != n_segs)
+        for (int i = 0; i < X.n_epochs; i++) {       // ascending, dst <= src: in place
+          FaEpoch e;
+          if (lane == 0) { e = p.epochs[sb + a + i]; p.epochs[sb + n_segs + i] = e; }
+        }
+      if (lane == 0)
+        for (int i = 0; i < X.n_epochs; i++) {
+          const int w = atomicAdd(p.work_count, 1);
+          p.work[w] = make_int2(u, n_segs + i);
+        }
+      n_segs += X.n_epochs;
+      ctl_load(X, st, epoch_first);
+      if (!X.fired) { st.T = X.T + dT; st.k = X.k + dk; }
+      overflow |= X.overflow;
+    } else {
+      // the warm-up had not reached the true state: rescan the chunk from it
+      if (lane == 0) atomicAdd(p.ctl_fixups, 1);
+      int fired = 0;
+      st.n_segs = n_segs;
+      st.overflow = 0;
+      int none = 0;
+      segctl_range(p, u, row0, a, b, st, epoch_first, fired, none, true, false, sb, true, maxp, lane);
+      n_segs = st.n_segs;
+      overflow |= st.overflow;
+    }
+    __syncwarp();
+  }
+  st.n_segs = n_segs;
+  st.current_frame = F;
+  st.overflow = overflow;
+  if (!overflow) ctl_attempt(p, st, epoch_first, st.c_ci, F - 1, maxp, sb, u, true, true, lane);   // segment_truncate @B30800
+  if (lane == 0) {
+    p.n_segs[u] = st.n_segs;
+    p.overflow[u] = overflow;
   }
 }
 
@@ -1183,7 +1350,7 @@ __global__ void __launch_bounds__(kBound) fa_segtrack_kernel(const FaSegmentPara
       }
       if (n > PCAP) { st.overflow = 1; break; }
       __syncwarp();
-      accumulate_fm(p, S, st, bs, n, (int)(ctl & 0x7fffffffu), g, vmin, lane);
+      accumulate_fm(p, S, st, bs, n, (int)(ctl & kCtlLabel), g, vmin, lane);
       __syncwarp();
       if (lane <= FA_MAX_BANDS / 32) S.pmask[lane] = 0u;
       __syncwarp();
@@ -1211,27 +1378,10 @@ __global__ void __launch_bounds__(kCtlWarps * 32) fa_segfix_kernel(const FaSegme
     for (int si = 0; si < nseg; si++) {
       fa_segment sg = p.segs[sb + si];
       if (sg.stored < 0) continue;       // dropped by the throw: seg_ci keeps it, nothing was stored
-      const int src = sg.row_offset, ssrc = sg.first_syllable;
-      if (src != rows) {                 // rows move down in place: dst < src, ascending chunks, reads before writes
-        float* Fm = p.formants + (size_t)row0 * 9;
-        for (int e0 = 0; e0 < sg.len * 9; e0 += 32) {
-          const int e = e0 + lane;
-          float x = 0.f;
-          if (e < sg.len * 9) x = Fm[(size_t)src * 9 + e];
-          __syncwarp();
-          if (e < sg.len * 9) Fm[(size_t)rows * 9 + e] = x;
-          __syncwarp();
-        }
-        float* Eg = p.energy + (size_t)row0 * 3;
-        for (int e0 = 0; e0 < sg.len * 3; e0 += 32) {
-          const int e = e0 + lane;
-          float x = 0.f;
-          if (e < sg.len * 3) x = Eg[(size_t)src * 3 + e];
-          __syncwarp();
-          if (e < sg.len * 3) Eg[(size_t)rows * 3 + e] = x;
-          __syncwarp();
-        }
-      }
+      // the formant / energy rows stay where K3b put them (the epoch's first frame): K4 / K6 / K5 find them through the
+      // epoch table, and the dense gather (K5) copies them segment by segment with many CTAs -- moving 136 k rows of a
+      // one-hour stream down in place with one warp took 23 ms
+      const int ssrc = sg.first_syllable;
       for (int j0 = 0; j0 < sg.n_syllables; j0 += 32) {
         const int j = j0 + lane;
         fa_syllable sy;
@@ -1260,7 +1410,13 @@ cudaError_t fa_launch_segment(const FaSegmentParams& p, cudaStream_t s, int* lau
   static int regs = -1;
   if (regs < 0) { const char* ev = getenv("FA_K3_REGS"); regs = ev ? atoi(ev) : 128; }
   if (p.mode == 1) {
-    fa_segctl_kernel<<<(p.utt_count + kCtlWarps - 1) / kCtlWarps, kCtlWarps * 32, 0, s>>>(p);
+    if (p.ctl_chunk > 0) {
+      if (p.n_cchunks > 0) fa_segctl_chunk_kernel<<<(p.n_cchunks + kCtlWarps - 1) / kCtlWarps, kCtlWarps * 32, 0, s>>>(p);
+      fa_segctl_verify_kernel<<<(p.utt_count + kCtlWarps - 1) / kCtlWarps, kCtlWarps * 32, 0, s>>>(p);
+      if (launches) (*launches)++;
+    } else {
+      fa_segctl_kernel<<<(p.utt_count + kCtlWarps - 1) / kCtlWarps, kCtlWarps * 32, 0, s>>>(p);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int grid = (p.n_workers + kw - 1) / kw;

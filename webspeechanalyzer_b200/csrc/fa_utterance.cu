@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kUttWarps * 32) fa_utterance_kernel(const FaUt
     int voiced = 0;
     for (int e = lane; e < sg.n_syllables; e += 32) {
       const fa_syllable sy = p.syls[sb + sg.first_syllable + e];
-      const float* F = p.formants + (size_t)(row0 + sg.row_offset + sy.start) * 9;
+      const float* F = p.formants + (size_t)(row0 + (p.epochs ? p.epochs[sb + s].first : sg.row_offset) + sy.start) * 9;
       double a = 0, en = 0, sp = 0, st = 0, c = 0, a1 = 0, en1 = 0, sp1 = 0, st1 = 0, c1 = 0;
       float prev0 = 0.f, prev3 = 0.f;
       for (int o = 0; o < sy.len; o++) {

@@ -143,7 +143,12 @@ class Engine:
     @property
     def stream_fixups(self) -> int:
         """Chunks the verification pass of the chunk-parallel smoothing had to recompute in the last run (stream mode)."""
-        return self._check(self._lib.fa_stream_fixups(self._h))
+        return self._check(self._lib.fa_stream_fixups(self._h, 0))
+
+    @property
+    def control_fixups(self) -> int:
+        """Chunks of the control scan that had to be rescanned from the true state in the last run (stream mode)."""
+        return self._check(self._lib.fa_stream_fixups(self._h, 1))
 
     @property
     def launches(self) -> int:
