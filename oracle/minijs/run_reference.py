@@ -153,3 +153,91 @@ class ReferenceModules:
 
 
 __all__ = ["ReferenceModules", "available", "module_sources", "JSThrow"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The reference's PUBLIC API module (inner module 1 @B2714: configure / LaunchAudioNodes / StopAudioNodes /
+# set_predicted_label_for_segment), executed with its audio-graph module (inner module 2, browser-only) replaced by a
+# recording stub: what configure() leaves in the settings object, which string a LaunchAudioNodes call rejects with, and
+# which calls it makes into module 2 in which order with which arguments.
+_API_ANCHOR = 'n.d(t,"configure"'
+
+
+class ReferenceAPI:
+    def __init__(self, bundle_path: str = BUNDLE):
+        with open(bundle_path, encoding="utf-8") as f:
+            src = f.read()
+        a = src.index(_API_ANCHOR)
+        start = src.rindex(_HEAD, 0, a)
+        end = matching_end(src, start + len("function(e,t,n)"))
+        self.source = src[start:end]
+        self.it = it = Interp()
+        self.calls = []
+        self.playing = False
+        self.fail = {}          # module-2 function name -> rejection value
+
+        def stub(name, ret_promise=True):
+            def f(this, args):
+                self.calls.append((name, [_to_py(x) for x in args]))
+                if not ret_promise:
+                    return UNDEF
+                p = it.eval_expression("new Promise(function(a,b){window.__r=a;window.__j=b})")
+                w = it.globals.vars['window']
+                if name in self.fail:
+                    it.call(it.get(w, '__j'), UNDEF, [self.fail[name]])
+                else:
+                    it.call(it.get(w, '__r'), UNDEF, [True])
+                return p
+            return Native(f, name)
+
+        mod2 = JSObject({n: stub(n) for n in ("reset_nodes", "reset_segmentor", "reset_plot", "offline_play_the_file",
+                                                "online_play_the_file", "online_play_the_sop", "online_play_the_mic")})
+        mod2.props["isNodePlaying"] = Native(lambda this, args: self.playing, "isNodePlaying")
+        for n in ("Garbage_Collect", "disconnect_nodes", "set_predicted_label_for_segment"):
+            mod2.props[n] = stub(n, ret_promise=False)
+        exports = JSObject()
+        module = JSObject({'exports': exports})
+
+        def req(this, args):
+            assert int(args[0]) == 2
+            return mod2
+
+        def n_r(this, a_):
+            return UNDEF
+
+        def n_d(this, a_):
+            if a_[0].getters is None:
+                a_[0].getters = {}
+            a_[0].getters[a_[1]] = a_[2]
+            return UNDEF
+
+        require = Native(req, 'require')
+        require.props = {'r': Native(n_r, 'r'), 'd': Native(n_d, 'd')}
+        fn = it.eval_expression('(' + self.source + ')')
+        it.call(fn, exports, [module, exports, require])
+        self.exports = exports
+
+    def _js(self, v):
+        if isinstance(v, dict):
+            return JSObject({k: self._js(x) for k, x in v.items()})
+        if isinstance(v, (list, tuple)):
+            return JSArray([self._js(x) for x in v])
+        if isinstance(v, bool) or v is None or isinstance(v, str):
+            return v
+        return float(v)
+
+    def settings(self) -> dict:
+        """The module-level settings object (`a` @B2972) as configure() left it."""
+        env = self.it.get(self.exports, 'configure').env
+        return _to_py(env.vars['a'])
+
+    def configure(self, cfg: dict) -> dict:
+        self.it.call(self.it.get(self.exports, 'configure'), UNDEF, [self._js(cfg)])
+        return self.settings()
+
+    def launch(self, *args):
+        """-> ('resolved', value) | ('rejected', value), plus self.calls = the calls made into the audio-graph module."""
+        self.calls.clear()
+        p = self.it.call(self.it.get(self.exports, 'LaunchAudioNodes'), UNDEF, [self._js(a) if not isinstance(a, Native) else a for a in args])
+        self.it.run_microtasks()
+        return ('resolved' if p.state == 1 else 'rejected' if p.state == 2 else 'pending', _to_py(p.value))
