@@ -394,7 +394,15 @@ def main():
         names = ["spectrum", "peaks", "segment", "features"]
         shares = {k: float(stage_ms[i] / max(stage_ms[4], 1e-9)) for i, k in enumerate(names)}
         top = max(names, key=lambda k: stage_ms[names.index(k)])
+        stage_kernels = {"spectrum": ["fa_fftmag_2048_kernel", "fa_smooth_bands_kernel"], "peaks": ["fa_peaks_kernel"],
+                         "segment": ["fa_segment_kernel"], "features": ["fa_features_kernel"]}
+
+        def stage_traffic(k):     # DRAM bytes per launch of the stage's kernels from the committed ncu --set full capture
+            vals = [ncu_traffic(name) for name in stage_kernels[k]]
+            return None if any(v is None for v in vals) else float(sum(vals))
+
         stages = {k: {"ms": float(stage_ms[i]), "share": shares[k], "algorithmic_bytes": int(alg[k]),
+                      "ncu_dram_bytes": stage_traffic(k),
                       "achieved_gbs": alg[k] / (stage_ms[i] * 1e-3) / 1e9 if stage_ms[i] > 0 else None,
                       "frac_of_hbm_peak": alg[k] / (stage_ms[i] * 1e-3) / 1e9 / peak if stage_ms[i] > 0 else None}
                   for i, k in enumerate(names)}
