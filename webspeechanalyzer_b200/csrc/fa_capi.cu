@@ -848,6 +848,7 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
     FaPeaksParams pp;
     pp.frames = h->d_frames.as<uint32_t>(); pp.B = h->B; pp.maxp = h->maxp; pp.n_frames = sb.r1 - sb.r0; pp.row_begin = sb.r0;
     pp.cand = h->d_cand.as<FaCand>(); pp.ncand = h->d_ncand.as<int>(); pp.gsum = h->d_gsum.as<double>();
+    { static int st = -1; if (st < 0) { const char* ev = getenv("FA_K2_STAGED"); st = ev ? atoi(ev) != 0 : 0; } pp.staged = st; }   // measured slower: knob only
     FA_CUDA(fa_launch_peaks(pp, s, &h->launches));
     if (getenv("FA_DEBUG_SYNC")) FA_CUDA(cudaStreamSynchronize(s));
   }
