@@ -8,7 +8,7 @@ spectrum + formants output modes, producing the dB spectrum, the formant rows an
 batch (sharded by utterance, no data-path collective) => weak scaling.
 
   value     audio-seconds per second, inputs resident in HBM, CUDA events on the launching stream, max over ranks;
-            --depth batches in flight (one handle + stream per slot), every step one full pass over one batch
+            --depth batches in flight (default 4: one handle + stream per slot), every step one full pass over one batch
   e2e       the same metric through the C-ABI with HOST buffers: fa_submit_pcm_batch (pinned caller PCM, zero copy),
             H2D, kernels, D2H of every result table and of the dB spectrum inside the timed region; --depth batches in
             flight, all batches drained before the clock stops
@@ -164,9 +164,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--serial", action="store_true", help="one sub-batch (profiling: full-batch kernel launches)")
-    ap.add_argument("--pipeline", type=int, default=2, help="sub-batches for the resident timed region (0 = automatic)")
+    ap.add_argument("--pipeline", type=int, default=1, help="sub-batches for the resident timed region (0 = automatic)")
     ap.add_argument("--e2e-pipeline", type=int, default=0, help="sub-batches of an e2e step (0 = automatic)")
-    ap.add_argument("--depth", type=int, default=2,
+    ap.add_argument("--depth", type=int, default=4,
                     help="batches in flight: one handle + stream per batch slot, steps alternate between them so that batch "
                          "i+1's spectrum kernels overlap batch i's (latency-bound) segment scan and PCIe copies")
     args = ap.parse_args()
@@ -258,6 +258,7 @@ def main():
 
     # ---- end to end through the C-ABI with host buffers ----
     e2e = None
+    edepth = min(depth, 2)      # host-buffer steps: two batches in flight keep the PCIe link busy; more only pins more memory
     if not args.no_e2e:
         M = cfg.fft_size // 2
         # the caller's buffers: page-locked host memory for the PCM batches (inputs) and for the dB spectra (outputs);
@@ -267,7 +268,7 @@ def main():
         offs = np.zeros(n_utt + 1, np.int64)
         offs[1:] = np.cumsum([p.size for p in pcms])
         spec_hosts, pcm_hosts = [], []
-        for j in range(depth):
+        for j in range(edepth):
             spec_hosts.append(torch.empty((frames_per_step, M), dtype=torch.float32, pin_memory=True).numpy())
             ph = torch.empty(int(offs[-1]), dtype=torch.float32, pin_memory=True).numpy()
             for i, p in enumerate(pcms):
@@ -294,8 +295,8 @@ def main():
         def e2e_steps(k_steps):
             inflight = []
             for k in range(k_steps):
-                j = k % depth
-                if len(inflight) == depth:
+                j = k % edepth
+                if len(inflight) == edepth:
                     collect(inflight.pop(0))
                 launch(j)
                 inflight.append(j)
@@ -306,7 +307,7 @@ def main():
         for e in engs:
             e.set_pipeline(1 if args.serial else args.e2e_pipeline)
             e.set_d2h_stream(copy_stream.cuda_stream)   # the batches' dB rows leave in submission order (FIFO on PCIe)
-        e2e_steps(2 * depth)
+        e2e_steps(2 * edepth)
         barrier()
         t0 = time.perf_counter()
         e2e_steps(args.steps)
@@ -318,7 +319,7 @@ def main():
         d2h = d2h_seen[-1]
         e2e = {"value": world * audio_per_step * args.steps / float(tt.item()), "unit": "audio-s/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": 1e3 * float(tt.item()) / args.steps, "batches_in_flight": depth,
+               "ms_per_step": 1e3 * float(tt.item()) / args.steps, "batches_in_flight": edepth,
                "path": "per batch: fa_reset + fa_submit_pcm_batch (pinned host PCM) + fa_set_spectrum_sink (pinned) + fa_run "
                        "(async) ... fa_sync + fa_copy_{segments,formants,energy,syllables,features}; one handle per batch slot"}
 
@@ -330,7 +331,7 @@ def main():
         from webspeechanalyzer_b200 import FaConfig
         cfg2 = FaConfig.default(output_level=5, want_spectrum=0)
         engs2, pcm16_hosts = [], []
-        for j in range(depth):
+        for j in range(edepth):
             e = Engine(cfg2, device=local)
             e.set_stream(streams[j].cuda_stream)
             e.set_pipeline(1 if args.serial else args.e2e_pipeline)
@@ -354,15 +355,15 @@ def main():
         def steps2(k_steps):
             inflight = []
             for k in range(k_steps):
-                j = k % depth
-                if len(inflight) == depth:
+                j = k % edepth
+                if len(inflight) == edepth:
                     collect2(inflight.pop(0))
                 launch2(j)
                 inflight.append(j)
             while inflight:
                 collect2(inflight.pop(0))
 
-        steps2(2 * depth)
+        steps2(2 * edepth)
         barrier()
         t0 = time.perf_counter()
         steps2(args.steps)
@@ -373,7 +374,7 @@ def main():
             dist.all_reduce(tt2, op=dist.ReduceOp.MAX)
         e2e_feat = {"value": world * audio_per_step * args.steps / float(tt2.item()), "unit": "audio-s/s",
                     "h2d_bytes_per_step": int(pcm16_hosts[0].nbytes), "d2h_bytes_per_step": int(seen2[-1]),
-                    "ms_per_step": 1e3 * float(tt2.item()) / args.steps, "batches_in_flight": depth,
+                    "ms_per_step": 1e3 * float(tt2.item()) / args.steps, "batches_in_flight": edepth,
                     "path": "Segment Features only (output_level 5, no spectrum output): fa_reset + fa_submit_pcm_i16_batch (pinned int16 "
                             "PCM, converted on the device) + fa_run ... fa_sync + fa_copy_{segments,formants,energy,syllables,features}"}
         for e in engs2:
