@@ -38,6 +38,9 @@ sys.path.insert(0, ROOT)
 # same queue and a 1 ms segment scan falsely serialises other streams' kernels (profiles/r1_sweep_overlap.txt).
 # Read by the CUDA driver at context creation, so it has to be set before torch / the library touch the device.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION in this image) off it
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 N_UTT, SECONDS, SR = 1000, 5, 16000
 WORKLOAD = ("C2: 1000 synthetic 5 s 16 kHz utterances per GPU, spectrum + formants output modes + 53-dim Segment "
