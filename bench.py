@@ -60,6 +60,30 @@ def make_workload(rank: int, n_utt: int):
         return list(ex.map(lambda u: synth_speech(n, SR, 20261017, rank * n_utt + u), range(n_utt)))
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Run this rank on the CPUs of its GPU's NUMA node, so that the page-locked PCM / spectrum buffers it allocates next
+    (first touch) are local to the GPU's PCIe root: the e2e path moves 1.1 GB per step per GPU over PCIe and host memory.
+    Returns a short description for the JSON line; silently does nothing where sysfs does not say."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(local)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"gpu": local, "pci": bus, "numa_node": node, "cpus": len(cpus)}
+    except Exception:   # noqa: BLE001  (affinity is an optimisation only)
+        return None
+
+
 def ncu_traffic(kernel: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
     (profiles/r1_ncu_kernels.json, written by profiles/ncu_kernels.py); None if there is no capture."""
@@ -187,6 +211,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -429,6 +454,7 @@ def main():
             "stages": stages,
             "e2e": e2e,
             "e2e_feature_modes": e2e_feat,
+            "host_affinity": numa,
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "results": {"segments": tot["segments"], "feature_rows": tot["feature_rows"], "formant_rows": tot["formant_rows"],
