@@ -52,7 +52,7 @@ typedef enum fa_status {
   FA_ERR_CAPACITY = -6,       /* destination too small, or an internal table overflowed */
   FA_ERR_OUT_OF_MEMORY = -7,
   FA_ERR_BUSY = -8,           /* "Error: Already playing" (@B4469): fa_run while a run is in flight */
-  FA_ERR_UNSUPPORTED = -9     /* e.g. output_level 11/12, fft size outside 256..16384 */
+  FA_ERR_UNSUPPORTED = -9     /* e.g. an unknown output_level, fft size outside 256..16384 */
 } fa_status;
 
 /* spec_type (formantanalyzer defaults @B2972; tool-tips /root/reference/index.html:249-282) */
@@ -205,7 +205,9 @@ FA_API int fa_stage_times(fa_handle* h, float ms[5]);
 FA_API int fa_launch_count(fa_handle* h);
 /* Stream mode (utterances of >= 1000 frames on average): the smoothing recursion (stage 0) and the segmentor's control
  * scan (stage 1) run chunk-parallel from speculated entry states that a verification pass checks exactly; returns how many
- * chunks of that stage the last run had to redo (> 0 only means extra work, never a different result). */
+ * chunks of that stage the last run had to redo (> 0 only means extra work, never a different result).
+ * stage 2: utterances (epochs in stream mode) that the fast segment-scan kernel (<= 64 live tracks, <= 32 accepted peaks per
+ * frame) handed back to the general kernel in the last run. */
 FA_API int fa_stream_fixups(fa_handle* h, int stage);
 
 FA_API int fa_num_utterances(const fa_handle* h);

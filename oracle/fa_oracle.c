@@ -270,6 +270,9 @@ typedef struct {
   fao_track* tr;
   int n_tr, cap_tr;
   double s_energy, c_energy;
+  /* diagnostics for the GPU capacity tests: most tracks that could still be matched after one accumulate_fm call (gap < 4,
+   * the live-track slots the CUDA kernels need) and most accepted peaks in one call */
+  int max_live, max_peaks;
 } fao_state;
 
 struct fao_result {
@@ -293,6 +296,7 @@ struct fao_result {
   /* level 11: one 264-dim row per callback = get_utterance_features(u, h) over the stores that exist at that time */
   dvec utt_rows;
   int n_utt_rows;
+  int max_live, max_peaks; /* see fao_state */
 };
 typedef struct fao_result fao_result;
 
@@ -410,6 +414,12 @@ static void accumulate_fm(fao_state* st, const uint32_t* e, const fao_peak* pk, 
     }
   }
   free(owner); free(best);
+  {
+    int live = 0;
+    for (int r = 0; r < st->n_tr; r++) if (n - st->tr[r].last_frame < 4) live++;
+    if (live > st->max_live) st->max_live = live;
+    if (u > st->max_peaks) st->max_peaks = u;
+  }
 }
 
 /* get_ranked_formants @B35670: indices of tracks, ascending mean, stable */
@@ -912,6 +922,7 @@ FAO_API fao_result* fao_analyze_frames(const fa_config* c, const uint32_t* frame
   }
   clear_fm(&st);
   free(st.tr);
+  R->max_live = st.max_live; R->max_peaks = st.max_peaks;
   return R;
 }
 
@@ -930,6 +941,7 @@ FAO_API void fao_counts(const fao_result* R, int* out /*[8]*/) {
   out[0] = R->F; out[1] = R->seg_start.n; out[2] = R->st_len.n; out[3] = R->n_rows; out[4] = R->syl_seg.n;
   out[5] = R->n_feature_rows; out[6] = R->cb_si.n; out[7] = R->B;
 }
+FAO_API void fao_track_stats(const fao_result* R, int* out /*[2]*/) { out[0] = R->max_live; out[1] = R->max_peaks; }
 FAO_API void fao_get_segments(const fao_result* R, fa_segment* dst) {
   for (int i = 0; i < R->seg_start.n; i++) {
     fa_segment* s = &dst[i];

@@ -31,6 +31,7 @@ _lib.fao_analyze_frames.restype = C.c_void_p
 _lib.fao_free.argtypes = [C.c_void_p]
 _lib.fao_counts.argtypes = [C.c_void_p, _i32p]
 _lib.fao_get_segments.argtypes = [C.c_void_p, C.POINTER(FaSegment)]
+_lib.fao_track_stats.argtypes = [C.c_void_p, _i32p]
 _lib.fao_get_formants.argtypes = [C.c_void_p, _f32p, _f32p]
 _lib.fao_get_syllables.argtypes = [C.c_void_p, C.POINTER(FaSyllable)]
 _lib.fao_get_features.argtypes = [C.c_void_p, _f64p]
@@ -101,6 +102,8 @@ class Analysis:
     callbacks: np.ndarray           # store indices in firing order
     trace: dict = field(default_factory=dict)
     utterance: np.ndarray = None    # [callbacks, 264] float64 (level 11)
+    max_live_tracks: int = 0        # most tracks still matchable after one accumulate_fm call (GPU slot demand)
+    max_peaks: int = 0              # most accepted peaks in one accumulate_fm call
 
     @property
     def seg_ci(self):
@@ -149,7 +152,9 @@ def analyze_frames(cfg: FaConfig, frames: np.ndarray, trace: bool = False) -> An
         utt = np.zeros((nu, 264), np.float64)
         if nu:
             _lib.fao_get_utterance_features(R, _p(utt, _f64p))
-        return Analysis(F, B, segs, Fm, Eg, syl, feat, cb, tr, utt)
+        ts = (C.c_int * 2)()
+        _lib.fao_track_stats(R, ts)
+        return Analysis(F, B, segs, Fm, Eg, syl, feat, cb, tr, utt, int(ts[0]), int(ts[1]))
     finally:
         _lib.fao_free(R)
 

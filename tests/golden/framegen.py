@@ -75,3 +75,37 @@ def dropped_segment_frames(B: int = 128) -> np.ndarray:
     v = voiced([12, 30, 50, 70, 85], [8000, 40000, 8000, 8000, 8000])
     z = np.zeros(B, np.uint32)
     return np.stack([v, z, v, v] + [z] * 10 + [v] * 12 + [z] * 10)
+
+
+def dense_peak_frames(seed: int, B: int, F: int, spacing: float) -> np.ndarray:
+    """Capacity stress: voiced runs of comb spectra -- a peak every `spacing` bins, all far above the gate, positions
+    re-drawn every frame (jitter of +-1 bin, whole comb shifted now and then) so that most peaks found no track and start a
+    new one.  spacing 6 keeps ~20 peaks per frame and drives the live tracks (alive for four frames) past the 64 slots of the
+    fast K3 kernel; spacing 3 reaches ~40 peaks per frame and more live tracks than any kernel holds (FA_ERR_CAPACITY)."""
+    rng = np.random.default_rng(seed)
+    bins = np.arange(B)
+    out = np.zeros((F, B))
+    t = 0
+    while t < F:
+        run = int(rng.integers(12, 40))
+        level = 10 ** rng.uniform(3.0, 5.0)
+        phase = rng.uniform(0, spacing)
+        dom = rng.uniform(10, 0.6 * B)
+        for _ in range(run):
+            if t >= F:
+                break
+            if rng.random() < 0.3:
+                phase = rng.uniform(0, spacing)
+            centres = np.arange(phase + 2, B - 2, spacing) + rng.integers(-1, 2, size=len(np.arange(phase + 2, B - 2, spacing)))
+            e = rng.uniform(0, 2, size=B)
+            for c in centres:
+                e += level * rng.uniform(0.3, 0.6) * np.exp(-0.5 * ((bins - c) / 0.6) ** 2)
+            e += 3 * level * np.exp(-0.5 * ((bins - dom) / 0.8) ** 2)
+            out[t] = e
+            t += 1
+        for _ in range(int(rng.integers(9, 14))):
+            if t >= F:
+                break
+            out[t] = rng.uniform(0, 1, size=B)
+            t += 1
+    return np.rint(out).astype(np.uint32)

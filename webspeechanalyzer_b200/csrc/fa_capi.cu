@@ -129,7 +129,7 @@ struct fa_handle {
   int chunk_frames = 0, warm_frames = 0;
   long long total_chunks = 0;
   std::vector<long long> chunk_base;   // host copy of base[]
-  int fixups[2] = {-1, -1};             // chunks recomputed in the last run by K1b / K3a (fetched lazily)
+  int fixups[3] = {-1, -1, -1};         // chunks recomputed in the last run by K1b / K3a, utterances redone by the general K3 (fetched lazily)
   // K3a stream mode: chunk work list, speculated entry / exit control states, T / k record of the gate's tests
   DevBuf d_cchunks, d_cstate, d_frT, d_frk, d_frthr;
   int ctl_chunk = 0, ctl_warm = 0;
@@ -141,6 +141,9 @@ struct fa_handle {
                          // unset = automatic (prepare): long utterances / streams take mode 1, short ones mode 0
   int k3_mode = 0;
   int k3_workers = 0;    // warps of the epoch-tracking grid
+  int k3_impl = 2;       // FA_K3_IMPL: 2 = accumulate_fm2 kernel + redo launch (default), 1 = the general kernel alone
+  int k3_warps = 0, k3_regs = 0, k3_finalize_smem = 1, k2_staged = 0;   // FA_K3_WARPS, FA_K3_REGS, FA_K3_FINALIZE_HBM, FA_K2_STAGED
+  bool debug_sync = false;  // FA_DEBUG_SYNC
   DevBuf g_segs, g_syls, g_formants, g_energy, g_features;
   int n_weights = 0;
   long long track_total = 0, urow_total = 0;
@@ -305,6 +308,13 @@ int fa_create(const fa_config* cfg, int device, fa_handle** out) {
   if (const char* ev = getenv("FA_K3_MODE")) h->k3_cfg = atoi(ev) != 0;
   h->k3_workers = prop.multiProcessorCount * 14;   // 7 CTAs x 2 warps per SM (shared memory bound)
   if (const char* ev = getenv("FA_K3_WORKERS")) { const int v = atoi(ev); if (v >= 32 && v <= 1 << 16) h->k3_workers = v; }
+  // every environment knob is read here, once per handle -- nothing on the launch path calls getenv
+  if (const char* ev = getenv("FA_K3_IMPL")) h->k3_impl = atoi(ev) == 1 ? 1 : 2;
+  if (const char* ev = getenv("FA_K3_WARPS")) { const int v = atoi(ev); if (v >= 1 && v <= 4) h->k3_warps = v; }
+  if (const char* ev = getenv("FA_K3_REGS")) h->k3_regs = atoi(ev);
+  if (getenv("FA_K3_FINALIZE_HBM")) h->k3_finalize_smem = 0;
+  if (const char* ev = getenv("FA_K2_STAGED")) h->k2_staged = atoi(ev) != 0;
+  if (getenv("FA_DEBUG_SYNC")) h->debug_sync = true;
 
   // Streams are created on first use (ensure_sub_streams): the device has at most 32 hardware work queues
   // (CUDA_DEVICE_MAX_CONNECTIONS, default 8) and streams beyond that alias onto the same queue, where a stream that waits
@@ -609,9 +619,9 @@ static int prepare(fa_handle* h) {
     m[n + i] = u.n;
     m[2 * n + i] = u.row0;
     m[3 * n + 1 + i] = tb;
-    // track table: mode 0 (serial) 16 per frame; mode 1 gives every epoch its own frame range of `maxp` entries per frame
-    // (tracks <= points <= accepted peaks <= maxp per frame), so no epoch can overflow its slice
-    tb += h->k3_mode == 1 ? (long long)u.frames * h->maxp + 64 : (long long)u.frames * 16 + 64;
+    // track table: tracks <= points <= accepted peaks <= maxp per frame, so `maxp` entries per frame can never overflow
+    // (mode 1 gives every epoch its own frame range of the table); the pages nobody touches cost nothing
+    tb += (long long)u.frames * h->maxp + 64;
     m[4 * n + 2 + i] = ub;
     ub += u.frames / std::max<long long>(seg_span, 1) + 2;
   }
@@ -839,7 +849,7 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
     sp.fixups = h->d_fix.as<int>();
   }
   if (!h->frames_mode) FA_CUDA(fa_launch_spectrum(sp, s, &h->launches));
-  if (getenv("FA_DEBUG_SYNC")) FA_CUDA(cudaStreamSynchronize(s));
+  if (h->debug_sync) FA_CUDA(cudaStreamSynchronize(s));
   if (ev) FA_CUDA(cudaEventRecord(ev[1], s));
   if (!ev) FA_CUDA(cudaEventRecord(h->spec_done[slot], s));  // the dB rows of this sub-batch are final
   if (!ev && h->trace) FA_CUDA(cudaEventRecord(h->tr_ev[slot][1], s));
@@ -848,9 +858,9 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
     FaPeaksParams pp;
     pp.frames = h->d_frames.as<uint32_t>(); pp.B = h->B; pp.maxp = h->maxp; pp.n_frames = sb.r1 - sb.r0; pp.row_begin = sb.r0;
     pp.cand = h->d_cand.as<FaCand>(); pp.ncand = h->d_ncand.as<int>(); pp.gsum = h->d_gsum.as<double>();
-    { static int st = -1; if (st < 0) { const char* ev = getenv("FA_K2_STAGED"); st = ev ? atoi(ev) != 0 : 0; } pp.staged = st; }   // measured slower: knob only
+    pp.staged = h->k2_staged;   // measured slower: knob only
     FA_CUDA(fa_launch_peaks(pp, s, &h->launches));
-    if (getenv("FA_DEBUG_SYNC")) FA_CUDA(cudaStreamSynchronize(s));
+    if (h->debug_sync) FA_CUDA(cudaStreamSynchronize(s));
   }
   if (ev) FA_CUDA(cudaEventRecord(ev[2], s));
   if (tr) FA_CUDA(cudaEventRecord(h->tr_k[slot][2], s));
@@ -882,7 +892,8 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
     g.pt_e = h->d_pt_e.as<double>();
     g.row_count = h->d_rows.as<int>(); g.row_off = g.row_count + R; g.row_list = h->d_rowlist.as<int>();
     g.cs_spill = h->d_spill.as<unsigned long long>();
-    g.finalize_in_smem = getenv("FA_K3_FINALIZE_HBM") ? 0 : 1;
+    g.finalize_in_smem = h->k3_finalize_smem;
+    g.impl = h->k3_impl; g.warps_per_cta = h->k3_warps; g.reg_cap = h->k3_regs; g.redo_count = h->d_fix.as<int>() + 2;
     g.mode = h->k3_mode;
     if (g.mode == 1) {
       g.fr_ctl = h->d_frctl.as<unsigned>(); g.fr_v = h->d_frv.as<double>(); g.epochs = h->d_epochs.as<FaEpoch>();
@@ -947,8 +958,8 @@ static int run_device(fa_handle* h, bool with_h2d, bool with_sink) {
   h->launches = 0;
   if (c.output_level >= 3) FA_CUDA(cudaMemsetAsync(h->d_counts.p, 0, sizeof(int) * 6 * (size_t)n, s));
   if (c.output_level >= 3 && h->k3_mode == 1) FA_CUDA(cudaMemsetAsync(h->d_k3q.p, 0, 2 * kMaxSub * sizeof(int), s));
-  FA_CUDA(cudaMemsetAsync(h->d_fix.p, 0, 2 * sizeof(int), s));
-  h->fixups[0] = h->fixups[1] = -1;
+  FA_CUDA(cudaMemsetAsync(h->d_fix.p, 0, 3 * sizeof(int), s));
+  h->fixups[0] = h->fixups[1] = h->fixups[2] = -1;
   FA_CUDA(cudaEventRecord(h->ev[0], s));
   const std::vector<SubBatch> subs = plan(h, with_h2d || (with_sink && h->spec_sink));
   const bool sink = with_sink && h->spec_sink && h->want_spec && !h->frames_mode;
@@ -1137,14 +1148,14 @@ int fa_stage_times(fa_handle* h, float ms[5]) {
 int fa_launch_count(fa_handle* h) { return h ? h->launches : FA_ERR_INVALID_ARG; }
 
 int fa_stream_fixups(fa_handle* h, int stage) {
-  if (!h || stage < 0 || stage > 1) return FA_ERR_INVALID_ARG;
+  if (!h || stage < 0 || stage > 2) return FA_ERR_INVALID_ARG;
   if (!h->ran) return fail(h, FA_ERR_NOT_RUN, "no run yet");
   if (h->fixups[0] < 0) {
     cudaSetDevice(h->device);
-    int v[2] = {0, 0};
-    FA_CUDA(cudaMemcpyAsync(v, h->d_fix.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    int v[3] = {0, 0, 0};
+    FA_CUDA(cudaMemcpyAsync(v, h->d_fix.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     FA_CUDA(cudaStreamSynchronize(h->stream));
-    h->fixups[0] = v[0]; h->fixups[1] = v[1];
+    h->fixups[0] = v[0]; h->fixups[1] = v[1]; h->fixups[2] = v[2];
   }
   return h->fixups[stage];
 }

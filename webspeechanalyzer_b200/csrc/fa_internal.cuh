@@ -119,6 +119,12 @@ struct FaSegmentParams {
   int* row_list;                      // [F_total * maxp]
   unsigned long long* cs_spill;       // [n_utt][6][128] candidate scores beyond the three kept in shared memory
   int finalize_in_smem;               // 1: segments that fit are finalised in shared memory (0 forces the HBM path: tests)
+  // impl 2 (default): tracking with peak-lane ownership (accumulate_fm2: <= 64 live tracks, <= 32 accepted peaks per frame);
+  // an utterance / epoch that needs more is flagged (overflow == 2) and redone by the general kernel (impl 1) in a second,
+  // normally empty launch with redo_only = 1
+  int impl, redo_only;
+  int* redo_count;                    // utterances / epochs handed back to the general kernel (fa_stream_fixups(h, 2))
+  int warps_per_cta, reg_cap;         // launch shape knobs (FA_K3_WARPS, FA_K3_REGS), read once per handle
   // mode 1: control scan (K3a, warp per utterance) + epoch-parallel tracking / finalisation (K3b, warp per epoch) + fix-up (K3c)
   int mode;
   unsigned* fr_ctl;                   // [F_total] bit 31: the frame reaches accumulate_fm; low bits: its (stale) label c_ci

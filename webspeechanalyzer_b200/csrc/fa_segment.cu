@@ -68,6 +68,8 @@ struct WarpShared {
   unsigned char newlist[PCAP];                // un-owned peaks above the gate, in peak order
   // ---- end of the scratch-able prefix ----
   uint32_t pmask[FA_MAX_BANDS / 32 + 1];      // bit b: an accepted peak has pk == b (all zero between frames)
+  uint32_t wmask[2][FA_MAX_BANDS];            // K3 v2: [set][bin] lanes whose track slot holds the peak at `bin` in its window
+                                              // (all zero between frames)
 };
 constexpr int kScratchBytes = (int)offsetof(WarpShared, pmask);
 
@@ -791,6 +793,7 @@ __global__ void __launch_bounds__(kBound) fa_segment_kernel(const FaSegmentParam
   const int ui = blockIdx.x * (int)(blockDim.x >> 5) + wib;
   if (ui >= p.utt_count) return;
   const int u = p.utt_begin + ui;
+  if (p.redo_only && p.overflow[u] != 2) return;   // second launch behind fa_segment2_kernel: only what it handed back
   WarpShared& S = sh[wib];
   Bases bs;
   bs.row0 = p.frame_off[u];
@@ -929,6 +932,363 @@ __global__ void __launch_bounds__(kBound) fa_segment_kernel(const FaSegmentParam
     p.n_rows[u] = st.n_rows;
     p.n_syls[u] = st.n_syls;
     p.overflow[u] = st.overflow;
+  }
+}
+
+
+// =====================================================================================================================
+// K3 v2: the same scan with accumulate_fm restructured for latency (ncu on v1: 40 % of the stall samples were fixed-latency
+// dependencies, 17 % shared-memory round trips, 16 % branch resolution -- one warp per utterance has nothing else to issue,
+// so the length of the dependent chain per frame IS the run time).  What changes:
+//   * ownership is decided in PEAK lanes: phase 1 is one ballot per accepted peak over the track lanes (slot = lane and
+//     lane + 32: both register sets in flight at once) and leaves, in the peak's lane, the 64-bit mask of the tracks whose
+//     window holds it; phase 2 lets every peak lane score its own claimants (usually one or two) and keep the arg-max with
+//     the reference's tie rule (earlier track wins) in registers -- no shared-memory atomics, no second pass for ties;
+//   * a track that owns several peaks is a __match_any group of peak lanes: the lowest lane (= first owned peak, the peaks
+//     sit in bin order) merges the others by shuffle and updates the track record in place;
+//   * new tracks take the i-th free slot straight from the ballots of free lanes (bit select, no list in shared memory);
+//   * the velocity quotient k/3 is a two-FMA Markstein step (exact for |k| < 4096: exhaustively checked), k/2 = k * 0.5.
+// Limits: 64 live-track slots and 32 accepted peaks per frame.  An utterance / epoch that needs more stops with
+// overflow = 2 and is redone by the general kernel above (ACAP 128, PCAP 136) in a second, normally empty launch.
+// Same operations on the same operands as accumulate_fm => identical bits (tests: 83 reference-JS vectors, both paths).
+// =====================================================================================================================
+constexpr int ACAP2 = 64;
+
+// position of the (i + 1)-th set bit of x (i < popc(x))
+__device__ __forceinline__ int select64(const unsigned long long x, int i) {
+  unsigned w = (unsigned)x;
+  int pos = 0;
+  const int c = __popc(w);
+  if (i >= c) { i -= c; pos = 32; w = (unsigned)(x >> 32); }
+  int t = __popc(w & 0xffffu);
+  if (i >= t) { i -= t; pos += 16; w >>= 16; }
+  t = __popc(w & 0xffu);
+  if (i >= t) { i -= t; pos += 8; w >>= 8; }
+  t = __popc(w & 0xfu);
+  if (i >= t) { i -= t; pos += 4; w >>= 4; }
+  t = __popc(w & 0x3u);
+  if (i >= t) { i -= t; pos += 2; w >>= 2; }
+  if (i >= (int)(w & 1u)) pos += 1;
+  return pos;
+}
+
+__device__ __forceinline__ unsigned long long shfl_u64(const unsigned long long v, const int src) {
+  const unsigned lo = __shfl_sync(FULL, (unsigned)v, src), hi = __shfl_sync(FULL, (unsigned)(v >> 32), src);
+  return (unsigned long long)lo | ((unsigned long long)hi << 32);
+}
+
+// accumulate_fm @B35952.  m: lanes that hold an accepted peak of this frame (ascending bin order); the peak's packed bounds,
+// amplitude and prefix sums are in that lane's registers.
+__device__ __forceinline__ void accumulate_fm2(const FaSegmentParams& p, WarpShared& S, ScanState& st, const Bases& bs,
+                                               const unsigned m, const uint32_t my_pkd, const uint32_t my_amp,
+                                               const unsigned long long my_pl, const unsigned long long my_ph,
+                                               const int n_label, const double g, const double vmin, const int lane) {
+  if (m == 0u) return;
+  st.s_energy += g;
+  const unsigned lt = (1u << lane) - 1u;
+  const bool useB = st.n_slots > 32;
+  // ---- phase 1a, peak lanes: bitmap of the accepted peaks' bins ----
+  const bool active = (m >> lane) & 1u;
+  const int my_pk = (int)((my_pkd >> 16) & 0xffu);
+  if (active) atomicOr(&S.pmask[my_pk >> 5], 1u << (my_pk & 31));
+  __syncwarp();
+  // ---- phase 0 + 1b, track lanes (slot = lane and lane + 32, both sets in flight): expire; the peaks inside the window
+  //      |lastBin - pk| < DIST[gap] (@B32325) are the set bits of the bitmap there; every one is claimed by OR-ing the lane's
+  //      bit into the peak's claimant mask wmask[set][bin] (one shared-memory atomic per claim, all claims in parallel) ----
+  int idA = S.t_id[lane], idB = -1;
+  {
+    int B = p.B;
+    asm volatile("" : "+r"(B));   // ordinary register (ptxas uniform-register hazard, see fa_peaks.cu)
+    auto window = [&](const int slot, int& id, int& wlo) -> unsigned {
+      if (id < 0) return 0u;
+      const int gap = n_label - S.t_lf[slot];
+      if (gap >= 4) { id = -1; S.t_id[slot] = -1; return 0u; }   // can never match again (the reference keeps it, untouched)
+      if (gap < 0) return 0u;
+      const int lb = S.t_bins[slot] & 255;
+      const int lim = (0x9643 >> (4 * gap)) & 15;
+      wlo = max(lb - lim + 1, 0);
+      const int whi = min(lb + lim - 1, B - 1);
+      const int word = wlo >> 5, sh = wlo & 31;
+      const unsigned long long two = (unsigned long long)S.pmask[word] | ((unsigned long long)S.pmask[word + 1] << 32);
+      return (unsigned)(two >> sh) & ((2u << (whi - wlo)) - 1u);
+    };
+    int wloA = 0, wloB = 0;
+    unsigned bitsA = window(lane, idA, wloA), bitsB = 0u;
+    if (useB) { idB = S.t_id[lane + 32]; bitsB = window(lane + 32, idB, wloB); }
+    while (bitsA | bitsB) {
+      if (bitsA) { const int b = __ffs(bitsA) - 1; bitsA &= bitsA - 1u; atomicOr(&S.wmask[0][wloA + b], 1u << lane); }
+      if (bitsB) { const int b = __ffs(bitsB) - 1; bitsB &= bitsB - 1u; atomicOr(&S.wmask[1][wloB + b], 1u << lane); }
+    }
+  }
+  __syncwarp();
+  unsigned WA = 0u, WB = 0u;
+  if (active) {
+    WA = S.wmask[0][my_pk]; S.wmask[0][my_pk] = 0u;
+    if (useB) { WB = S.wmask[1][my_pk]; S.wmask[1][my_pk] = 0u; }
+  }
+  if (lane <= FA_MAX_BANDS / 32) S.pmask[lane] = 0u;
+  // ---- phase 2, peak lanes: score the claimants; strict '>' in track order == max score, earliest creation index ----
+  unsigned long long best = 0ull;
+  int best_id = BIG, best_q = -1, best_np = 0, best_bins = 0;
+  while (__any_sync(FULL, (WA | WB) != 0u)) {
+    int q = -1;
+    if (WA) { q = __ffs(WA) - 1; WA &= WA - 1u; }
+    else if (WB) { q = 32 + __ffs(WB) - 1; WB &= WB - 1u; }
+    if (q >= 0) {
+      const int lf = S.t_lf[q], tb = S.t_bins[q], np = S.t_np[q], id = S.t_id[q];
+      const double amp_old = (double)S.t_amp[q], vel = S.t_vel[q];
+      const int lb = tb & 255;
+      const double sc = fm_score(n_label - lf, (double)abs(lb - my_pk), np, lb, my_pk, amp_old, (double)my_amp, vel);
+      if (sc > 1) {
+        const unsigned long long sb = (unsigned long long)__double_as_longlong(sc);
+        if (sb > best || (sb == best && id < best_id)) { best = sb; best_id = id; best_q = q; best_np = np; best_bins = tb; }
+      }
+    }
+  }
+  __syncwarp();   // every claimant record has been read; the owners are rewritten below
+  // ---- phase 3: every owning track absorbs its (merged) peaks -- the first owned peak's lane acts for the track ----
+  const bool owned = active && best_q >= 0;
+  const unsigned grp = __match_any_sync(FULL, owned ? best_q : -1 - lane);
+  const bool leader = owned && lane == __ffs(grp) - 1;
+  int lo_b = (int)(my_pkd & 0xffu), hi_b = (int)((my_pkd >> 8) & 0xffu), ob = my_pk;
+  uint32_t bamp = my_amp;
+  unsigned long long pl = my_pl, ph = my_ph;
+  {
+    unsigned rem = leader ? (grp & ~(1u << lane)) : 0u;
+    while (__any_sync(FULL, rem != 0u)) {
+      const int src = rem ? __ffs(rem) - 1 : lane;
+      const uint32_t pkd2 = __shfl_sync(FULL, my_pkd, src), amp2 = __shfl_sync(FULL, my_amp, src);
+      const unsigned long long pl2 = shfl_u64(my_pl, src), ph2 = shfl_u64(my_ph, src);
+      if (rem) {
+        rem &= rem - 1u;
+        pl = pl2 < pl ? pl2 : pl; ph = ph2 > ph ? ph2 : ph;
+        lo_b = min(lo_b, (int)(pkd2 & 0xffu)); hi_b = max(hi_b, (int)((pkd2 >> 8) & 0xffu));
+        if (amp2 > bamp) { bamp = amp2; ob = (int)((pkd2 >> 16) & 0xffu); }   // strict: the first of equal amplitudes stays
+      }
+    }
+  }
+  const bool upd = leader && (double)my_amp > vmin;   // the amplitude of the FIRST owned peak decides (and is stored)
+  const unsigned um = __ballot_sync(FULL, upd);
+  unsigned long long moved = 0ull;
+  if (upd) {
+    const int q = best_q;
+    const unsigned long long Ei = ph - pl;
+    const double E = (double)Ei;
+    moved = Ei;
+    const int h = best_np;
+    const int b1 = best_bins & 255, b2 = (best_bins >> 8) & 255, b3 = (best_bins >> 16) & 255;
+    if (h >= 3) {
+      // k / 3, correctly rounded: q0 = k * fl(1/3), r = k - 3 q0 (exact), q = q0 + r * fl(1/3)   (Markstein; |k| < 4096 checked)
+      const double k = (double)(ob - b1 + (b2 - b1) + (b3 - b2)), third = 1.0 / 3.0;
+      const double q0 = k * third;
+      S.t_vel[q] = fma(fma(-3.0, q0, k), third, q0);
+    } else if (h == 2) S.t_vel[q] = (double)(ob - b1 + (b2 - b1)) * 0.5;
+    else if (h == 1) S.t_vel[q] = (double)(ob - b1);
+    const double se = S.t_se[q] + E, seb = S.t_seb[q] + E * (double)ob;
+    S.t_lf[q] = n_label; S.t_bins[q] = ob | (b1 << 8) | (b2 << 16); S.t_amp[q] = my_amp; S.t_np[q] = h + 1;
+    S.t_se[q] = se; S.t_seb[q] = seb;
+    const long long pq = bs.pb + st.n_pts + __popc(um & lt);
+    p.pt_track[pq] = best_id; p.pt_ord[pq] = h; p.pt_frame[pq] = n_label;
+    p.pt_binspan[pq] = ob | ((hi_b - lo_b + 1) << 16); p.pt_e[pq] = E;
+    const long long ti = bs.tb + best_id;
+    p.trk_count[ti] = h + 1; p.trk_sum_e[ti] = se; p.trk_sum_eb[ti] = seb;
+  }
+  st.n_pts += __popc(um);
+  if (um) {
+    const double mv = (double)warp_sum_u64(moved);  // exact integers: one subtraction == the reference's sequence
+    st.s_energy -= mv;
+    st.c_energy += mv;
+  }
+  // ---- phase 4: un-owned peaks above the gate start new tracks, in peak order, in the free slots ----
+  const bool mk = active && best_q < 0 && (double)my_amp > vmin;
+  const unsigned nm = __ballot_sync(FULL, mk);
+  if (nm) {
+    const int nn = __popc(nm);
+    if (st.n_tr + nn > bs.tcap) { st.overflow = 1; return; }
+    const unsigned fa = __ballot_sync(FULL, idA < 0);
+    const unsigned fb = useB ? __ballot_sync(FULL, idB < 0) : FULL;
+    const unsigned long long fre = (unsigned long long)fa | ((unsigned long long)fb << 32);
+    if (__popcll(fre) < nn) { st.overflow = 2; return; }   // more than 64 live tracks: the general kernel redoes it
+    if (mk) {
+      const int i = __popc(nm & lt);
+      const int q = select64(fre, i);
+      const double E = (double)(my_ph - my_pl);
+      const int id = st.n_tr + i;
+      S.t_id[q] = id; S.t_lf[q] = n_label; S.t_bins[q] = my_pk; S.t_amp[q] = my_amp; S.t_vel[q] = 0; S.t_np[q] = 1;
+      S.t_se[q] = E; S.t_seb[q] = E * (double)my_pk;
+      const long long pq = bs.pb + st.n_pts + i;
+      p.pt_track[pq] = id; p.pt_ord[pq] = 0; p.pt_frame[pq] = n_label;
+      p.pt_binspan[pq] = my_pk | (((int)((my_pkd >> 8) & 0xffu) - (int)(my_pkd & 0xffu) + 1) << 16); p.pt_e[pq] = E;
+      const long long ti = bs.tb + id;
+      p.trk_count[ti] = 1; p.trk_sum_e[ti] = E; p.trk_sum_eb[ti] = E * (double)my_pk;
+    }
+    st.n_slots = max(st.n_slots, select64(fre, nn - 1) + 1);
+    st.n_tr += nn;
+    st.n_pts += nn;
+  }
+  __syncwarp();   // the records written by the peak lanes are read by the track lanes of the next call
+}
+
+// one frame's accepted peaks for accumulate_fm2: the candidates of K2 filtered by the gate v, one per lane.  Frames with at
+// most 32 candidates (all but noise frames) keep every accepted peak in its candidate's lane; longer candidate lists are
+// compacted through shared memory.  Returns false when more than 32 peaks were accepted (-> redo by the general kernel).
+struct PeakRegs {
+  unsigned m;
+  uint32_t pkd, amp;
+  unsigned long long pl, ph;
+};
+
+template <int kBound>
+__global__ void __launch_bounds__(kBound) fa_segment2_kernel(const FaSegmentParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WarpShared* sh = reinterpret_cast<WarpShared*>(smem_raw);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int ui = blockIdx.x * (int)(blockDim.x >> 5) + wib;
+  if (ui >= p.utt_count) return;
+  const int u = p.utt_begin + ui;
+  WarpShared& S = sh[wib];
+  Bases bs;
+  bs.row0 = p.frame_off[u];
+  bs.F = (int)(p.frame_off[u + 1] - bs.row0);
+  bs.tb = p.track_base[u];
+  bs.tcap = (int)(p.track_base[u + 1] - bs.tb);
+  int maxp = p.maxp;
+  asm volatile("" : "+r"(maxp));  // keep it in an ordinary register (ptxas uniform-register hazard, see fa_peaks.cu)
+  bs.pb = bs.row0 * maxp;
+  bs.sb = bs.row0 + u;
+  bs.rb = bs.sb;
+  bs.u = u;
+  bs.spill = u;
+  const unsigned lt = (1u << lane) - 1u;
+
+  ScanState st;
+  st.current_frame = 0; st.no_fm_segs = 0; st.c_ci = 0; st.c_started = -1; st.w = 0; st.k = 0;
+  st.y = p.y0; st.v = p.v0; st.x = p.y0; st.v0 = p.v0; st.T = 0; st.s_energy = 0; st.c_energy = 0;
+  st.n_tr = 0; st.n_pts = 0; st.n_slots = 0; st.n_segs = 0; st.n_stored = 0; st.n_rows = 0; st.n_syls = 0;
+  st.overflow = 0;
+  for (int r = lane; r < ACAP; r += 32) S.t_id[r] = -1;
+  if (lane <= FA_MAX_BANDS / 32) S.pmask[lane] = 0u;
+  for (int r = lane; r < 2 * FA_MAX_BANDS; r += 32) (&S.wmask[0][0])[r] = 0u;
+  __syncwarp();
+
+  // software prefetch of the next frame: count, g, and the first 32 candidates (one per lane)
+  uint32_t pkd_next = 0, amp_next = 0;
+  unsigned long long pl_next = 0, ph_next = 0;
+  int nc_next = 0;
+  double g_next = 0;
+  auto prefetch = [&](int t) {
+    const size_t row = (size_t)(bs.row0 + t);
+    nc_next = __ldg(p.ncand + row);
+    g_next = __ldg(p.gsum + row);
+    if (lane < maxp) {
+      const uint4* c4 = reinterpret_cast<const uint4*>(p.cand + row * maxp + lane);
+      const uint4 a = __ldg(c4), b = __ldg(c4 + 1);
+      pkd_next = a.x; amp_next = a.y; pl_next = a.z | ((unsigned long long)a.w << 32); ph_next = b.x | ((unsigned long long)b.y << 32);
+    }
+  };
+  if (bs.F > 0) prefetch(0);
+
+  for (int t = 0; t < bs.F && !st.overflow; t++) {
+    // ---- spectrum_push @B30392 ----
+    st.current_frame++;
+    PeakRegs pr;
+    pr.m = 0u; pr.pkd = pkd_next; pr.amp = amp_next; pr.pl = pl_next; pr.ph = ph_next;
+    const int nc = min(nc_next, maxp);
+    if (nc_next > maxp) st.overflow = 1;
+    const double g = g_next;
+    if (t + 1 < bs.F) prefetch(t + 1);
+
+    // ---- D() @B25717: filter the candidates of K2 by the gate v (value at frame start) ----
+    const double v = st.v;
+    const int t_stale = st.c_ci;
+    int n = 0, pbin = 0;
+    unsigned long long dsum = 0;
+    double h = 2 * v;
+    const bool one_chunk = nc <= 32;
+    auto filter = [&](const int c0, const uint32_t pkd, const uint32_t amp, const unsigned long long pl,
+                      const unsigned long long ph) {
+      const bool acc = c0 + lane < nc && (double)amp > v;
+      const unsigned mm = __ballot_sync(FULL, acc);
+      if (mm == 0u) return;
+      const int pk = (pkd >> 16) & 0xff;
+      if (one_chunk) pr.m = mm;
+      else if (acc) {
+        const int pos = n + __popc(mm & lt);
+        if (pos < 32) { S.pa[pos] = make_uint2(pkd, amp); S.plh[pos] = make_ulonglong2(pl, ph); }
+      }
+      n += __popc(mm);
+      const uint32_t a = acc ? amp : 0u;
+      dsum += (unsigned long long)__reduce_add_sync(FULL, a & 0xffffu) +
+              ((unsigned long long)__reduce_add_sync(FULL, a >> 16) << 16);
+      // h / p: first strictly greater wins; the last-bin peak never updates them
+      const bool hp = acc && !((pkd >> 24) & 1u);
+      const uint32_t mx = __reduce_max_sync(FULL, hp ? amp : 0u);
+      const unsigned who = __ballot_sync(FULL, hp && amp == mx);
+      if (who && (double)mx > h) {
+        h = (double)mx;
+        pbin = __shfl_sync(FULL, pk, __ffs(who) - 1);
+      }
+    };
+    filter(0, pr.pkd, pr.amp, pr.pl, pr.ph);
+    for (int c0 = 32; c0 < nc; c0 += 32) {  // more than 32 candidates in a frame: noise frames
+      uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+      if (c0 + lane < nc) {
+        const uint4* c4 = reinterpret_cast<const uint4*>(p.cand + (size_t)(bs.row0 + t) * maxp + c0 + lane);
+        a = __ldg(c4); b = __ldg(c4 + 1);
+      }
+      filter(c0, a.x, a.y, a.z | ((unsigned long long)a.w << 32), b.x | ((unsigned long long)b.y << 32));
+    }
+    if (n > 32) { st.overflow = 2; break; }   // more accepted peaks than lanes: the general kernel redoes the utterance
+    if (!one_chunk) {
+      __syncwarp();
+      pr.m = n >= 32 ? FULL : ((1u << n) - 1u);
+      if (lane < n) {
+        const uint2 a = S.pa[lane];
+        const ulonglong2 e2 = S.plh[lane];
+        pr.pkd = a.x; pr.amp = a.y; pr.pl = e2.x; pr.ph = e2.y;
+      }
+      __syncwarp();
+    }
+    const double d = (double)dsum;
+    // exact integer forms of the reference's quotient tests (see gate_update and fa_segctl_kernel)
+    const unsigned long long gi = (unsigned long long)g;
+    const bool weak = gi > dsum && 10ull * dsum < gi - dsum;       // d / (g - d) < 0.1
+
+    int fin = -2;
+    if (st.c_started < 0) {
+      bool strong;                                                  // h (n - 1) / (d - h) > 4
+      if (p.auto_gate) strong = d > h && h * (double)(n - 1) > 4 * (d - h);
+      else strong = (d > h ? h * (double)(n - 1) / (d - h) : 0) > 4;
+      if (n > 0 && pbin > 7 && pbin < p.max_voiced_bin && n > 4 && strong) { seg_reset(st, S, 0, lane); st.c_started = 0; }
+      else st.no_fm_segs++;
+    }
+    if (st.c_started >= 0) {
+      if (n == 0 || pbin < 7 || pbin >= p.max_voiced_bin || (n > 3 && weak)) {
+        st.no_fm_segs++;
+        if (st.c_started < 2) st.c_started--;
+        else if ((double)st.no_fm_segs >= p.seg_breaker) fin = finalize_copy(p, S, st, bs, st.c_ci + 1, lane);
+        else if (p.auto_gate) noise_gate(st, S, h, lane);
+      } else {
+        if (p.auto_gate) noise_gate(st, S, h, lane);
+        accumulate_fm2(p, S, st, bs, pr.m, pr.pkd, pr.amp, pr.pl, pr.ph, t_stale, g, st.v, lane);
+        if (st.c_started < 2) st.c_started++; else st.no_fm_segs = 0;
+      }
+    }
+    st.c_ci++;
+    if (fin != -2) seg_reset(st, S, -1, lane);  // the promise's micro-task runs before the next frame
+  }
+  // segment_truncate @B30800
+  if (!st.overflow) {
+    finalize_copy(p, S, st, bs, st.c_ci, lane);
+    seg_reset(st, S, 1, lane);
+  }
+  if (lane == 0) {
+    p.n_segs[u] = st.n_segs;
+    p.n_stored[u] = st.n_stored;
+    p.n_rows[u] = st.n_rows;
+    p.n_syls[u] = st.n_syls;
+    p.overflow[u] = st.overflow;
+    if (st.overflow == 2 && p.redo_count) atomicAdd(p.redo_count, 1);
   }
 }
 
@@ -1402,13 +1762,12 @@ __global__ void __launch_bounds__(kCtlWarps * 32) fa_segfix_kernel(const FaSegme
 
 }  // namespace
 
-cudaError_t fa_launch_segment(const FaSegmentParams& p, cudaStream_t s, int* launches) {
-  if (p.utt_count <= 0) return cudaSuccess;
-  int kw = kWarps;
-  if (const char* ev = getenv("FA_K3_WARPS")) { const int v = atoi(ev); if (v >= 1 && v <= 4) kw = v; }  // tuning knob
+cudaError_t fa_launch_segment(const FaSegmentParams& p_in, cudaStream_t s, int* launches) {
+  if (p_in.utt_count <= 0) return cudaSuccess;
+  FaSegmentParams p = p_in;
+  const int kw = p.warps_per_cta >= 1 && p.warps_per_cta <= 4 ? p.warps_per_cta : kWarps;
   const int bytes = (int)sizeof(WarpShared) * kw;
-  static int regs = -1;
-  if (regs < 0) { const char* ev = getenv("FA_K3_REGS"); regs = ev ? atoi(ev) : 128; }
+  const int regs = p.reg_cap > 0 ? p.reg_cap : 128;
   if (p.mode == 1) {
     if (p.ctl_chunk > 0) {
       if (p.n_cchunks > 0) fa_segctl_chunk_kernel<<<(p.n_cchunks + kCtlWarps - 1) / kCtlWarps, kCtlWarps * 32, 0, s>>>(p);
@@ -1439,8 +1798,17 @@ cudaError_t fa_launch_segment(const FaSegmentParams& p, cudaStream_t s, int* lau
     kernel<<<grid, kw * 32, bytes, s>>>(p);
     return cudaGetLastError();
   };
-  const cudaError_t e = regs <= 64 ? launch(fa_segment_kernel<1024>) : regs <= 96 ? launch(fa_segment_kernel<640>)
-                                                                                   : launch(fa_segment_kernel<128>);
+  cudaError_t e = cudaSuccess;
+  if (p.impl == 2) {
+    p.redo_only = 0;
+    e = regs <= 64 ? launch(fa_segment2_kernel<1024>) : regs <= 96 ? launch(fa_segment2_kernel<640>) : launch(fa_segment2_kernel<128>);
+    if (launches) (*launches)++;
+    if (e != cudaSuccess) return e;
+    p.redo_only = 1;   // whatever fa_segment2_kernel handed back (overflow == 2): normally nothing, every warp exits at once
+  } else {
+    p.redo_only = 0;
+  }
+  e = regs <= 64 ? launch(fa_segment_kernel<1024>) : regs <= 96 ? launch(fa_segment_kernel<640>) : launch(fa_segment_kernel<128>);
   if (launches) (*launches)++;
   return e;
 }

@@ -151,6 +151,12 @@ class Engine:
         return self._check(self._lib.fa_stream_fixups(self._h, 1))
 
     @property
+    def k3_redos(self) -> int:
+        """Utterances (epochs in stream mode) the fast segment-scan kernel handed back to the general one in the last run
+        (more than 64 live tracks or 32 accepted peaks in a frame); > 0 only means extra work, never a different result."""
+        return self._check(self._lib.fa_stream_fixups(self._h, 2))
+
+    @property
     def launches(self) -> int:
         return self._lib.fa_launch_count(self._h)
 
