@@ -125,6 +125,7 @@ struct FaSegmentParams {
   int impl, redo_only;
   int* redo_count;                    // utterances / epochs handed back to the general kernel (fa_stream_fixups(h, 2))
   int warps_per_cta, reg_cap;         // launch shape knobs (FA_K3_WARPS, FA_K3_REGS), read once per handle
+  int smem_per_warp;                  // bytes of shared memory per warp (set by fa_launch_segment)
   // mode 1: control scan (K3a, warp per utterance) + epoch-parallel tracking / finalisation (K3b, warp per epoch) + fix-up (K3c)
   int mode;
   unsigned* fr_ctl;                   // [F_total] bit 31: the frame reaches accumulate_fm; low bits: its (stale) label c_ci

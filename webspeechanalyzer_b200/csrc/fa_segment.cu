@@ -49,7 +49,13 @@ constexpr int BIG = 0x7fffffff;
 constexpr int CSM = 3;     // candidate scores per slot kept in shared memory; the rest spill to the point-pool tail
 
 struct WarpShared {
-  // ---- everything up to pmask is dead while a segment is finalised: finalize_fast reuses these bytes as scratch ----
+  // ---- live across a finalisation ----
+  uint32_t pmask[FA_MAX_BANDS / 32 + 1];      // bit b: an accepted peak has pk == b (all zero between frames)
+  uint32_t pad0[3];
+  uint32_t wmask[2][FA_MAX_BANDS];            // K3 v2: [set][bin] lanes whose track slot holds the peak at `bin` in its window
+                                              // (all zero between frames)
+  // ---- everything from here to the end of the warp's shared-memory slice (this struct + the extra bytes the launch adds
+  //      behind it) is dead while a segment is finalised: finalize_fast uses it as scratch ----
   unsigned long long cs[CSM][ACAP];           // [j][slot]: score of the slot's j-th retained candidate
   // accepted peaks of the frame
   ulonglong2 plh[PCAP];                       // P[lo-1], P[hi]
@@ -63,15 +69,13 @@ struct WarpShared {
   int t_bins[ACAP];                           // last three peak bins: b1 | b2 << 8 | b3 << 16
   int t_np[ACAP];                             // points so far
   uint32_t t_amp[ACAP];                       // lastAmp
-  uint32_t t_wm[ACAP];                        // this frame: retained candidates (bit j = bin wlo + j)
+  uint32_t t_wm[ACAP];                        // this frame: retained candidates (bit j = bin wlo + j); v2: peak lanes per owner
   unsigned char pidx[FA_MAX_BANDS];           // index of the accepted peak at bin b in the accepted list
   unsigned char newlist[PCAP];                // un-owned peaks above the gate, in peak order
-  // ---- end of the scratch-able prefix ----
-  uint32_t pmask[FA_MAX_BANDS / 32 + 1];      // bit b: an accepted peak has pk == b (all zero between frames)
-  uint32_t wmask[2][FA_MAX_BANDS];            // K3 v2: [set][bin] lanes whose track slot holds the peak at `bin` in its window
-                                              // (all zero between frames)
 };
-constexpr int kScratchBytes = (int)offsetof(WarpShared, pmask);
+static_assert(offsetof(WarpShared, cs) % 16 == 0 && sizeof(WarpShared) % 16 == 0, "16-byte aligned slices");
+constexpr int kScratchOff = (int)offsetof(WarpShared, cs);
+
 
 struct ScanState {
   int current_frame, no_fm_segs, c_ci, c_started, w, k;
@@ -360,57 +364,69 @@ __device__ __forceinline__ void accumulate_fm(const FaSegmentParams& p, WarpShar
 
 // O() @B27088, fast path: the segment's tables (T tracks, len rows, n_pts points) fit the per-frame shared-memory bytes
 // that are dead during finalisation.  Same results as finalize_segment below, which works in HBM for any size.
-//   scratch: mean f64[T] | rank u8[T] | slot s8[T] | order u8[T] | rc i32[len] | ro i32[len] | key u32[n_pts]
+//   scratch: mean f64[T] | rank u8[T] | slot s8[T] | order u8[T] | rc i32[len] | ro i32[len] | key u32[cap]
 //   key = rank << 24 | ordinal << 14 | point << 2 | slot  (T <= 255, ordinal < 1024, point < 4096)
+//   (Keeping the points' energy / bin / span beside the keys was tried: 12 B per point instead of 4 no longer fits the
+//   1000-1600 selected points of a synthetic-speech segment, and more shared memory per warp squeezes the L1 -- so the row
+//   pass prefetches its points' pool lines to L1 instead, ahead of the dependent loads.)
 // Returns -3 (nothing changed) when the selected points turn out not to fit: the caller then takes the HBM path.
-__device__ __forceinline__ bool finalize_fits(const ScanState& st, const int len) {
+__device__ __forceinline__ bool finalize_fits(const ScanState& st, const int len, const int scratch_bytes) {
   const int T = st.n_tr;
   const int need = ((8 * T + 3 * T + 7) & ~7) + 8 * len;
-  return T <= 255 && st.n_pts < 4096 && st.c_ci + 1 < 1024 && len < 1024 && need + 1024 <= kScratchBytes;
+  return T <= 255 && st.n_pts < 4096 && st.c_ci + 1 < 1024 && len < 1024 && need + 2304 <= scratch_bytes;
 }
 
 __device__ __noinline__ int finalize_fast(const FaSegmentParams p, WarpShared& S, ScanState& st, const Bases bs,
                                           const int n_arg, const int lane) {
+  const int scratch_bytes = p.smem_per_warp - kScratchOff;
   const int len = n_arg - st.no_fm_segs;
   const int start = st.current_frame - len;
   const double vmin = st.v;
   const int T = st.n_tr, NP = st.n_pts;
-  unsigned char* W = reinterpret_cast<unsigned char*>(&S);
+  unsigned char* W = reinterpret_cast<unsigned char*>(&S.cs[0][0]);
   double* mean = reinterpret_cast<double*>(W);
   unsigned char* rank = W + 8 * T;
   signed char* slot = reinterpret_cast<signed char*>(rank + T);
   unsigned char* order = rank + 2 * T;
   int* rc = reinterpret_cast<int*>(W + ((11 * T + 7) & ~7));
   int* ro = rc + len;
-  uint32_t* key = reinterpret_cast<uint32_t*>(ro + len);
+  unsigned char* tail = W + ((((11 * T + 7) & ~7) + 8 * len + 7) & ~7);
+  const int cap_keys = (scratch_bytes - (int)(tail - W)) / 4;
+  uint32_t* key = reinterpret_cast<uint32_t*>(tail);
+  const unsigned lt = (1u << lane) - 1u;
   __syncwarp();  // the track table is written through at every update (by whichever lane owns the track)
-  // get_ranked_formants @B35670: count >= 2, mean >= 7, stable ascending by mean
+  // get_ranked_formants @B35670: count >= 2, mean >= 7, stable ascending by mean.  Most tracks are one-point noise tracks, so
+  // the eligible ones are compacted first (their means and indices, in the not-yet-used key area) and ranked among themselves
+  double* cmean = reinterpret_cast<double*>(tail);                  // [nr]   (>= 4 KB are left: finalize_fits)
+  unsigned char* cidx = tail + 2048;                                // [nr]
   int nr = 0;
   for (int i0 = 0; i0 < T; i0 += 32) {
     const int i = i0 + lane;
     bool elig = false;
+    double m = -1.0;
     if (i < T) {
-      const double m = p.trk_sum_eb[bs.tb + i] / p.trk_sum_e[bs.tb + i];
+      m = p.trk_sum_eb[bs.tb + i] / p.trk_sum_e[bs.tb + i];
       elig = p.trk_count[bs.tb + i] >= 2 && m >= 7;
       mean[i] = elig ? m : -1.0;
       slot[i] = -1;
     }
-    nr += __popc(__ballot_sync(FULL, elig));
+    const unsigned em = __ballot_sync(FULL, elig);
+    if (elig) { const int k = nr + __popc(em & lt); cmean[k] = m; cidx[k] = (unsigned char)i; }
+    nr += __popc(em);
   }
   for (int r = lane; r < len; r += 32) rc[r] = 0;
   __syncwarp();
-  for (int i = lane; i < T; i += 32) {
-    const double m = mean[i];
-    if (m >= 7) {
-      int rk = 0;
+  for (int k = lane; k < nr; k += 32) {
+    const double m = cmean[k];
+    int rk = 0;
 #pragma unroll 4
-      for (int j = 0; j < T; j++) {
-        const double mj = mean[j];
-        rk += (mj >= 7 && (mj < m || (mj == m && j < i))) ? 1 : 0;
-      }
-      rank[i] = (unsigned char)rk;
-      order[rk] = (unsigned char)i;
+    for (int j = 0; j < nr; j++) {
+      const double mj = cmean[j];
+      rk += (mj < m || (mj == m && j < k)) ? 1 : 0;   // the compacted list keeps the tracks in creation order
     }
+    const int i = cidx[k];
+    rank[i] = (unsigned char)rk;
+    order[rk] = (unsigned char)i;
   }
   __syncwarp();
   // slot assignment of straighten_formants @B35074 (sequential over the ranking)
@@ -439,10 +455,8 @@ __device__ __noinline__ int finalize_fast(const FaSegmentParams p, WarpShared& S
   // c_ci of its frame, quirk #1) grows strictly from the second call of the epoch on, so the points of one row are
   // contiguous in the pool -- except the run at the pool's head (the first call, whose stale label is arbitrary and may
   // name a row that comes again later).  One pass therefore does everything: select (track has a slot), check for the
-  // reference's TypeError, compact the selected points' keys into shared memory in pool order, and note where each
-  // row's keys start; the head run is kept as a second key range [0, x_cnt) of row x_row.
-  const unsigned lt = (1u << lane) - 1u;
-  const int cap_keys = (kScratchBytes - (int)(reinterpret_cast<unsigned char*>(key) - W)) / 4;
+  // reference's TypeError, compact the selected points' keys and payloads into shared memory in pool order, and note
+  // where each row's keys start; the head run is kept as a second key range [0, x_cnt) of row x_row.
   bool thrown = false, nofit = false;
   int n_sel = 0, x_row = -1, x_cnt = 0, last_label = -1;
   {
@@ -507,6 +521,12 @@ __device__ __noinline__ int finalize_fast(const FaSegmentParams p, WarpShared& S
     const int k1 = rc[fr], off = k1 ? ro[fr] : 0;
     const int k2 = fr == x_row ? x_cnt : 0;   // the head run's keys sit at [0, x_cnt)
     const int k = k1 + k2;
+    // the points are visited in (rank, ordinal) order, each visit two dependent loads from the pool: pull the lines to L1 first
+    for (int z = 0; z < k; z++) {
+      const int q = (int)((key[z < k1 ? off + z : z - k1] >> 2) & 4095u);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.pt_e + bs.pb + q));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.pt_binspan + bs.pb + q));
+    }
     float f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0, f6 = 0, f7 = 0, f8 = 0, g0 = 0, g1 = 0, g2 = 0;
     long long last = -1;
     for (int it = 0; it < k; it++) {
@@ -775,7 +795,7 @@ __device__ __forceinline__ int finalize_copy(const FaSegmentParams& p, WarpShare
   if (!(len > p.seg_min_frames && st.c_started >= 2)) return 0;
   ScanState cp = st;
   int r = -3;
-  if (p.finalize_in_smem && finalize_fits(st, len)) {
+  if (p.finalize_in_smem && finalize_fits(st, len, p.smem_per_warp - kScratchOff)) {
     r = finalize_fast(p, S, cp, bs, n_arg, lane);
     st.n_slots = ACAP;  // the track slots were used as scratch: the seg_reset that follows clears all of them
   }
@@ -786,15 +806,14 @@ __device__ __forceinline__ int finalize_copy(const FaSegmentParams& p, WarpShare
 
 // kBound only sets the register cap (65536 / kBound): 128 -> 127 registers, 640 -> 96, 1024 -> 64
 template <int kBound>
-__global__ void __launch_bounds__(kBound) fa_segment_kernel(const FaSegmentParams p) {
+__global__ void __launch_bounds__(kBound, 1) fa_segment_kernel(const FaSegmentParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  WarpShared* sh = reinterpret_cast<WarpShared*>(smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int ui = blockIdx.x * (int)(blockDim.x >> 5) + wib;
   if (ui >= p.utt_count) return;
   const int u = p.utt_begin + ui;
   if (p.redo_only && p.overflow[u] != 2) return;   // second launch behind fa_segment2_kernel: only what it handed back
-  WarpShared& S = sh[wib];
+  WarpShared& S = *reinterpret_cast<WarpShared*>(smem_raw + (size_t)wib * p.smem_per_warp);
   Bases bs;
   bs.row0 = p.frame_off[u];
   bs.F = (int)(p.frame_off[u + 1] - bs.row0);
@@ -1048,8 +1067,13 @@ __device__ __forceinline__ void accumulate_fm2(const FaSegmentParams& p, WarpSha
   __syncwarp();   // every claimant record has been read; the owners are rewritten below
   // ---- phase 3: every owning track absorbs its (merged) peaks -- the first owned peak's lane acts for the track ----
   const bool owned = active && best_q >= 0;
-  const unsigned grp = __match_any_sync(FULL, owned ? best_q : -1 - lane);
+  // peak lanes with the same owner: OR the lane bit into the owner slot's word, read it back (MATCH.ANY costs ~450 cycles here)
+  if (owned) atomicOr(&S.t_wm[best_q], 1u << lane);
+  __syncwarp();
+  const unsigned grp = owned ? S.t_wm[best_q] : 0u;
   const bool leader = owned && lane == __ffs(grp) - 1;
+  __syncwarp();
+  if (leader) S.t_wm[best_q] = 0u;
   int lo_b = (int)(my_pkd & 0xffu), hi_b = (int)((my_pkd >> 8) & 0xffu), ob = my_pk;
   uint32_t bamp = my_amp;
   unsigned long long pl = my_pl, ph = my_ph;
@@ -1139,14 +1163,13 @@ struct PeakRegs {
 };
 
 template <int kBound>
-__global__ void __launch_bounds__(kBound) fa_segment2_kernel(const FaSegmentParams p) {
+__global__ void __launch_bounds__(kBound, 1) fa_segment2_kernel(const FaSegmentParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  WarpShared* sh = reinterpret_cast<WarpShared*>(smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int ui = blockIdx.x * (int)(blockDim.x >> 5) + wib;
   if (ui >= p.utt_count) return;
   const int u = p.utt_begin + ui;
-  WarpShared& S = sh[wib];
+  WarpShared& S = *reinterpret_cast<WarpShared*>(smem_raw + (size_t)wib * p.smem_per_warp);
   Bases bs;
   bs.row0 = p.frame_off[u];
   bs.F = (int)(p.frame_off[u + 1] - bs.row0);
@@ -1166,7 +1189,7 @@ __global__ void __launch_bounds__(kBound) fa_segment2_kernel(const FaSegmentPara
   st.y = p.y0; st.v = p.v0; st.x = p.y0; st.v0 = p.v0; st.T = 0; st.s_energy = 0; st.c_energy = 0;
   st.n_tr = 0; st.n_pts = 0; st.n_slots = 0; st.n_segs = 0; st.n_stored = 0; st.n_rows = 0; st.n_syls = 0;
   st.overflow = 0;
-  for (int r = lane; r < ACAP; r += 32) S.t_id[r] = -1;
+  for (int r = lane; r < ACAP; r += 32) { S.t_id[r] = -1; S.t_wm[r] = 0u; }
   if (lane <= FA_MAX_BANDS / 32) S.pmask[lane] = 0u;
   for (int r = lane; r < 2 * FA_MAX_BANDS; r += 32) (&S.wmask[0][0])[r] = 0u;
   __syncwarp();
@@ -1197,6 +1220,10 @@ __global__ void __launch_bounds__(kBound) fa_segment2_kernel(const FaSegmentPara
     if (nc_next > maxp) st.overflow = 1;
     const double g = g_next;
     if (t + 1 < bs.F) prefetch(t + 1);
+    // pauses are short iterations: one frame of look-ahead does not cover a DRAM miss (ncu: 6 % of the stall samples sat on
+    // the first use of g) -- pull the candidate rows of frame t + 4 towards L2 now, one 32-byte sector per lane
+    if (t + 4 < bs.F && lane < maxp)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.cand + (size_t)(bs.row0 + t + 4) * maxp + lane));
 
     // ---- D() @B25717: filter the candidates of K2 by the gate v (value at frame start) ----
     const double v = st.v;
@@ -1275,7 +1302,10 @@ __global__ void __launch_bounds__(kBound) fa_segment2_kernel(const FaSegmentPara
       }
     }
     st.c_ci++;
-    if (fin != -2) seg_reset(st, S, -1, lane);  // the promise's micro-task runs before the next frame
+    if (fin != -2) {
+      S.t_wm[lane] = 0u; S.t_wm[lane + 32] = 0u;   // the finalisation used the track slots as scratch
+      seg_reset(st, S, -1, lane);                  // the promise's micro-task runs before the next frame
+    }
   }
   // segment_truncate @B30800
   if (!st.overflow) {
@@ -1615,11 +1645,10 @@ __global__ void __launch_bounds__(kCtlWarps * 32) fa_segctl_verify_kernel(const 
 }
 
 template <int kBound>
-__global__ void __launch_bounds__(kBound) fa_segtrack_kernel(const FaSegmentParams p) {
+__global__ void __launch_bounds__(kBound, 1) fa_segtrack_kernel(const FaSegmentParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  WarpShared* sh = reinterpret_cast<WarpShared*>(smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  WarpShared& S = sh[wib];
+  WarpShared& S = *reinterpret_cast<WarpShared*>(smem_raw + (size_t)wib * p.smem_per_warp);
   const int worker = blockIdx.x * (int)(blockDim.x >> 5) + wib;
   int maxp = p.maxp;
   asm volatile("" : "+r"(maxp));
@@ -1718,7 +1747,7 @@ __global__ void __launch_bounds__(kBound) fa_segtrack_kernel(const FaSegmentPara
     if (!st.overflow) {
       const int len = E.n_arg - st.no_fm_segs;
       int r = -3;
-      if (p.finalize_in_smem && finalize_fits(st, len)) r = finalize_fast(p, S, st, bs, E.n_arg, lane);
+      if (p.finalize_in_smem && finalize_fits(st, len, p.smem_per_warp - kScratchOff)) r = finalize_fast(p, S, st, bs, E.n_arg, lane);
       if (r == -3) r = finalize_segment(p, st, bs, E.n_arg, lane);
     }
     if (st.overflow && lane == 0) p.overflow[u] = 1;
@@ -1766,7 +1795,10 @@ cudaError_t fa_launch_segment(const FaSegmentParams& p_in, cudaStream_t s, int* 
   if (p_in.utt_count <= 0) return cudaSuccess;
   FaSegmentParams p = p_in;
   const int kw = p.warps_per_cta >= 1 && p.warps_per_cta <= 4 ? p.warps_per_cta : kWarps;
-  const int bytes = (int)sizeof(WarpShared) * kw;
+  // per-warp shared-memory slice = the struct.  (Extra scratch behind it for finalize_fast was tried: 56 KB per CTA x 4 CTAs
+  // per SM leaves ~4 KB of L1 for the candidate / pool reads and the stack, and every variant of the scan lost 0.35 ms.)
+  p.smem_per_warp = (int)sizeof(WarpShared);
+  const int bytes = p.smem_per_warp * kw;
   const int regs = p.reg_cap > 0 ? p.reg_cap : 128;
   if (p.mode == 1) {
     if (p.ctl_chunk > 0) {
