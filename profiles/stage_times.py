@@ -24,7 +24,7 @@ for v in variants:
     old = {k: os.environ.get(k) for k, _ in sets}
     for k, val in sets:
         os.environ[k] = val
-    cfg = FaConfig.default(output_level=LEVEL, want_spectrum=1)
+    cfg = FaConfig.default(output_level=LEVEL, want_spectrum=int(os.environ.get("WANT_SPEC", "1")))
     e = Engine(cfg)
     e.set_pipeline(1)
     for i, p in enumerate(pcms):

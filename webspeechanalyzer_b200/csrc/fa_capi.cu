@@ -144,6 +144,11 @@ struct fa_handle {
   int k3_impl = 2;       // FA_K3_IMPL: 2 = accumulate_fm2 kernel + redo launch (default), 1 = the general kernel alone
   int k3_warps = 0, k3_regs = 0, k3_finalize_smem = 1, k2_staged = 0;   // FA_K3_WARPS, FA_K3_REGS, FA_K3_FINALIZE_HBM, FA_K2_STAGED
   bool debug_sync = false;  // FA_DEBUG_SYNC
+  int k1_fused = 0;         // FA_K1_FUSED=1: the fused K1 kernel (fft_size 2048, utterance mode) instead of K1a + K1b.  Measured
+                            // slower on B200 (C2: 0.99 vs 0.94 ms with dB rows, 0.93 vs 0.86 ms without; the stage is FP32-issue
+                            // bound and the fused kernel's barriers idle issue slots), so it is a knob: it moves 1.19 instead of
+                            // 2.79 GB through HBM and needs no 4 KB-per-frame magnitude buffer when no dB rows are wanted
+  bool use_fused() const { return k1_fused != 0 && N == 2048 && chunk_frames <= 0 && !frames_mode; }
   DevBuf g_segs, g_syls, g_formants, g_energy, g_features;
   int n_weights = 0;
   long long track_total = 0, urow_total = 0;
@@ -315,6 +320,7 @@ int fa_create(const fa_config* cfg, int device, fa_handle** out) {
   if (getenv("FA_K3_FINALIZE_HBM")) h->k3_finalize_smem = 0;
   if (const char* ev = getenv("FA_K2_STAGED")) h->k2_staged = atoi(ev) != 0;
   if (getenv("FA_DEBUG_SYNC")) h->debug_sync = true;
+  if (const char* ev = getenv("FA_K1_FUSED")) h->k1_fused = atoi(ev) != 0;
 
   // Streams are created on first use (ensure_sub_streams): the device has at most 32 hardware work queues
   // (CUDA_DEVICE_MAX_CONNECTIONS, default 8) and streams beyond that alias onto the same queue, where a stream that waits
@@ -639,7 +645,8 @@ static int prepare(fa_handle* h) {
     if (any16) FA_CUDA(h->d_pcm16.reserve((size_t)(dev + 16) * sizeof(int16_t)));
   }
   const size_t Fz = (size_t)std::max<long long>(F, 1), nz = (size_t)n;
-  FA_CUDA(h->d_spec.reserve(Fz * h->M * sizeof(float)));  // the K1a -> K1b magnitude rows, turned into dB rows in place
+  // the K1a -> K1b magnitude rows, turned into dB rows in place; the fused kernel needs them only as dB output
+  if (h->want_spec || !h->use_fused()) FA_CUDA(h->d_spec.reserve(Fz * h->M * sizeof(float)));
   FA_CUDA(h->d_frames.reserve(Fz * h->B * sizeof(uint32_t)));
   FA_CUDA(h->d_counter.reserve(2 * kMaxSub * sizeof(int)));
   if (h->cfg.output_level >= 3) {
@@ -833,6 +840,7 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
   sp.clamp_db = c.clamp_db;
   sp.scratch_mag = 1;
   sp.write_db = h->want_spec;
+  sp.fused = h->use_fused();
   sp.n_rows = sb.r1 - sb.r0;
   sp.spec_db = h->d_spec.as<float>();
   sp.frames = h->d_frames.as<uint32_t>();

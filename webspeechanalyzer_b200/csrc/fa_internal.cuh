@@ -42,6 +42,7 @@ struct FaSpectrumParams {
                                  // generic path: dB rows or nullptr
   int scratch_mag;               // 1: spec_db is allocated and may be used as the K1a -> K1b magnitude buffer
   int write_db;                  // 1: the caller wants the dB rows
+  int fused;                     // 1: fft_size 2048 in utterance mode runs the fused K1 kernel (no magnitude round trip)
   long long n_rows;              // frames of the sub-batch
   uint32_t* frames;              // [F_total][B] or nullptr
   int* work_counter;             // dynamic utterance queue
