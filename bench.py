@@ -15,6 +15,13 @@ batch (sharded by utterance, no data-path collective) => weak scaling.
   roofline  the dominant kernel's algorithmic bytes / its CUDA-event time vs the measured HBM peak
   cpu_baseline  the CPU oracle (a restatement: kind "port") on the host cores, same workload
 
+With --gpus N > 1 (torchrun, one rank per GPU) the workload is BASELINE.json configs[2] (C3): 48 kHz utterances, Syllable
+Features (output_level 13), 12 500 utterances per GPU (100 000 on 8 GPUs), utterance u on rank u mod N, 16-bit PCM in pinned host
+memory (what WAV files hold), NO data-path collective; the feature rows of all ranks are gathered on the host (gloo group) inside
+the e2e timed region.  The line also carries the N-rank PCIe / host-memory floor of a step, measured in the same run with the same
+buffers on all ranks at once, and the one-rank-alone figures of the same workload on the same box (weak-scaling reference).
+`--workload c3` runs the same shard on one GPU.
+
 `--impl reference` times the reference's CPU path.  The reference is browser JavaScript and this image has no JS
 engine, so oracle/_ref does not exist; the arm runs the C restatement (oracle/fa_oracle.c) with OpenMP over
 utterances on all host threads (kind "port").
@@ -46,6 +53,10 @@ N_UTT, SECONDS, SR = 1000, 5, 16000
 WORKLOAD = ("C2: 1000 synthetic 5 s 16 kHz utterances per GPU, spectrum + formants output modes + 53-dim Segment "
             "Features (output_level 5, fftSize 2048, smoothing 0.8, mel 128, step 25 ms)")
 METRIC = "audio-sec/sec for 53-dim Segment Features (spectrum + formants modes)"
+C3_UTT, C3_SECONDS, C3_SR, C3_HOP = 12500, 5, 48000, 1200
+C3_WORKLOAD = ("C3: synthetic 5 s 48 kHz utterances, Syllable Features (output_level 13, fftSize 2048, smoothing 0.8, mel 128, "
+               "step 25 ms), sharded by utterance (u mod N), int16 PCM from pinned host memory, host-side gather of the 53-dim rows")
+C3_METRIC = "audio-sec/sec for 53-dim Syllable Features (sharded by utterance)"
 
 
 def bench_config():
@@ -153,31 +164,280 @@ def cpu_port_run(cfg, pcms, threads: int):
 
 
 def run_reference(args):
+    """The reference's CPU implementation of the path on the host cores, on this arm's workload: C2 for one GPU, the C3
+    workload when launched for several (rank 0 alone works, the others exit).  The reference is browser JavaScript and neither
+    this image nor the GPU boxes carry a JS engine (probed below, reported in the line), so the arm runs the C restatement
+    (oracle/fa_oracle.c, pinned against outputs of the reference's own code) with OpenMP over utterances: kind "port"."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
-    cfg = bench_config()
+    import shutil
+    js = {name: shutil.which(name) for name in ("node", "nodejs", "deno", "bun", "qjs")}
+    js_found = {k: v for k, v in js.items() if v}
+    c3 = args.workload == "c3" or (args.workload == "auto" and world > 1)
     cores = os.cpu_count() or 1
-    n_utt = args.utts
-    pcms = make_workload(0, n_utt)
+    if c3:
+        from oracle import oracle
+        from webspeechanalyzer_b200 import synth_speech_i16_batch
+        cfg = c3_config()
+        n_utt = args.utts if args.utts != N_UTT else 2000       # a bounded sample of the 12 500-utterance shard
+        n = C3_SECONDS * C3_SR
+        i16 = synth_speech_i16_batch(np.empty(n_utt * n, np.int16), n_utt, n, C3_SR, 20261017, 0, world, threads=cores)
+        flat = i16.astype(np.float32) * np.float32(1.0 / 32768.0)      # what fa_submit_pcm_i16 hands the kernels
+        offs = np.arange(n_utt + 1, dtype=np.int64) * n
+        sr, seconds, metric, workload = C3_SR, C3_SECONDS, C3_METRIC, C3_WORKLOAD
+        sample = f"{n_utt} of {C3_UTT} utterances per GPU and step ({n_utt * seconds} s of audio), C oracle, OpenMP over utterances"
+
+        def step(sub=None):
+            m = n_utt if sub is None else sub
+            t0 = time.perf_counter()
+            fr = oracle.run_batch(cfg, flat[: m * n], offs[: m + 1], sr, cores)
+            return time.perf_counter() - t0, fr
+    else:
+        cfg = bench_config()
+        n_utt = args.utts
+        pcms = make_workload(0, n_utt)
+        sr, seconds, metric, workload = SR, SECONDS, METRIC, WORKLOAD
+        sample = f"{n_utt} of {N_UTT} utterances per step ({n_utt * seconds} s of audio), C oracle, OpenMP over utterances"
+
+        def step(sub=None):
+            return cpu_port_run(cfg, pcms if sub is None else pcms[:sub], cores)
     for _ in range(args.warmup):
-        cpu_port_run(cfg, pcms[: max(8, n_utt // 10)], cores)
-    t = 0.0
+        step(max(8, n_utt // 10))
+    t, frames = 0.0, 0
     for _ in range(args.steps):
-        dt, frames = cpu_port_run(cfg, pcms, cores)
+        dt, frames = step()
         t += dt
-    audio = n_utt * SECONDS * args.steps
+    audio = n_utt * seconds * args.steps
     val = audio / t
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "audio-s/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": metric, "value": val, "unit": "audio-s/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 spectrum / u32 peaks / f64 features", "data": "synthetic",
             "frames_per_sec": frames * args.steps / t,
-            "config": {"workload": WORKLOAD, "utterances_per_step": n_utt},
-            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                             "sample": f"{n_utt} of {N_UTT} utterances per step ({n_utt * SECONDS} s of audio), C oracle, OpenMP over utterances"},
+            "config": {"workload": workload, "utterances_per_step": n_utt},
+            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "reference is browser JavaScript; no JS engine in this image, so the CPU arm is the C restatement (oracle/fa_oracle.c)"}
+            "js_engines_found": js_found,
+            "note": "reference is browser JavaScript; no JS engine on this box (probed: node, nodejs, deno, bun, qjs), so the CPU "
+                    "arm is the scalar -O2 C restatement (oracle/fa_oracle.c) with OpenMP -- a stated baseline, not the reference's "
+                    "own JavaScript" if not js_found else
+                    "a JS engine exists on this box: oracle/run_reference_modules.js can execute the reference's own modules here"}
     print(json.dumps(line))
+    return 0
+
+def c3_config():
+    from webspeechanalyzer_b200 import FaConfig
+    return FaConfig.default(output_level=13, want_spectrum=0)
+
+
+def run_c3(args, world, rank, local):
+    """BASELINE configs[2]: the utterance-sharded Syllable-Features workload (see the module docstring)."""
+    import torch
+    import torch.distributed as dist
+
+    from webspeechanalyzer_b200 import Engine, PinnedBuffer, shard, synth_speech_i16_batch
+    from webspeechanalyzer_b200 import _capi
+    import ctypes as C
+
+    torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
+    host_group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        host_group = dist.new_group(backend="gloo")     # the host-side gather of feature rows: no NCCL on the data path
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    cfg = c3_config()
+    n_utt = args.utts if args.utts != N_UTT else C3_UTT
+    n = C3_SECONDS * C3_SR
+    frames_per_step = n_utt * (n // C3_HOP)
+    audio_per_step = n_utt * C3_SECONDS
+    # ---- the shard: utterances rank, rank + world, ... of the global set, 16-bit PCM in page-locked host memory ----
+    t_gen = time.perf_counter()
+    pcm = PinnedBuffer((n_utt * n,), np.int16, write_combined=bool(args.wc))
+    threads = max(1, (len(os.sched_getaffinity(0)) or 1) // max(1, world))
+    synth_speech_i16_batch(pcm.array, n_utt, n, C3_SR, 20261017, rank, world, threads=threads)
+    offs = np.arange(n_utt + 1, dtype=np.int64) * n
+    utt_ids = np.arange(n_utt, dtype=np.int64) * world + rank
+    t_gen = time.perf_counter() - t_gen
+
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    engs = []
+    for j in range(2):
+        e = Engine(cfg, device=local)
+        e.set_stream(streams[j].cuda_stream)
+        engs.append(e)
+    eng = engs[0]
+
+    # ---- device-resident throughput: PCM uploaded once, K passes of the whole path ----
+    eng.set_pipeline(args.pipeline)
+    eng.submit_batch(0, pcm.array, offs, C3_SR)
+    eng.upload()
+    for _ in range(max(3, args.warmup)):
+        eng.run_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(streams[0])
+    for _ in range(args.steps):
+        eng.run_resident()
+    ev1.record(streams[0])
+    barrier()
+    ms_max = max_over_ranks(ev0.elapsed_time(ev1))
+    launches_per_step = eng.launches
+    stage_acc = np.zeros(5)
+    eng.set_pipeline(1)
+    eng.run_resident()
+    for _ in range(3):
+        eng.run_resident()
+        eng.sync()
+        st = eng.stage_times()
+        stage_acc += np.array([st["spectrum"], st["peaks"], st["segment"], st["features"], st["total"]])
+    stage_ms = stage_acc / 3
+    eng.download()
+    eng.sync()
+    tot = eng.counts()
+    value = world * audio_per_step * args.steps / (ms_max / 1e3)
+
+    # ---- end to end: host PCM -> device -> feature rows -> host -> gathered on rank 0 ----
+    gathered = {"rows": 0, "bytes": 0}
+    d2h_seen = []
+
+    def launch(j):
+        e = engs[j]
+        e.reset()
+        e.set_pipeline(args.e2e_pipeline)
+        e.submit_batch(0, pcm.array, offs, C3_SR)      # zero copy: the H2D transfers read the pinned buffer
+        e.run()                                        # asynchronous
+
+    def collect(j, group):
+        e = engs[j]
+        e.sync()
+        ct = e.counts_table()
+        feats = e.feature_table()
+        d2h_seen.append(int(feats.nbytes + ct.nbytes))
+        keys = shard.keys_from_counts(utt_ids, ct["feature_rows"])
+        out = shard.gather_rows(keys, feats, dst=0, group=group, sort=False)
+        if out is not None:
+            gathered["rows"], gathered["bytes"] = int(out[1].shape[0]), int(out[0].nbytes + out[1].nbytes)
+
+    def e2e_steps(k_steps, group):
+        inflight = []
+        for k in range(k_steps):
+            j = k % 2
+            if len(inflight) == 2:
+                collect(inflight.pop(0), group)
+            launch(j)
+            inflight.append(j)
+        while inflight:
+            collect(inflight.pop(0), group)
+
+    e2e = None
+    alone = None
+    floor = None
+    if not args.no_e2e:
+        e2e_steps(2, host_group)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps(args.steps, host_group)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * audio_per_step * args.steps / dt, "unit": "audio-s/s",
+               "h2d_bytes_per_step": int(pcm.array.nbytes), "d2h_bytes_per_step": int(d2h_seen[-1]),
+               "ms_per_step": 1e3 * dt / args.steps, "batches_in_flight": 2,
+               "gathered_rows_per_step": gathered["rows"], "gathered_bytes_per_step": gathered["bytes"],
+               "path": "per rank and step: fa_reset + fa_submit_pcm_i16_batch (pinned int16 PCM, converted on the device) + fa_run "
+                       "(async) ... fa_sync + fa_copy_counts_table + fa_copy_features, then shard.gather_rows of the keyed 53-dim "
+                       "rows to rank 0 over a host-side gloo group; all inside the timed region"}
+        # ---- the floor of a step: the same pinned buffer copied to the device by ALL ranks at once ----
+        L = _capi.lib()
+        ms = C.c_float(0)
+
+        def probe(reps):
+            rc = L.fa_pcie_probe(local, C.c_void_p(pcm.array.ctypes.data), pcm.array.nbytes, reps, 0, C.byref(ms))
+            if rc != 0:
+                raise RuntimeError(f"fa_pcie_probe failed ({rc})")
+            return float(ms.value)
+
+        probe(1)
+        barrier()
+        floor_ms = max_over_ranks(probe(4))
+        barrier()
+        floor = {"h2d_ms_per_step_all_ranks_at_once": floor_ms, "gbps_per_gpu": pcm.array.nbytes / floor_ms / 1e6,
+                 "aggregate_gbps": world * pcm.array.nbytes / floor_ms / 1e6,
+                 "e2e_fraction_of_floor": floor_ms / e2e["ms_per_step"],
+                 "how": "fa_pcie_probe: 4 back-to-back cudaMemcpyAsync of the step's int16 PCM from the same page-locked buffer, "
+                        "CUDA events, all ranks between two barriers, max over ranks"}
+        # ---- weak-scaling reference on the same box: rank 0 alone, the other GPUs idle ----
+        if world > 1:
+            if rank == 0:
+                e2e_steps(2, None)
+                t0 = time.perf_counter()
+                e2e_steps(max(3, args.steps // 2), None)
+                torch.cuda.synchronize()
+                dt1 = time.perf_counter() - t0
+                f1 = probe(4)
+                alone = {"e2e_value": audio_per_step * max(3, args.steps // 2) / dt1, "e2e_ms_per_step": 1e3 * dt1 / max(3, args.steps // 2),
+                         "h2d_floor_ms": f1, "h2d_gbps": pcm.array.nbytes / f1 / 1e6}
+            barrier()
+    clocks = sampler.stop()
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        N, B, hop = cfg.fft_size, cfg.bands, C3_HOP
+        alg = {
+            "spectrum": frames_per_step * (2 * hop + 4 * B),                                       # int16 PCM once + u32 frame (no dB rows)
+            "peaks": frames_per_step * (4 * B + 4 * 6 + 12),
+            "segment": frames_per_step * (4 * B + 4 * 6 + 12) + tot["formant_rows"] * 48,
+            "features": tot["formant_rows"] * 36 + tot["feature_rows"] * 424,
+        }
+        names = ["spectrum", "peaks", "segment", "features"]
+        shares = {k: float(stage_ms[i] / max(stage_ms[4], 1e-9)) for i, k in enumerate(names)}
+        top = max(names, key=lambda k: stage_ms[names.index(k)])
+        stages = {k: {"ms": float(stage_ms[i]), "share": shares[k], "algorithmic_bytes": int(alg[k]),
+                      "achieved_gbs": alg[k] / (stage_ms[i] * 1e-3) / 1e9 if stage_ms[i] > 0 else None,
+                      "frac_of_hbm_peak": alg[k] / (stage_ms[i] * 1e-3) / 1e9 / peak if stage_ms[i] > 0 else None}
+                  for i, k in enumerate(names)}
+        kern = {"spectrum": "fa_fftmag_2048_kernel", "peaks": "fa_peaks_kernel", "segment": "fa_segment2_kernel",
+                "features": "fa_features_kernel"}[top]
+        ach = stages[top]["achieved_gbs"]
+        line = {
+            "metric": C3_METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 spectrum / u32 peaks / f64 features", "data": "synthetic",
+            "frames_per_sec": world * frames_per_step * args.steps / (ms_max / 1e3),
+            "config": {"workload": C3_WORKLOAD, "utterances_per_gpu": n_utt, "utterances_total": n_utt * world,
+                       "parallelism": f"shard-by-utterance x{world} (u mod N), no data-path collective, host-side gather (gloo)",
+                       "pinned_pcm": "write-combined" if args.wc else "default",
+                       "l2": f"inputs ({pcm.array.nbytes / 1e9:.1f} GB of PCM per step and GPU) exceed the 126 MB L2; no flush needed",
+                       "workload_generation_s": t_gen},
+            "roofline": {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src, "share_of_step": shares[top],
+                         "note": "spectrum is FP32-issue bound, segment scan / features latency bound (DESIGN.md)"},
+            "stages": stages, "e2e": e2e, "pcie_floor": floor, "one_rank_alone_same_box": alone, "host_affinity": numa,
+            "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks,
+            "results": {"segments": tot["segments"], "feature_rows": tot["feature_rows"], "formant_rows": tot["formant_rows"],
+                        "overflow": tot["overflow"]},
+        }
+        print(json.dumps(line))
+    for e in engs:
+        e.close()
+    pcm.free()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 
@@ -188,6 +448,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--utts", type=int, default=N_UTT, help="utterances per GPU per step (default: the C2 workload)")
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3"],
+                    help="auto: C2 on one GPU (the configuration the metric is quoted on), C3 (utterance-sharded Syllable Features) "
+                         "when launched with more than one rank")
+    ap.add_argument("--wc", type=int, default=0, help="C3: allocate the pinned PCM buffer write-combined (cudaHostAllocWriteCombined)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--serial", action="store_true", help="one sub-batch (profiling: full-batch kernel launches)")
@@ -210,6 +474,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the hot path has no CPU fallback")
+    if args.workload == "c3" or (args.workload == "auto" and world > 1):
+        return run_c3(args, world, rank, local)
     torch.cuda.set_device(local)
     numa = bind_to_gpu_numa_node(local)
     if world > 1:

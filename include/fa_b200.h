@@ -41,6 +41,7 @@ extern "C" {
 #define FA_N_FEATURES 53 /* /root/reference/src/localstore.js:7 (levels 5 and 13 -> 53) */
 #define FA_N_UTT_FEATURES 264 /* get_utterance_features, /root/reference/dist/main.js:2@B107983 (level 11) */
 #define FA_ABI_VERSION 1
+#define FA_ALL_UTTS (-1) /* utt_id of the getters: the whole batch, in submission order (utterance ids themselves are >= 0) */
 
 typedef enum fa_status {
   FA_OK = 0,
@@ -142,6 +143,8 @@ FA_API const char* fa_status_string(int status);
 FA_API int fa_create(const fa_config* cfg, int device, fa_handle** out);
 FA_API int fa_destroy(fa_handle* h);
 FA_API const char* fa_last_error(const fa_handle* h);
+/* The configuration the handle was created with (spectrum rows hold fft_size / 2 values, level 11 rows 264 doubles, ...). */
+FA_API int fa_get_config(const fa_handle* h, fa_config* out);
 
 /* Use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the handle's own. */
 FA_API int fa_set_stream(fa_handle* h, void* cuda_stream);
@@ -213,9 +216,13 @@ FA_API int fa_stream_fixups(fa_handle* h, int stage);
 FA_API int fa_num_utterances(const fa_handle* h);
 FA_API int fa_result_counts(fa_handle* h, int64_t utt_id, fa_counts* out);
 FA_API int fa_total_counts(fa_handle* h, fa_counts* out);
+/* The fa_counts of every utterance of the batch, in submission order, in one call (a 100 k-utterance shard needs the rows per
+ * utterance to key its dense feature table); returns the number of entries written. */
+FA_API int fa_copy_counts_table(fa_handle* h, fa_counts* dst, size_t cap);
 
 /* Caller-allocated destinations; `cap` counts elements of the destination type's row
- * (rows for tables).  Return value: rows written (>= 0) or an fa_status (< 0). */
+ * (rows for tables).  Return value: rows written (>= 0) or an fa_status (< 0).  utt_id FA_ALL_UTTS returns the whole batch --
+ * and FA_ERR_CAPACITY if ANY utterance of the batch overflowed an internal table (fa_counts.overflow; its tables are partial). */
 FA_API int fa_copy_spectrum(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows);      /* rows of fft_size/2 dB values */
 FA_API int fa_copy_frames(fa_handle* h, int64_t utt_id, uint32_t* dst, size_t cap_rows);     /* rows of `bands` uint32 */
 FA_API int fa_copy_segments(fa_handle* h, int64_t utt_id, fa_segment* dst, size_t cap_rows);
@@ -260,9 +267,15 @@ FA_API int fa_hop_samples(const fa_config* cfg, int sample_rate);
 FA_API int fa_frames_for(const fa_config* cfg, int sample_rate, size_t n_samples);
 FA_API int fa_spec_bands(const fa_config* cfg);
 
-/* Synthetic "glottal pulse through formant resonators" speech; host code,
- * deterministic in (seed, utt_index).  Used by bench.py and the tests to build workloads. */
-FA_API int fa_synth_speech(float* dst, size_t n_samples, int sample_rate, uint64_t seed, uint64_t utt_index);
+/* Page-locked host memory for callers that want the zero-copy paths (fa_submit_pcm*_batch, fa_set_spectrum_sink) without a
+ * CUDA runtime of their own.  write_combined != 0: cudaHostAllocWriteCombined -- for buffers the host only WRITES (PCM on its
+ * way to the device): not snooped during the PCIe transfer, very slow to read back on the host.  Portable across devices. */
+FA_API void* fa_host_alloc(size_t bytes, int write_combined);
+FA_API void fa_host_free(void* p);
+/* Time `reps` back-to-back copies of `bytes` between `host` (page-locked) and a scratch buffer on `device` with CUDA events:
+ * direction 0 = host to device, 1 = device to host.  The PCIe / host-memory floor of an end-to-end step, measured with the
+ * caller's own buffer (bench.py runs it on all ranks at once). */
+FA_API int fa_pcie_probe(int device, void* host, size_t bytes, int reps, int direction, float* ms_per_copy);
 
 #ifdef __cplusplus
 }

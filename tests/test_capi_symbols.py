@@ -28,6 +28,23 @@ def test_library_exports_every_declared_symbol():
     assert L.fa_abi_version() == 1
 
 
+def test_synth_library_is_separate_from_the_product():
+    """The workload generator lives in its own host library: a process that only generates a workload (bench.py's CPU arm)
+    does not map libfa_b200.so."""
+    txt = open(os.path.join(ROOT, "include", "fa_synth.h")).read()
+    syms = re.findall(r"^FA_SYNTH_API\s+[\w\s\*]+?\b(fa_[a-z0-9_]+)\(", txt, flags=re.M)
+    assert sorted(syms) == sorted(_capi.SYNTH_EXPORTS)
+    S = _capi.synth_lib()
+    for s in syms:
+        assert hasattr(S, s), s
+    assert not any(hasattr(_capi.lib(), s) for s in syms)
+    from webspeechanalyzer_b200 import synth_speech, synth_speech_i16_batch
+    a = synth_speech_i16_batch(np.zeros(3 * 8000, np.int16), 3, 8000, 16000, 5, 10, 2, threads=2).reshape(3, 8000)
+    for i in range(3):
+        ref = np.clip(np.rint(synth_speech(8000, 16000, 5, 10 + 2 * i).astype(np.float64) * 32768.0), -32768, 32767)
+        assert np.array_equal(a[i], ref.astype(np.int16))
+
+
 def test_struct_layouts_match_the_header():
     assert C.sizeof(FaSegment) == 48 and C.sizeof(FaSyllable) == 16 and C.sizeof(FaCounts) == 48
     assert C.sizeof(FaConfig) == 6 * 4 + 10 * 8 + 4 * 4 + 4 * 8

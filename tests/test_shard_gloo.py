@@ -17,21 +17,27 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_utt, q):
+def _worker(rank, world, port, n_utt, q, level=13):
     import torch.distributed as dist
 
     from oracle import oracle
     from webspeechanalyzer_b200 import FaConfig, synth_speech
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    cfg = FaConfig.default(output_level=13)
+    host_group = dist.new_group(backend="gloo")     # what an NCCL job uses for the host-side gather
+    cfg = FaConfig.default(output_level=level)
     mine = shard.shard_indices(n_utt, rank, world)
     rows = []
     for u in mine:
         _, an = oracle.analyze_pcm(cfg, synth_speech(3 * 16000, 16000, 5, int(u)), 16000)
-        rows.append(an.features)
-    keys, r = shard.pack_rows(mine, rows)
-    out = shard.gather_rows(keys, r, dst=0)
+        rows.append(an.utterance if level == 11 else an.features)
+    width = 264 if level == 11 else 53
+    # the dense layout of Engine.result(None): rows of the shard's utterances back to back + rows per utterance
+    dense = np.concatenate(rows) if rows else np.zeros((0, width))
+    keys = shard.keys_from_counts(mine, [len(x) for x in rows])
+    k2, r2 = shard.pack_rows(mine, rows, width)
+    assert np.array_equal(keys, k2) and np.array_equal(dense, r2, equal_nan=True)
+    out = shard.gather_rows(keys, dense, dst=0, group=host_group)
     if rank == 0:
         q.put((out[0], out[1]))
     else:
@@ -48,21 +54,27 @@ def test_shard_indices_partition():
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
 
 
-def test_two_rank_gather_equals_single_process():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("level", [13, 11])
+def test_two_rank_gather_equals_single_process(level):
     from oracle import oracle
     from webspeechanalyzer_b200 import FaConfig, synth_speech
     n_utt = 5
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_utt, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_utt, q, level)) for r in range(2)]
     for p in procs:
         p.start()
     keys, rows = q.get(timeout=300)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    cfg = FaConfig.default(output_level=13)
-    ref = [oracle.analyze_pcm(cfg, synth_speech(3 * 16000, 16000, 5, u), 16000)[1].features for u in range(n_utt)]
-    k2, r2 = shard.pack_rows(range(n_utt), ref)
+    cfg = FaConfig.default(output_level=level)
+    ans = [oracle.analyze_pcm(cfg, synth_speech(3 * 16000, 16000, 5, u), 16000)[1] for u in range(n_utt)]
+    ref = [a.utterance if level == 11 else a.features for a in ans]
+    k2, r2 = shard.pack_rows(range(n_utt), ref, 264 if level == 11 else 53)
+    assert rows.shape[1] == (264 if level == 11 else 53) and len(rows) > 0
     assert np.array_equal(keys, k2) and np.array_equal(rows, r2, equal_nan=True)

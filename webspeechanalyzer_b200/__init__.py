@@ -8,4 +8,4 @@ and fails loudly if libfa_b200.so is missing (there is no CPU fallback).
 from ._ctypes_defs import FaConfig, FaCounts, FaSegment, FaSyllable, N_FEATURES  # noqa: F401
 from .api import (LaunchAudioNodes, LaunchError, StopAudioNodes, configure,  # noqa: F401
                   set_predicted_label_for_segment)
-from .engine import Engine, synth_speech  # noqa: F401
+from .engine import Engine, PinnedBuffer, synth_speech, synth_speech_i16_batch  # noqa: F401

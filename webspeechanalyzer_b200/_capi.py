@@ -19,14 +19,15 @@ FA_ERR_CAPACITY, FA_ERR_OUT_OF_MEMORY, FA_ERR_BUSY, FA_ERR_UNSUPPORTED = -6, -7,
 
 # every symbol include/fa_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
-    "fa_config_default", "fa_abi_version", "fa_status_string", "fa_create", "fa_destroy", "fa_last_error",
+    "fa_config_default", "fa_abi_version", "fa_status_string", "fa_create", "fa_destroy", "fa_last_error", "fa_get_config",
     "fa_set_stream", "fa_set_d2h_stream", "fa_set_pipeline", "fa_set_spectrum_sink", "fa_reset", "fa_submit_pcm", "fa_submit_pcm_i16", "fa_submit_pcm_batch", "fa_submit_pcm_i16_batch", "fa_submit_frames", "fa_run", "fa_sync", "fa_upload",
     "fa_run_resident", "fa_download", "fa_stage_times", "fa_launch_count", "fa_stream_fixups", "fa_num_utterances", "fa_result_counts",
-    "fa_total_counts", "fa_copy_spectrum", "fa_copy_frames", "fa_copy_segments", "fa_copy_formants", "fa_copy_energy",
+    "fa_total_counts", "fa_copy_counts_table", "fa_pcie_probe", "fa_copy_spectrum", "fa_copy_frames", "fa_copy_segments", "fa_copy_formants", "fa_copy_energy",
     "fa_copy_syllables", "fa_copy_features", "fa_copy_utterance_features", "fa_mlp_create", "fa_mlp_destroy", "fa_mlp_last_error",
     "fa_mlp_classify", "fa_mlp_classify_features", "fa_copy_peak_candidates", "fa_copy_gsum", "fa_hop_samples", "fa_frames_for",
-    "fa_spec_bands", "fa_synth_speech",
+    "fa_spec_bands", "fa_host_alloc", "fa_host_free",
 ]
+SYNTH_EXPORTS = ["fa_synth_speech", "fa_synth_speech_i16_batch"]   # include/fa_synth.h -> libfa_synth.so (host-only generator)
 
 
 class FaError(RuntimeError):
@@ -57,6 +58,7 @@ def lib() -> C.CDLL:
     L.fa_create.argtypes = [cfgp, C.c_int, C.POINTER(H)]
     L.fa_destroy.argtypes = [H]
     L.fa_last_error.argtypes = [H]; L.fa_last_error.restype = C.c_char_p
+    L.fa_get_config.argtypes = [H, cfgp]
     L.fa_set_stream.argtypes = [H, C.c_void_p]
     L.fa_set_d2h_stream.argtypes = [H, C.c_void_p]
     L.fa_reset.argtypes = [H]
@@ -73,6 +75,8 @@ def lib() -> C.CDLL:
     L.fa_stage_times.argtypes = [H, C.POINTER(C.c_float)]
     L.fa_result_counts.argtypes = [H, C.c_int64, C.POINTER(FaCounts)]
     L.fa_total_counts.argtypes = [H, C.POINTER(FaCounts)]
+    L.fa_copy_counts_table.argtypes = [H, C.c_void_p, C.c_size_t]
+    L.fa_pcie_probe.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_float)]
     for n in ("fa_copy_gsum", "fa_copy_spectrum", "fa_copy_frames", "fa_copy_segments", "fa_copy_formants", "fa_copy_energy",
               "fa_copy_syllables", "fa_copy_features", "fa_copy_utterance_features"):
         getattr(L, n).argtypes = [H, C.c_int64, C.c_void_p, C.c_size_t]
@@ -85,6 +89,25 @@ def lib() -> C.CDLL:
     L.fa_hop_samples.argtypes = [cfgp, C.c_int]
     L.fa_frames_for.argtypes = [cfgp, C.c_int, C.c_size_t]
     L.fa_spec_bands.argtypes = [cfgp]
-    L.fa_synth_speech.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_uint64]
+    L.fa_host_alloc.argtypes = [C.c_size_t, C.c_int]; L.fa_host_alloc.restype = C.c_void_p
+    L.fa_host_free.argtypes = [C.c_void_p]; L.fa_host_free.restype = None
     _lib = L
     return L
+
+
+_synth = None
+SYNTH_LIB_PATH = os.path.join(_HERE, "libfa_synth.so")
+
+
+def synth_lib() -> C.CDLL:
+    """The host-only workload generator (csrc/fa_synth.cpp); a separate library, so that generating a workload -- e.g. for a
+    CPU baseline -- never maps the CUDA library."""
+    global _synth
+    if _synth is None:
+        if not os.path.exists(SYNTH_LIB_PATH):
+            raise ImportError(f"{SYNTH_LIB_PATH} is missing: build it with `python -m webspeechanalyzer_b200.build`")
+        S = C.CDLL(SYNTH_LIB_PATH)
+        S.fa_synth_speech.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_uint64]
+        S.fa_synth_speech_i16_batch.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]
+        _synth = S
+    return _synth

@@ -14,13 +14,24 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfa_b200.so")
-SOURCES = ["fa_spectrum.cu", "fa_peaks.cu", "fa_segment.cu", "fa_features.cu", "fa_utterance.cu", "fa_mlp.cu", "fa_capi.cu", "fa_synth.cpp"]
+SYNTH_LIB = os.path.join(HERE, "libfa_synth.so")   # host-only workload generator (bench / tests), not part of the product
+SOURCES = ["fa_spectrum.cu", "fa_peaks.cu", "fa_segment.cu", "fa_features.cu", "fa_utterance.cu", "fa_mlp.cu", "fa_capi.cu"]
 HEADERS = [os.path.join(CSRC, "fa_internal.cuh")] + [os.path.join(ROOT, "include", h)
                                                       for h in ("fa_b200.h", "fa_jsmath.h", "fa_tables.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "-diag-suppress", "39,222",
          "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+
+
+def build_synth(force: bool = False) -> str:
+    src, hdr = os.path.join(CSRC, "fa_synth.cpp"), os.path.join(ROOT, "include", "fa_synth.h")
+    if not force and os.path.exists(SYNTH_LIB) and os.path.getmtime(SYNTH_LIB) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return SYNTH_LIB
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-fopenmp", "-fvisibility=hidden", "-I",
+                           os.path.join(ROOT, "include"), "-o", SYNTH_LIB + ".tmp", src])
+    os.replace(SYNTH_LIB + ".tmp", SYNTH_LIB)
+    return SYNTH_LIB
 
 
 def needs_build() -> bool:
@@ -32,6 +43,7 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    build_synth(force)
     if not force and not needs_build():
         return LIB
     objdir = os.path.join(HERE, "build")

@@ -368,6 +368,48 @@ int fa_destroy(fa_handle* h) {
 
 const char* fa_last_error(const fa_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
+void* fa_host_alloc(size_t bytes, int write_combined) {
+  void* p = nullptr;
+  const unsigned flags = cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0u);
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, flags) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void fa_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int fa_pcie_probe(int device, void* host, size_t bytes, int reps, int direction, float* ms_per_copy) {
+  if (!host || !bytes || reps <= 0 || !ms_per_copy || direction < 0 || direction > 1) return FA_ERR_INVALID_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return FA_ERR_NO_DEVICE;
+  void* d = nullptr;
+  cudaStream_t s = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = FA_OK;
+  if (cudaMalloc(&d, bytes) != cudaSuccess) { cudaGetLastError(); return FA_ERR_OUT_OF_MEMORY; }
+  if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&e0) != cudaSuccess ||
+      cudaEventCreate(&e1) != cudaSuccess) rc = FA_ERR_CUDA;
+  if (rc == FA_OK) {
+    const cudaMemcpyKind kind = direction == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    cudaMemcpyAsync(direction == 0 ? d : host, direction == 0 ? host : d, bytes, kind, s);   // warm-up
+    cudaEventRecord(e0, s);
+    for (int i = 0; i < reps; i++) cudaMemcpyAsync(direction == 0 ? d : host, direction == 0 ? host : d, bytes, kind, s);
+    cudaEventRecord(e1, s);
+    float ms = 0.f;
+    if (cudaStreamSynchronize(s) != cudaSuccess || cudaEventElapsedTime(&ms, e0, e1) != cudaSuccess) rc = FA_ERR_CUDA;
+    *ms_per_copy = ms / (float)reps;
+  }
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (s) cudaStreamDestroy(s);
+  cudaFree(d);
+  if (rc != FA_OK) cudaGetLastError();
+  return rc;
+}
+
+int fa_get_config(const fa_handle* h, fa_config* out) {
+  if (!h || !out) return FA_ERR_INVALID_ARG;
+  *out = h->cfg;
+  return FA_OK;
+}
+
 int fa_set_stream(fa_handle* h, void* s) {
   if (!h) return FA_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
@@ -414,6 +456,7 @@ int fa_reset(fa_handle* h) {
 }
 
 static int add_utt(fa_handle* h, int64_t utt_id, int region, long long off, size_t n, int sr) {
+  if (utt_id < 0) return fail(h, FA_ERR_INVALID_ARG, "utterance ids must be >= 0 (FA_ALL_UTTS = -1 names the whole batch)");
   if (h->index.count(utt_id)) return fail(h, FA_ERR_INVALID_ARG, "duplicate utterance id");
   Utt u;
   u.id = utt_id; u.region = region; u.off = off; u.n = (long long)n;
@@ -438,6 +481,7 @@ static int submit_check(fa_handle* h, int sr) {
 static int submit_common(fa_handle* h, int64_t utt_id, size_t n, int sr, float** dst) {
   int rc = submit_check(h, sr);
   if (rc != FA_OK) return rc;
+  if (utt_id < 0) return fail(h, FA_ERR_INVALID_ARG, "utterance ids must be >= 0 (FA_ALL_UTTS = -1 names the whole batch)");
   if (h->index.count(utt_id)) return fail(h, FA_ERR_INVALID_ARG, "duplicate utterance id");
   const long long off = h->staged;
   const long long padded = ((long long)n + 3) & ~3ll;
@@ -474,6 +518,7 @@ int fa_submit_pcm_batch(fa_handle* h, int64_t first_utt_id, const float* pcm, co
   if (!pcm || !offsets || n_utt <= 0) return fail(h, FA_ERR_INVALID_ARG, "Invalid audio source");
   for (int i = 0; i < n_utt; i++)
     if (offsets[i + 1] < offsets[i] || offsets[0] < 0) return fail(h, FA_ERR_INVALID_ARG, "offsets must be non-decreasing");
+  if (first_utt_id < 0) return fail(h, FA_ERR_INVALID_ARG, "utterance ids must be >= 0 (FA_ALL_UTTS = -1 names the whole batch)");
   for (int i = 0; i < n_utt; i++)
     if (h->index.count(first_utt_id + i)) return fail(h, FA_ERR_INVALID_ARG, "duplicate utterance id");
   cudaPointerAttributes attr;
@@ -507,6 +552,7 @@ int fa_submit_pcm_i16_batch(fa_handle* h, int64_t first_utt_id, const int16_t* p
   if (!pcm || !offsets || n_utt <= 0) return fail(h, FA_ERR_INVALID_ARG, "Invalid audio source");
   for (int i = 0; i < n_utt; i++)
     if (offsets[i + 1] < offsets[i] || offsets[0] < 0) return fail(h, FA_ERR_INVALID_ARG, "offsets must be non-decreasing");
+  if (first_utt_id < 0) return fail(h, FA_ERR_INVALID_ARG, "utterance ids must be >= 0 (FA_ALL_UTTS = -1 names the whole batch)");
   for (int i = 0; i < n_utt; i++)
     if (h->index.count(first_utt_id + i)) return fail(h, FA_ERR_INVALID_ARG, "duplicate utterance id");
   cudaPointerAttributes attr;
@@ -544,6 +590,7 @@ int fa_submit_frames(fa_handle* h, int64_t utt_id, const uint32_t* frames, size_
   if (bands != B) return fail(h, FA_ERR_INVALID_ARG, "Error: bins num mismatch");   // spectrum_push's own check @B30392
   if (!frames && n_frames) return fail(h, FA_ERR_INVALID_ARG, "Invalid audio source");
   if (n_frames > (size_t)INT32_MAX) return fail(h, FA_ERR_CAPACITY, "too many frames");
+  if (utt_id < 0) return fail(h, FA_ERR_INVALID_ARG, "utterance ids must be >= 0 (FA_ALL_UTTS = -1 names the whole batch)");
   if (h->index.count(utt_id)) return fail(h, FA_ERR_INVALID_ARG, "duplicate utterance id");
   if (h->sample_rate <= 0) h->sample_rate = 16000;   // only sizes the (unused) spectrum tables
   const size_t row = (size_t)B * sizeof(uint32_t);
@@ -1182,6 +1229,16 @@ static int need_results(fa_handle* h) {
   return FA_OK;
 }
 
+// whole-batch results are only handed out when no utterance overflowed an internal table (their tables are partial)
+static int batch_overflow(fa_handle* h) {
+  if (h->cfg.output_level < 3) return 0;
+  const int n = (int)h->utts.size();
+  const int* k = h->h_counts.as<int>() + 5 * (size_t)n;
+  int bad = 0;
+  for (int i = 0; i < n; i++) bad += k[i] != 0;
+  return bad;
+}
+
 static void fill_counts(fa_handle* h, int i, fa_counts* c) {
   const Utt& u = h->utts[i];
   const int n = (int)h->utts.size();
@@ -1217,7 +1274,17 @@ int fa_total_counts(fa_handle* h, fa_counts* out) {
     out->stored_segments += c.stored_segments; out->formant_rows += c.formant_rows; out->syllables += c.syllables;
     out->feature_rows += c.feature_rows; out->overflow += c.overflow;
   }
-  return FA_OK;
+  return out->overflow ? fail(h, FA_ERR_CAPACITY, "an internal table overflowed for at least one utterance of the batch") : FA_OK;
+}
+
+int fa_copy_counts_table(fa_handle* h, fa_counts* dst, size_t cap) {
+  int rc = need_results(h);
+  if (rc != FA_OK) return rc;
+  const size_t n = h->utts.size();
+  if (n > cap) return fail(h, FA_ERR_CAPACITY, "destination too small");
+  if (n && !dst) return FA_ERR_INVALID_ARG;
+  for (size_t i = 0; i < n; i++) fill_counts(h, (int)i, dst + i);
+  return (int)n;
 }
 
 // rows of utterance `utt_id` (or of the whole batch when utt_id < 0) from a device table with a fixed row size
@@ -1264,7 +1331,7 @@ static int copy_dense(fa_handle* h, int64_t utt_id, int kind, const void* host, 
     const int i = (int)(u - h->utts.data());
     if (h->h_counts.as<int>()[5 * n + i]) return fail(h, FA_ERR_CAPACITY, "an internal table overflowed for this utterance");
     r0 = off[i]; nr = off[i + 1] - off[i];
-  }
+  } else if (batch_overflow(h)) return fail(h, FA_ERR_CAPACITY, "an internal table overflowed for at least one utterance of the batch");
   if ((size_t)nr > cap_rows) return fail(h, FA_ERR_CAPACITY, "destination too small");
   if (nr && !dst) return FA_ERR_INVALID_ARG;
   if (nr) memcpy(dst, (const char*)host + (size_t)r0 * row_bytes, (size_t)nr * row_bytes);
@@ -1306,6 +1373,7 @@ int fa_mlp_classify_features(fa_mlp* m, fa_handle* h, int64_t utt_id, float* pro
   if (lvl != FA_LEVEL_SEG_FEATURES && lvl != FA_LEVEL_SYL_FEATURES && lvl != FA_LEVEL_UTTERANCE)
     return fail(h, FA_ERR_INVALID_ARG, "no feature rows at this output_level");
   if (fa_mlp_in_dim(m) != h->feat_width()) return fail(h, FA_ERR_INVALID_ARG, "model input width != feature row width");
+  if (fa_mlp_device(m) != h->device) return fail(h, FA_ERR_INVALID_ARG, "the model and the handle live on different devices");
   int rc = need_results(h);
   if (rc != FA_OK) return rc;
   const int n = (int)h->utts.size();
@@ -1315,8 +1383,9 @@ int fa_mlp_classify_features(fa_mlp* m, fa_handle* h, int64_t utt_id, float* pro
     Utt* u = find_utt(h, utt_id);
     if (!u) return fail(h, FA_ERR_UNKNOWN_UTT, "unknown utterance id");
     const int i = (int)(u - h->utts.data());
+    if (h->h_counts.as<int>()[5 * n + i]) return fail(h, FA_ERR_CAPACITY, "an internal table overflowed for this utterance");
     r0 = off[i]; nr = off[i + 1] - off[i];
-  }
+  } else if (batch_overflow(h)) return fail(h, FA_ERR_CAPACITY, "an internal table overflowed for at least one utterance of the batch");
   if ((size_t)nr > cap_rows) return fail(h, FA_ERR_CAPACITY, "destination too small");
   if (nr == 0) return 0;
   if (!probs) return FA_ERR_INVALID_ARG;

@@ -204,6 +204,7 @@ cudaError_t fa_launch_segment(const FaSegmentParams& p, cudaStream_t s, int* lau
 cudaError_t fa_launch_features(const FaFeatureParams& p, cudaStream_t s, int* launches);
 int fa_mlp_run_device(fa_mlp* m, const double* d_rows, int n_rows, float* probs_host, cudaStream_t s);
 int fa_mlp_in_dim(const fa_mlp* m);
+int fa_mlp_device(const fa_mlp* m);
 int fa_mlp_out_dim(const fa_mlp* m);
 cudaError_t fa_launch_utterance(const FaUtteranceParams& p, cudaStream_t s, int* launches);
 cudaError_t fa_launch_prefix(const FaGatherArgs& a, cudaStream_t s, int* launches);

@@ -251,4 +251,5 @@ int fa_mlp_run_device(fa_mlp* m, const double* d_rows, int n_rows, float* probs_
 }
 
 int fa_mlp_in_dim(const fa_mlp* m) { return m->dims[0]; }
+int fa_mlp_device(const fa_mlp* m) { return m->device; }
 int fa_mlp_out_dim(const fa_mlp* m) { return m->dims[m->n_layers]; }

@@ -8,11 +8,13 @@
 // by U(30,80) ms gaps, phrases of 3-8 syllables separated by U(250,600) ms silences; white noise at
 // -50 dBFS; peak-normalised to 0.3.  Deterministic in (seed, utt_index); no reference counterpart
 // (the reference ships one demo WAV and no generator).
+// Built as its own small host library (libfa_synth.so): workload generation is not part of the product library, so a process
+// that only times a CPU baseline never maps libfa_b200.so.
 #include <cmath>
 #include <cstdint>
 #include <vector>
 
-#include "fa_b200.h"
+#include "fa_synth.h"
 
 namespace {
 
@@ -55,7 +57,7 @@ double rosenberg(double ph) {
 }  // namespace
 
 extern "C" int fa_synth_speech(float* dst, size_t n, int sr, uint64_t seed, uint64_t utt) {
-  if (!dst || sr < 4000) return FA_ERR_INVALID_ARG;
+  if (!dst || sr < 4000) return -1;
   Rng rng(0x5EEDull ^ seed ^ (utt * 0xD1B54A32D192ED03ull));
   std::vector<double> x(n, 0.0);
   const double nyq = 0.5 * sr;
@@ -96,5 +98,25 @@ extern "C" int fa_synth_speech(float* dst, size_t n, int sr, uint64_t seed, uint
   for (size_t i = 0; i < n; i++) peak = std::fmax(peak, std::fabs(x[i]));
   const double scale = 0.3 / peak, noise = std::pow(10.0, -50.0 / 20.0) * std::sqrt(3.0);  // uniform noise, rms -50 dBFS
   for (size_t i = 0; i < n; i++) dst[i] = (float)(x[i] * scale + noise * (2.0 * rng.uni() - 1.0));
-  return FA_OK;
+  return 0;
+}
+
+// A whole batch as 16-bit PCM (what a WAV file holds): utterance i = index first_index + i * index_stride, n samples each,
+// written back to back; rint(x * 32768) clipped.  OpenMP over utterances.
+extern "C" int fa_synth_speech_i16_batch(int16_t* dst, int n_utt, size_t n, int sr, uint64_t seed, uint64_t first_index,
+                                         uint64_t index_stride, int threads) {
+  if (!dst || n_utt < 0 || sr < 4000) return -1;
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 4) num_threads(threads > 0 ? threads : 1) reduction(+ : bad)
+  for (int i = 0; i < n_utt; i++) {
+    std::vector<float> x(n);
+    if (fa_synth_speech(x.data(), n, sr, seed, first_index + (uint64_t)i * index_stride) != 0) { bad++; continue; }
+    int16_t* o = dst + (size_t)i * n;
+    for (size_t k = 0; k < n; k++) {
+      double v = std::nearbyint((double)x[k] * 32768.0);
+      v = v < -32768.0 ? -32768.0 : v > 32767.0 ? 32767.0 : v;
+      o[k] = (int16_t)v;
+    }
+  }
+  return bad ? -1 : 0;
 }

@@ -14,6 +14,9 @@ SEG_DTYPE = np.dtype([("start", "<i4"), ("len", "<i4"), ("stored", "<i4"), ("n_s
                       ("first_syllable", "<i4"), ("row_offset", "<i4"), ("ymax", "<f8"), ("vmin", "<f8"),
                       ("cs_ratio", "<f8")])
 SYL_DTYPE = np.dtype([("stored_seg", "<i4"), ("start", "<i4"), ("len", "<i4"), ("reserved", "<i4")])
+COUNTS_DTYPE = np.dtype([("samples", "<i8"), ("sample_rate", "<i4"), ("hop", "<i4"), ("frames", "<i4"), ("bands", "<i4"),
+                         ("segments", "<i4"), ("stored_segments", "<i4"), ("formant_rows", "<i4"), ("syllables", "<i4"),
+                         ("feature_rows", "<i4"), ("overflow", "<i4")])
 
 
 @dataclass
@@ -34,10 +37,43 @@ class UtteranceResult:
 def synth_speech(n_samples: int, sample_rate: int, seed: int, utt_index: int) -> np.ndarray:
     """Synthetic glottal-pulse speech (csrc/fa_synth.cpp); host code, needs no GPU."""
     out = np.empty(n_samples, np.float32)
-    rc = _capi.lib().fa_synth_speech(out.ctypes.data, n_samples, sample_rate, seed, utt_index)
+    rc = _capi.synth_lib().fa_synth_speech(out.ctypes.data, n_samples, sample_rate, seed, utt_index)
     if rc != 0:
         raise FaError(rc, "fa_synth_speech")
     return out
+
+
+def synth_speech_i16_batch(dst: np.ndarray, n_utt: int, n_samples: int, sample_rate: int, seed: int, first_index: int,
+                           index_stride: int = 1, threads: int = 1) -> np.ndarray:
+    """n_utt utterances of 16-bit PCM written back to back into `dst` (int16, at least n_utt * n_samples; may be page-locked
+    caller memory); utterance i carries index first_index + i * index_stride.  OpenMP over utterances, host code."""
+    assert dst.dtype == np.int16 and dst.flags.c_contiguous and dst.size >= n_utt * n_samples
+    rc = _capi.synth_lib().fa_synth_speech_i16_batch(dst.ctypes.data, n_utt, n_samples, sample_rate, seed, first_index,
+                                                     index_stride, threads)
+    if rc != 0:
+        raise FaError(rc, "fa_synth_speech_i16_batch")
+    return dst
+
+
+class PinnedBuffer:
+    """Page-locked host memory from the C-ABI (fa_host_alloc), as a numpy array; write_combined for H2D-only buffers."""
+
+    def __init__(self, shape, dtype, write_combined: bool = False):
+        self._lib = _capi.lib()
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape))
+        self._p = self._lib.fa_host_alloc(max(1, n * dt.itemsize), 1 if write_combined else 0)
+        if not self._p:
+            raise MemoryError("fa_host_alloc failed")
+        self.array = np.ctypeslib.as_array((C.c_byte * (n * dt.itemsize)).from_address(self._p)).view(dt).reshape(shape)
+
+    def free(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            self._lib.fa_host_free(C.c_void_p(self._p))
+            self._p = None
+
+    __del__ = free
 
 
 class Engine:
@@ -52,6 +88,8 @@ class Engine:
             self._h = C.c_void_p()
             raise FaError(rc, self._lib.fa_status_string(rc).decode())
         self.device = device
+        self._keep = []      # zero-copy buffers of the batch in flight (page-locked caller memory must outlive fa_sync)
+        self._sink = None
 
     # -- lifetime --
     def close(self):
@@ -82,7 +120,8 @@ class Engine:
         self._check(self._lib.fa_set_d2h_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
 
     def reset(self):
-        self._check(self._lib.fa_reset(self._h))
+        self._check(self._lib.fa_reset(self._h))   # waits for the stream: nothing reads the old batch's buffers any more
+        self._keep.clear()
 
     def submit(self, utt_id: int, pcm: np.ndarray, sample_rate: int) -> int:
         if pcm.dtype == np.int16:
@@ -101,7 +140,7 @@ class Engine:
         """Whole batch in one float32 buffer; zero-copy when `pcm` is page-locked (keep it alive until sync())."""
         assert pcm.dtype in (np.float32, np.int16) and pcm.flags.c_contiguous
         offsets = np.ascontiguousarray(offsets, np.int64)
-        self._keep = (pcm, offsets)
+        self._keep.append((pcm, offsets))
         if pcm.dtype == np.int16:      # crosses PCIe as int16 (half the bytes), converted on the device
             return self._check(self._lib.fa_submit_pcm_i16_batch(self._h, first_utt_id, pcm.ctypes.data, offsets.ctypes.data,
                                                                  offsets.size - 1, sample_rate))
@@ -125,6 +164,7 @@ class Engine:
 
     def sync(self):
         self._check(self._lib.fa_sync(self._h))
+        self._keep.clear()                          # the H2D copies of the batch are done
 
     def upload(self):
         self._check(self._lib.fa_upload(self._h))
@@ -168,6 +208,20 @@ class Engine:
         else:
             self._check(self._lib.fa_result_counts(self._h, utt_id, C.byref(c)))
         return {k: getattr(c, k) for k, _ in FaCounts._fields_}
+
+    def counts_table(self) -> np.ndarray:
+        """fa_counts of every utterance of the batch in submission order, as a structured array (one call)."""
+        n = self._lib.fa_num_utterances(self._h)
+        out = np.zeros(max(n, 0), COUNTS_DTYPE)
+        k = self._check(self._lib.fa_copy_counts_table(self._h, out.ctypes.data, out.size))
+        return out[:k]
+
+    def feature_table(self) -> np.ndarray:
+        """The dense feature rows of the whole batch ([rows, 53] or [rows, 264]), utterance after utterance."""
+        c = self.counts()
+        if self.cfg.output_level == 11:
+            return self._rows(self._lib.fa_copy_utterance_features, None, c["feature_rows"], (N_UTT_FEATURES,), np.float64)
+        return self._rows(self._lib.fa_copy_features, None, c["feature_rows"], (N_FEATURES,), np.float64)
 
     def _rows(self, fn, utt_id, nrows, shape_tail, dtype):
         out = np.empty((nrows,) + shape_tail, dtype)

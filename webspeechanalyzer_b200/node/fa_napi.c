@@ -41,9 +41,15 @@ static double get_num(napi_env env, napi_value obj, const char* key, double dflt
   return dflt;
 }
 
+/* the external wraps a box, so that destroyEngine can free the GPU memory at once and leave the finalizer nothing to do */
+typedef struct { fa_handle* h; } engine_box;
+
 static void finalize_engine(napi_env env, void* data, void* hint) {
   (void)env; (void)hint;
-  if (data) fa_destroy((fa_handle*)data);
+  engine_box* b = (engine_box*)data;
+  if (!b) return;
+  if (b->h) fa_destroy(b->h);
+  free(b);
 }
 
 /* createEngine(cfg, device): cfg uses formantanalyzer's field names (defaults @B2972) + the AnalyserNode extension */
@@ -88,13 +94,26 @@ static napi_value CreateEngine(napi_env env, napi_callback_info info) {
     napi_throw_error(env, NULL, rc == FA_ERR_INVALID_ARG ? "Invalid reset_nodes config" : fa_status_string(rc));
     return NULL;
   }
-  CHECK(napi_create_external(env, h, finalize_engine, NULL, &out));
+  engine_box* box = (engine_box*)malloc(sizeof(engine_box));
+  if (!box) { fa_destroy(h); napi_throw_error(env, NULL, "out of memory"); return NULL; }
+  box->h = h;
+  if (napi_create_external(env, box, finalize_engine, NULL, &out) != napi_ok) {
+    fa_destroy(h); free(box);
+    napi_throw_error(env, NULL, "N-API call failed: napi_create_external");
+    return NULL;
+  }
   return out;
 }
 
+/* destroyEngine(handle): release the handle's device and pinned memory now (StopAudioNodes / a new configuration) */
 static napi_value DestroyEngine(napi_env env, napi_callback_info info) {
-  (void)env; (void)info;
-  /* the external's finalizer frees the handle; explicit destruction is a no-op kept for API symmetry */
+  size_t argc = 1;
+  napi_value argv[1];
+  void* bp = NULL;
+  if (napi_get_cb_info(env, info, &argc, argv, NULL, NULL) != napi_ok || argc < 1) return NULL;
+  if (napi_get_value_external(env, argv[0], &bp) != napi_ok || !bp) return NULL;
+  engine_box* b = (engine_box*)bp;
+  if (b->h) { fa_destroy(b->h); b->h = NULL; }   /* the finalizer only frees the box afterwards */
   return NULL;
 }
 
@@ -127,22 +146,31 @@ static void job_execute(napi_env env, void* data) {
   if (rc == FA_OK) rc = fa_result_counts(h, 0, &j->counts);
   if (rc == FA_OK) {
     const fa_counts* c = &j->counts;
+    /* row widths come from the handle's own configuration, never from what the caller said */
+    fa_config cfg;
+    fa_get_config(h, &cfg);
+    j->fft_half = cfg.fft_size / 2;
+    j->feat_width = cfg.output_level == FA_LEVEL_UTTERANCE ? FA_N_UTT_FEATURES : FA_N_FEATURES;
+    j->want_spec = j->want_spec && !j->is_frames && (cfg.want_spectrum || cfg.output_level <= 2);
     j->segs = (fa_segment*)malloc(sizeof(fa_segment) * (size_t)(c->segments + 1));
     j->syls = (fa_syllable*)malloc(sizeof(fa_syllable) * (size_t)(c->syllables + 1));
     j->formants = (float*)malloc(sizeof(float) * 9 * (size_t)(c->formant_rows + 1));
     j->energy = (float*)malloc(sizeof(float) * 3 * (size_t)(c->formant_rows + 1));
     /* level 11 rows are the 264-dim utterance distributions (cumulative, one per stored segment) */
     j->features = (double*)malloc(sizeof(double) * (size_t)j->feat_width * (size_t)(c->feature_rows + 1));
+    if (j->want_spec) j->spectrum = (float*)malloc(sizeof(float) * (size_t)j->fft_half * (size_t)(c->frames + 1));
+    if (!j->segs || !j->syls || !j->formants || !j->energy || !j->features || (j->want_spec && !j->spectrum)) {
+      j->rc = FA_ERR_OUT_OF_MEMORY;
+      snprintf(j->err, sizeof(j->err), "out of memory");
+      return;
+    }
     rc = fa_copy_segments(h, 0, j->segs, (size_t)c->segments);
     if (rc >= 0) rc = fa_copy_syllables(h, 0, j->syls, (size_t)c->syllables);
     if (rc >= 0) rc = fa_copy_formants(h, 0, j->formants, (size_t)c->formant_rows);
     if (rc >= 0) rc = fa_copy_energy(h, 0, j->energy, (size_t)c->formant_rows);
     if (rc >= 0) rc = j->feat_width == FA_N_UTT_FEATURES ? fa_copy_utterance_features(h, 0, j->features, (size_t)c->feature_rows)
                                                          : fa_copy_features(h, 0, j->features, (size_t)c->feature_rows);
-    if (rc >= 0 && j->want_spec) {
-      j->spectrum = (float*)malloc(sizeof(float) * (size_t)j->fft_half * (size_t)(c->frames + 1));
-      rc = fa_copy_spectrum(h, 0, j->spectrum, (size_t)c->frames);
-    }
+    if (rc >= 0 && j->want_spec) rc = fa_copy_spectrum(h, 0, j->spectrum, (size_t)c->frames);
     if (rc >= 0) rc = FA_OK;
   }
   j->rc = rc;
@@ -222,12 +250,13 @@ static napi_value Analyze(napi_env env, napi_callback_info info) {
   CHECK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
   if (argc < 3) { napi_throw_error(env, NULL, "Invalid audio source"); return NULL; }
   job_t* j = (job_t*)calloc(1, sizeof(job_t));
+  if (!j) { napi_throw_error(env, NULL, "out of memory"); return NULL; }
   void* hp = NULL;
   napi_typedarray_type tt;
   void* pdata = NULL;
   size_t len = 0;
   bool is_ta = false;
-  if (napi_get_value_external(env, argv[0], &hp) != napi_ok || !hp || napi_is_typedarray(env, argv[1], &is_ta) != napi_ok || !is_ta ||
+  if (napi_get_value_external(env, argv[0], &hp) != napi_ok || !hp || !((engine_box*)hp)->h || napi_is_typedarray(env, argv[1], &is_ta) != napi_ok || !is_ta ||
       napi_get_typedarray_info(env, argv[1], &tt, &len, &pdata, NULL, NULL) != napi_ok ||
       (tt != napi_float32_array && tt != napi_uint32_array)) {
     free(j);
@@ -240,7 +269,7 @@ static napi_value Analyze(napi_env env, napi_callback_info info) {
   if (argc >= 5) napi_get_value_int32(env, argv[4], &fft);
   int32_t level = 0;
   if (argc >= 6) napi_get_value_int32(env, argv[5], &level);
-  j->h = (fa_handle*)hp; j->pcm = (const float*)pdata; j->n = len; j->sr = sr; j->want_spec = ws; j->fft_half = fft / 2;
+  j->h = ((engine_box*)hp)->h; j->pcm = (const float*)pdata; j->n = len; j->sr = sr; j->want_spec = ws; j->fft_half = fft / 2;
   j->feat_width = level == FA_LEVEL_UTTERANCE ? FA_N_UTT_FEATURES : FA_N_FEATURES;
   j->is_frames = tt == napi_uint32_array;   /* Uint32Array = the segmentor's own frames (spectrum_push); argv[2] = bands */
   CHECK(napi_create_reference(env, argv[1], 1, &j->pcm_ref)); /* keep the PCM alive while the pool thread reads it */

@@ -59,7 +59,10 @@ function decodeWav(buf) { // stand-in for decodeAudioData (@B18693); no resampli
     } else if (id === 'data') data = { off: pos + 8, size: Math.min(size, u8.length - pos - 8) };
     pos += 8 + size + (size & 1);
   }
-  if (!fmt || !data || fmt.ch < 1) throw 'Unable to decode audio data';
+  if (!fmt || !data || fmt.ch < 1 || fmt.sr < 1) throw 'Unable to decode audio data';
+  // linear PCM (1) and IEEE float (3) only: A-law / mu-law / ADPCM data must not be read as linear samples (wav.py: same rule)
+  if (fmt.tag !== 1 && fmt.tag !== 3) throw 'Unable to decode audio data';
+  if (fmt.tag === 3 && fmt.bits !== 32 && fmt.bits !== 64) throw 'Unable to decode audio data';
   const bps = fmt.bits / 8, n = Math.floor(data.size / (bps * fmt.ch)), out = new Float32Array(n);
   for (let i = 0; i < n; i++) {
     let acc = 0;
@@ -82,6 +85,7 @@ function decodeWav(buf) { // stand-in for decodeAudioData (@B18693); no resampli
 function engine() {
   const key = JSON.stringify(a);
   if (!state.engine || state.engineKey !== key) {
+    if (state.engine) native.destroyEngine(state.engine);   // frees the old handle's GPU memory now, not at the next GC
     state.engine = native.createEngine(Object.assign({}, a, { want_spectrum: a.output_level <= 2 ? 1 : 0 }), a.device | 0);
     state.engineKey = key;
   }

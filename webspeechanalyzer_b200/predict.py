@@ -65,8 +65,11 @@ def load_tfjs_model(model_dir: str, model_json: str = "model.json", meta_json: s
         dims.append(k.shape[1])
     nin = dims[0]
     ins = meta["inputs"]
-    in_min = np.array([ins[str(i)]["min"] for i in range(nin)], np.float64)
-    in_max = np.array([ins[str(i)]["max"] for i in range(nin)], np.float64)
+    if meta.get("isNormalized", True):
+        in_min = np.array([ins[str(i)]["min"] for i in range(nin)], np.float64)
+        in_max = np.array([ins[str(i)]["max"] for i in range(nin)], np.float64)
+    else:   # ml5 normalises a row only when the saved meta says the training data was (NeuralNetwork.classifyInternal)
+        in_min, in_max = np.zeros(nin, np.float64), np.ones(nin, np.float64)
     labels = None
     outs = meta.get("outputs") or {}
     for o in outs.values():
