@@ -59,6 +59,28 @@ C3_WORKLOAD = ("C3: synthetic 5 s 48 kHz utterances, Syllable Features (output_l
 C3_METRIC = "audio-sec/sec for 53-dim Syllable Features (sharded by utterance)"
 
 
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """NCCL (version banner), torchrun and friends write to fd 1: send all of that to stderr and keep the real stdout for the
+    ONE JSON line the driver parses."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def bench_config():
     from webspeechanalyzer_b200 import FaConfig
     return FaConfig.default(output_level=5, want_spectrum=1)
@@ -223,7 +245,7 @@ def run_reference(args):
                     "arm is the scalar -O2 C restatement (oracle/fa_oracle.c) with OpenMP -- a stated baseline, not the reference's "
                     "own JavaScript" if not js_found else
                     "a JS engine exists on this box: oracle/run_reference_modules.js can execute the reference's own modules here"}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 def c3_config():
@@ -323,36 +345,39 @@ def run_c3(args, world, rank, local):
         e.submit_batch(0, pcm.array, offs, C3_SR)      # zero copy: the H2D transfers read the pinned buffer
         e.run()                                        # asynchronous
 
-    def collect(j, group):
+    def collect(j, gather):
         e = engs[j]
         e.sync()
         ct = e.counts_table()
         feats = e.feature_table()
         d2h_seen.append(int(feats.nbytes + ct.nbytes))
         keys = shard.keys_from_counts(utt_ids, ct["feature_rows"])
-        out = shard.gather_rows(keys, feats, dst=0, group=group, sort=False)
+        if gather and world > 1:      # every rank takes part (host-side gloo group); the one-rank-alone pass must not
+            out = shard.gather_rows(keys, feats, dst=0, group=host_group, sort=False)
+        else:
+            out = (keys, feats)
         if out is not None:
             gathered["rows"], gathered["bytes"] = int(out[1].shape[0]), int(out[0].nbytes + out[1].nbytes)
 
-    def e2e_steps(k_steps, group):
+    def e2e_steps(k_steps, gather):
         inflight = []
         for k in range(k_steps):
             j = k % 2
             if len(inflight) == 2:
-                collect(inflight.pop(0), group)
+                collect(inflight.pop(0), gather)
             launch(j)
             inflight.append(j)
         while inflight:
-            collect(inflight.pop(0), group)
+            collect(inflight.pop(0), gather)
 
     e2e = None
     alone = None
     floor = None
     if not args.no_e2e:
-        e2e_steps(2, host_group)
+        e2e_steps(2, True)
         barrier()
         t0 = time.perf_counter()
-        e2e_steps(args.steps, host_group)
+        e2e_steps(args.steps, True)
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * audio_per_step * args.steps / dt, "unit": "audio-s/s",
@@ -381,12 +406,26 @@ def run_c3(args, world, rank, local):
                  "e2e_fraction_of_floor": floor_ms / e2e["ms_per_step"],
                  "how": "fa_pcie_probe: 4 back-to-back cudaMemcpyAsync of the step's int16 PCM from the same page-locked buffer, "
                         "CUDA events, all ranks between two barriers, max over ranks"}
+        # ---- would write-combined pinned memory lift the N-rank floor?  1 GB probes of both kinds, all ranks at once ----
+        probe_bytes = 1 << 30
+        kinds = {}
+        for name, wc in (("default", 0), ("write_combined", 1)):
+            hb = PinnedBuffer((probe_bytes,), np.uint8, write_combined=bool(wc))
+            hb.array[:: 4096] = 1                      # touch every page
+            L.fa_pcie_probe(local, C.c_void_p(hb.array.ctypes.data), probe_bytes, 1, 0, C.byref(ms))
+            barrier()
+            rc = L.fa_pcie_probe(local, C.c_void_p(hb.array.ctypes.data), probe_bytes, 8, 0, C.byref(ms))
+            t_k = max_over_ranks(float(ms.value) if rc == 0 else float("nan"))
+            barrier()
+            kinds[name] = {"ms_per_GiB": t_k, "gbps_per_gpu": probe_bytes / t_k / 1e6, "aggregate_gbps": world * probe_bytes / t_k / 1e6}
+            hb.free()
+        floor["h2d_1GiB_probe_all_ranks_at_once"] = kinds
         # ---- weak-scaling reference on the same box: rank 0 alone, the other GPUs idle ----
         if world > 1:
             if rank == 0:
-                e2e_steps(2, None)
+                e2e_steps(2, False)
                 t0 = time.perf_counter()
-                e2e_steps(max(3, args.steps // 2), None)
+                e2e_steps(max(3, args.steps // 2), False)
                 torch.cuda.synchronize()
                 dt1 = time.perf_counter() - t0
                 f1 = probe(4)
@@ -431,7 +470,7 @@ def run_c3(args, world, rank, local):
             "results": {"segments": tot["segments"], "feature_rows": tot["feature_rows"], "formant_rows": tot["formant_rows"],
                         "overflow": tot["overflow"]},
         }
-        print(json.dumps(line))
+        emit(line)
     for e in engs:
         e.close()
     pcm.free()
@@ -461,6 +500,7 @@ def main():
                     help="batches in flight: one handle + stream per batch slot, steps alternate between them so that batch "
                          "i+1's spectrum kernels overlap batch i's (latency-bound) segment scan and PCIe copies")
     args = ap.parse_args()
+    capture_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -674,6 +714,61 @@ def main():
         for e in engs2:
             e.close()
 
+    # ---- and with the spectrum as AnalyserNode.getByteFrequencyData (uint8 rows, a quarter of the float32 bytes), int16 PCM in ----
+    e2e_byte = None
+    if not args.no_e2e:
+        from webspeechanalyzer_b200 import FaConfig
+        M = cfg.fft_size // 2
+        cfg3 = FaConfig.default(output_level=5, want_spectrum=1, spectrum_format=1)
+        engs3, sinks3 = [], []
+        for j in range(edepth):
+            e = Engine(cfg3, device=local)
+            e.set_stream(streams[j].cuda_stream)
+            e.set_pipeline(1 if args.serial else args.e2e_pipeline)
+            e.set_d2h_stream(copy_stream.cuda_stream)
+            engs3.append(e)
+            sinks3.append(torch.empty((frames_per_step, M), dtype=torch.uint8, pin_memory=True).numpy())
+        seen3 = []
+
+        def launch3(j):
+            engs3[j].reset()
+            engs3[j].submit_batch(0, pcm16_hosts[j], offs, SR)
+            engs3[j].set_spectrum_sink(sinks3[j])
+            engs3[j].run()
+
+        def collect3(j):
+            engs3[j].sync()
+            r = engs3[j].result(None)
+            seen3.append(sinks3[j].nbytes + r.segments.nbytes + r.formants.nbytes + r.energy.nbytes + r.features.nbytes + r.syllables.nbytes)
+
+        def steps3(k_steps):
+            inflight = []
+            for k in range(k_steps):
+                j = k % edepth
+                if len(inflight) == edepth:
+                    collect3(inflight.pop(0))
+                launch3(j)
+                inflight.append(j)
+            while inflight:
+                collect3(inflight.pop(0))
+
+        steps3(2 * edepth)
+        barrier()
+        t0 = time.perf_counter()
+        steps3(args.steps)
+        torch.cuda.synchronize()
+        dt3 = time.perf_counter() - t0
+        tt3 = torch.tensor([dt3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt3, op=dist.ReduceOp.MAX)
+        e2e_byte = {"value": world * audio_per_step * args.steps / float(tt3.item()), "unit": "audio-s/s",
+                    "h2d_bytes_per_step": int(pcm16_hosts[0].nbytes), "d2h_bytes_per_step": int(seen3[-1]),
+                    "ms_per_step": 1e3 * float(tt3.item()) / args.steps, "batches_in_flight": edepth,
+                    "path": "the C2 outputs with the spectrum as getByteFrequencyData rows (spectrum_format FA_SPECTRUM_U8) and int16 PCM in: "
+                            "fa_reset + fa_submit_pcm_i16_batch + fa_set_spectrum_sink_raw + fa_run ... fa_sync + fa_copy_*"}
+        for e in engs3:
+            e.close()
+
     clocks = sampler.stop()
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -720,6 +815,7 @@ def main():
             "stages": stages,
             "e2e": e2e,
             "e2e_feature_modes": e2e_feat,
+            "e2e_byte_spectrum": e2e_byte,
             "host_affinity": numa,
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
@@ -734,7 +830,7 @@ def main():
             line["cpu_baseline"] = {"value": len(sub) * SECONDS / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
                                     "frames_per_sec": fr / dt,
                                     "sample": f"first {len(sub)} of {n_utt} utterances ({len(sub) * SECONDS} s of audio), C oracle, OpenMP over utterances"}
-        print(json.dumps(line))
+        emit(line)
     for e in engs:
         e.close()
     if world > 1:

@@ -61,6 +61,14 @@ typedef enum fa_status {
 #define FA_SPEC_POWER 2
 #define FA_SPEC_DFFT 3
 
+/* element type of the spectrum rows (fa_config.spectrum_format).  F32: AnalyserNode.getFloatFrequencyData (dB, float32).
+ * U8: AnalyserNode.getByteFrequencyData (W3C Web Audio API): trunc(clamp(255 / (max_db - min_db) *
+ * (Y - min_db), 0, 255)) of the UNclamped dB value Y, -inf -> 0 -- a quarter of the bytes.  F16: the float view rounded to
+ * IEEE half (clamp_db applies as for F32).  U8 / F16 rows are read with fa_copy_spectrum_raw / fa_set_spectrum_sink_raw. */
+#define FA_SPECTRUM_F32 0
+#define FA_SPECTRUM_U8 1
+#define FA_SPECTRUM_F16 2
+
 /* output_level (/root/reference/index.html:170-180) */
 #define FA_LEVEL_BARS 1
 #define FA_LEVEL_SPECTRUM 2
@@ -93,7 +101,7 @@ typedef struct fa_config {
   int32_t fft_size;         /* 2048 (power of two, 256..16384) */
   int32_t clamp_db;         /* 1: clamp the dB view to [min_db, max_db] */
   int32_t want_spectrum;    /* 1: materialise the dB spectrum [frames][fft_size/2] even for levels >= 3 */
-  int32_t reserved0;
+  int32_t spectrum_format;  /* FA_SPECTRUM_F32 (0, default) | FA_SPECTRUM_U8 | FA_SPECTRUM_F16: element type of the spectrum rows */
   double smoothing;         /* smoothingTimeConstant 0.8 */
   double min_db;            /* -100 */
   double max_db;            /* -30 */
@@ -160,6 +168,8 @@ FA_API int fa_set_pipeline(fa_handle* h, int n_sub_batches);
 /* Caller-owned destination (ideally page-locked) for the dB spectrum rows of the whole batch, in submission order:
  * fa_run streams the rows into it as sub-batches finish; valid after fa_sync.  NULL removes the sink. */
 FA_API int fa_set_spectrum_sink(fa_handle* h, float* dst, size_t cap_rows);
+/* The same for any spectrum_format: rows of fft_size / 2 elements of the configured type (float32 / uint8 / half). */
+FA_API int fa_set_spectrum_sink_raw(fa_handle* h, void* dst, size_t cap_rows);
 
 /* Drop all submitted utterances and results (StopAudioNodes / a new batch). */
 FA_API int fa_reset(fa_handle* h);
@@ -223,7 +233,8 @@ FA_API int fa_copy_counts_table(fa_handle* h, fa_counts* dst, size_t cap);
 /* Caller-allocated destinations; `cap` counts elements of the destination type's row
  * (rows for tables).  Return value: rows written (>= 0) or an fa_status (< 0).  utt_id FA_ALL_UTTS returns the whole batch --
  * and FA_ERR_CAPACITY if ANY utterance of the batch overflowed an internal table (fa_counts.overflow; its tables are partial). */
-FA_API int fa_copy_spectrum(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows);      /* rows of fft_size/2 dB values */
+FA_API int fa_copy_spectrum(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows);      /* rows of fft_size/2 dB values (FA_SPECTRUM_F32) */
+FA_API int fa_copy_spectrum_raw(fa_handle* h, int64_t utt_id, void* dst, size_t cap_rows);   /* rows of fft_size/2 elements, any spectrum_format */
 FA_API int fa_copy_frames(fa_handle* h, int64_t utt_id, uint32_t* dst, size_t cap_rows);     /* rows of `bands` uint32 */
 FA_API int fa_copy_segments(fa_handle* h, int64_t utt_id, fa_segment* dst, size_t cap_rows);
 FA_API int fa_copy_formants(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows);      /* rows of 9 float32 */

@@ -13,6 +13,21 @@
  * nvcc: --fmad=false); tests/test_jsmath.py checks it against glibc (<= 1 ulp) and on exact cases.
  *
  * Usable from C, C++ and CUDA device code.
+ *
+ * The algorithms (argument reduction, polynomial coefficients, the hi / lo splitting of the constants) are those of FDLIBM's
+ * e_log.c, e_log10.c and e_pow.c, whose notice is preserved here as it asks:
+ *
+ * ====================================================
+ * Copyright (C) 1993, 2004 by Sun Microsystems, Inc. All rights reserved.
+ *
+ * Developed at SunSoft / SunPro, a Sun Microsystems, Inc. business.
+ * Permission to use, copy, modify, and distribute this
+ * software is freely granted, provided that this notice
+ * is preserved.
+ * ====================================================
+ *
+ * How far this pins the reference's Math.log10 / Math.pow: tests/test_gate_enumeration.py (exhaustive over every reachable y of
+ * the noise gate).
  */
 #ifndef FA_JSMATH_H_
 #define FA_JSMATH_H_

@@ -45,5 +45,17 @@ def ensure_built(force: bool = False) -> str:
     return LIB
 
 
+def build_gate_enum(force: bool = False) -> str:
+    """oracle/gate/gate_enum.c: the exhaustive walk of the noise gate's y -> v map (tests/golden/make_gate_golden.py)."""
+    src, exe = os.path.join(HERE, "gate", "gate_enum.c"), os.path.join(BUILD, "gate_enum")
+    os.makedirs(BUILD, exist_ok=True)
+    if not force and os.path.exists(exe) and os.path.getmtime(exe) >= max(os.path.getmtime(src), os.path.getmtime(DEPS[2])):
+        return exe
+    subprocess.check_call(["gcc", "-std=gnu11", "-O2", "-fopenmp", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"),
+                           "-o", exe + ".tmp", src, "-lm"])
+    os.replace(exe + ".tmp", exe)
+    return exe
+
+
 if __name__ == "__main__":
     print(ensure_built(force="--force" in sys.argv))

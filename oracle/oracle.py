@@ -73,6 +73,17 @@ def frontend(cfg: FaConfig, pcm: np.ndarray, sr: int, spectrum=True, smooth=Fals
     return out
 
 
+def byte_view(spec_db_unclamped: np.ndarray, cfg: FaConfig) -> np.ndarray:
+    """AnalyserNode.getByteFrequencyData of the (unclamped) float dB rows: trunc(clamp(255 / (max - min) * (Y - min), 0, 255)),
+    float32 arithmetic, -inf -> 0 (DESIGN.md front-end spec)."""
+    y = np.asarray(spec_db_unclamped, np.float32)
+    scale = np.float32(255.0 / (cfg.max_db - cfg.min_db))
+    with np.errstate(invalid="ignore"):
+        t = (y - np.float32(cfg.min_db)) * scale
+    t = np.where(np.isnan(t), np.float32(0), t)
+    return np.minimum(np.maximum(t, np.float32(0)), np.float32(255)).astype(np.uint8)
+
+
 def frontend_f64(cfg: FaConfig, pcm: np.ndarray, sr: int) -> np.ndarray:
     pcm = np.ascontiguousarray(pcm, np.float32)
     F = num_frames(cfg, sr, pcm.size)

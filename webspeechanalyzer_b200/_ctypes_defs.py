@@ -4,6 +4,7 @@ from __future__ import annotations
 import ctypes as C
 
 N_FEATURES = 53  # /root/reference/src/localstore.js:7
+SPECTRUM_F32, SPECTRUM_U8, SPECTRUM_F16 = 0, 1, 2   # fa_config.spectrum_format
 N_UTT_FEATURES = 264  # get_utterance_features, /root/reference/dist/main.js:2@B107983 (level 11)
 
 
@@ -14,7 +15,7 @@ class FaConfig(C.Structure):
         ("f_min", C.c_double), ("f_max", C.c_double), ("window_width_ms", C.c_double), ("window_step_ms", C.c_double),
         ("pause_length_ms", C.c_double), ("min_seg_length_ms", C.c_double), ("voiced_max_db", C.c_double),
         ("voiced_min_db", C.c_double), ("pre_norm_gain", C.c_double), ("high_f_emph", C.c_double),
-        ("fft_size", C.c_int32), ("clamp_db", C.c_int32), ("want_spectrum", C.c_int32), ("reserved0", C.c_int32),
+        ("fft_size", C.c_int32), ("clamp_db", C.c_int32), ("want_spectrum", C.c_int32), ("spectrum_format", C.c_int32),
         ("smoothing", C.c_double), ("min_db", C.c_double), ("max_db", C.c_double), ("mag_scale", C.c_double),
     ]
 
@@ -24,7 +25,7 @@ class FaConfig(C.Structure):
         c = cls(spec_type=1, output_level=4, plot_len=200, n_fft_bins=256, n_mel_bins=128, auto_noise_gate=1,
                 f_min=50.0, f_max=4000.0, window_width_ms=25.0, window_step_ms=25.0, pause_length_ms=200.0,
                 min_seg_length_ms=50.0, voiced_max_db=100.0, voiced_min_db=10.0, pre_norm_gain=1000.0, high_f_emph=0.0,
-                fft_size=2048, clamp_db=1, want_spectrum=0, reserved0=0, smoothing=0.8, min_db=-100.0, max_db=-30.0,
+                fft_size=2048, clamp_db=1, want_spectrum=0, spectrum_format=0, smoothing=0.8, min_db=-100.0, max_db=-30.0,
                 mag_scale=0.0)
         for k, v in over.items():
             if not hasattr(c, k):

@@ -100,7 +100,7 @@ struct fa_handle {
   long long staged = 0;        // floats used in h_pcm
   long long dev_floats = 0;    // floats of d_pcm in use
   int pipeline = 0;            // sub-batches: 0 = auto, 1 = serial
-  float* spec_sink = nullptr;  // caller-owned destination of the dB rows (filled during fa_run)
+  void* spec_sink = nullptr;   // caller-owned destination of the spectrum rows (filled during fa_run), element type = spectrum_format
   size_t spec_sink_rows = 0;
   cudaStream_t sub_stream[kMaxSub] = {};
   cudaStream_t sub_hi[kMaxSub] = {};    // high-priority streams for the latency-bound segment scan + features of a sub-batch
@@ -126,6 +126,7 @@ struct fa_handle {
   DevBuf d_segs, d_syls, d_formants, d_energy, d_features, d_counts, d_off;
   // K1b stream mode: chunk work list (utt[], idx[], base[n+1]), speculated entry / true exit states, separate dB rows, fix-up count
   DevBuf d_chunks, d_state, d_specdb, d_fix;
+  DevBuf d_specq;   // spectrum rows as uint8 (getByteFrequencyData) or half: [F][M] elements
   int chunk_frames = 0, warm_frames = 0;
   long long total_chunks = 0;
   std::vector<long long> chunk_base;   // host copy of base[]
@@ -136,6 +137,10 @@ struct fa_handle {
   long long total_cchunks = 0;
   std::vector<long long> cchunk_base;
   float* spec_rows() const { return (chunk_frames > 0 && want_spec) ? d_specdb.as<float>() : d_spec.as<float>(); }
+  // the rows the caller gets: float32 dB (in d_spec / d_specdb) or the uint8 / half rows of d_specq
+  int spec_fmt() const { return cfg.spectrum_format; }
+  size_t spec_elem() const { return spec_fmt() == FA_SPECTRUM_U8 ? 1 : spec_fmt() == FA_SPECTRUM_F16 ? 2 : 4; }
+  const char* spec_out() const { return spec_fmt() == FA_SPECTRUM_F32 ? (const char*)spec_rows() : d_specq.as<char>(); }
   DevBuf d_frctl, d_frv, d_epochs, d_work, d_k3q;   // K3 mode 1: per-frame control record, epoch table, work list, queue counters
   int k3_cfg = -1;       // FA_K3_MODE: 0 = serial one-warp-per-utterance kernel, 1 = control scan + epoch-parallel tracking,
                          // unset = automatic (prepare): long utterances / streams take mode 1, short ones mode 0
@@ -190,6 +195,8 @@ int validate(const fa_config* c, std::string* why) {
   const int B = fa_tab_bands(c);
   if (B < 8 || B > FA_MAX_BANDS) { *why = "Invalid spec_bands"; return FA_ERR_INVALID_ARG; }
   if (!(c->window_step_ms > 0) || !(c->f_max > c->f_min) || !(c->f_min >= 0)) { *why = "Invalid reset_nodes config"; return FA_ERR_INVALID_ARG; }
+  if (c->spectrum_format < FA_SPECTRUM_F32 || c->spectrum_format > FA_SPECTRUM_F16) { *why = "spectrum_format must be FA_SPECTRUM_F32, _U8 or _F16"; return FA_ERR_INVALID_ARG; }
+  if (c->spectrum_format == FA_SPECTRUM_U8 && !(c->max_db > c->min_db)) { *why = "maxDecibels must exceed minDecibels"; return FA_ERR_INVALID_ARG; }
   if (!(c->smoothing >= 0.0 && c->smoothing <= 1.0)) { *why = "smoothingTimeConstant must be in [0, 1]"; return FA_ERR_INVALID_ARG; }
   return FA_OK;
 }
@@ -343,7 +350,7 @@ int fa_destroy(fa_handle* h) {
                     &h->d_win, &h->d_tw, &h->d_tws, &h->d_ws, &h->d_bmi, &h->d_bmw, &h->d_emph, &h->d_spill, &h->d_trkbase, &h->d_trk_i,
                     &h->d_trk_d, &h->d_trk_slot, &h->d_pt_i, &h->d_pt_e, &h->d_rows, &h->d_rowlist, &h->d_segs, &h->d_syls,
                     &h->d_formants, &h->d_energy, &h->d_features, &h->d_counts, &h->d_off, &h->g_segs, &h->g_syls,
-                    &h->g_formants, &h->g_energy, &h->g_features, &h->d_chunks, &h->d_state, &h->d_specdb, &h->d_fix, &h->d_cchunks, &h->d_cstate, &h->d_frT, &h->d_frk, &h->d_frthr, &h->d_frctl, &h->d_frv, &h->d_epochs, &h->d_work, &h->d_k3q})
+                    &h->g_formants, &h->g_energy, &h->g_features, &h->d_chunks, &h->d_state, &h->d_specdb, &h->d_specq, &h->d_fix, &h->d_cchunks, &h->d_cstate, &h->d_frT, &h->d_frk, &h->d_frthr, &h->d_frctl, &h->d_frv, &h->d_epochs, &h->d_work, &h->d_k3q})
     b->release();
   for (HostBuf* b : {&h->h_pcm, &h->h_frames, &h->h_meta, &h->h_counts, &h->h_off, &h->h_segs, &h->h_syls, &h->h_formants, &h->h_energy,
                      &h->h_features})
@@ -432,12 +439,18 @@ int fa_set_pipeline(fa_handle* h, int n_sub) {
   return FA_OK;
 }
 
-int fa_set_spectrum_sink(fa_handle* h, float* dst, size_t cap_rows) {
+int fa_set_spectrum_sink_raw(fa_handle* h, void* dst, size_t cap_rows) {
   if (!h) return FA_ERR_INVALID_ARG;
   if (dst && !h->want_spec) return fail(h, FA_ERR_INVALID_ARG, "spectrum not materialised (set want_spectrum or output_level <= 2)");
   h->spec_sink = dst;
   h->spec_sink_rows = dst ? cap_rows : 0;
   return FA_OK;
+}
+
+int fa_set_spectrum_sink(fa_handle* h, float* dst, size_t cap_rows) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  if (dst && h->spec_fmt() != FA_SPECTRUM_F32) return fail(h, FA_ERR_INVALID_ARG, "spectrum_format is not float32: use fa_set_spectrum_sink_raw");
+  return fa_set_spectrum_sink_raw(h, dst, cap_rows);
 }
 
 int fa_reset(fa_handle* h) {
@@ -694,6 +707,7 @@ static int prepare(fa_handle* h) {
   const size_t Fz = (size_t)std::max<long long>(F, 1), nz = (size_t)n;
   // the K1a -> K1b magnitude rows, turned into dB rows in place; the fused kernel needs them only as dB output
   if (h->want_spec || !h->use_fused()) FA_CUDA(h->d_spec.reserve(Fz * h->M * sizeof(float)));
+  if (h->want_spec && h->spec_fmt() != FA_SPECTRUM_F32) FA_CUDA(h->d_specq.reserve(Fz * h->M * h->spec_elem()));
   FA_CUDA(h->d_frames.reserve(Fz * h->B * sizeof(uint32_t)));
   FA_CUDA(h->d_counter.reserve(2 * kMaxSub * sizeof(int)));
   if (h->cfg.output_level >= 3) {
@@ -773,7 +787,7 @@ static int prepare(fa_handle* h) {
                             cudaMemcpyHostToDevice, s));
     FA_CUDA(cudaStreamSynchronize(s));   // `lists` dies at scope exit
     FA_CUDA(h->d_state.reserve(2 * tc * (size_t)h->M * sizeof(float)));
-    if (h->want_spec) FA_CUDA(h->d_specdb.reserve(Fz * h->M * sizeof(float)));
+    if (h->want_spec && h->spec_fmt() == FA_SPECTRUM_F32) FA_CUDA(h->d_specdb.reserve(Fz * h->M * sizeof(float)));
   }
   h->prepared = true;
   return FA_OK;
@@ -888,6 +902,9 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
   sp.scratch_mag = 1;
   sp.write_db = h->want_spec;
   sp.fused = h->use_fused();
+  sp.spec_fmt = h->spec_fmt();
+  sp.spec_q = h->d_specq.p;
+  sp.byte_scale = (float)(255.0 / (c.max_db - c.min_db));
   sp.n_rows = sb.r1 - sb.r0;
   sp.spec_db = h->d_spec.as<float>();
   sp.frames = h->d_frames.as<uint32_t>();
@@ -900,7 +917,7 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
     sp.chunk_frames = h->chunk_frames; sp.warm_frames = h->warm_frames;
     sp.chunk_base = base; sp.chunk_utt = utt_list + c0; sp.chunk_idx = utt_list + tc + c0; sp.n_chunks = (int)(c1 - c0);
     sp.st_entry = h->d_state.as<float>(); sp.st_exit = sp.st_entry + tc * h->M;
-    sp.spec_out = h->want_spec ? h->d_specdb.as<float>() : nullptr;
+    sp.spec_out = (h->want_spec && h->spec_fmt() == FA_SPECTRUM_F32) ? h->d_specdb.as<float>() : nullptr;
     sp.fixups = h->d_fix.as<int>();
   }
   if (!h->frames_mode) FA_CUDA(fa_launch_spectrum(sp, s, &h->launches));
@@ -1025,7 +1042,7 @@ static int run_device(fa_handle* h, bool with_h2d, bool with_sink) {
     const int rc = launch_sub(h, all, 0, s, h->ev);
     if (rc != FA_OK) return rc;
     if (sink && h->total_frames)
-      FA_CUDA(cudaMemcpyAsync(h->spec_sink, h->spec_rows(), (size_t)h->total_frames * h->M * sizeof(float), cudaMemcpyDeviceToHost, s));
+      FA_CUDA(cudaMemcpyAsync(h->spec_sink, h->spec_out(), (size_t)h->total_frames * h->M * h->spec_elem(), cudaMemcpyDeviceToHost, s));
   } else {
     { const int rc = ensure_sub_streams(h, (int)subs.size()); if (rc != FA_OK) return rc; }
     if (sink && !h->copy_stream) {
@@ -1046,8 +1063,9 @@ static int run_device(fa_handle* h, bool with_h2d, bool with_sink) {
         // the copy stream: FIFO over sub-batches -- and over batches when several handles share one copy stream
         FA_CUDA(cudaStreamWaitEvent(h->copy_stream, h->spec_done[b], 0));
         if (h->trace) FA_CUDA(cudaEventRecord(h->tr_ev[b][2], h->copy_stream));
-        FA_CUDA(cudaMemcpyAsync(h->spec_sink + (size_t)subs[b].r0 * h->M, h->spec_rows() + (size_t)subs[b].r0 * h->M,
-                                (size_t)(subs[b].r1 - subs[b].r0) * h->M * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+        const size_t row_bytes = (size_t)h->M * h->spec_elem();
+        FA_CUDA(cudaMemcpyAsync((char*)h->spec_sink + (size_t)subs[b].r0 * row_bytes, h->spec_out() + (size_t)subs[b].r0 * row_bytes,
+                                (size_t)(subs[b].r1 - subs[b].r0) * row_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
         FA_CUDA(cudaEventRecord(h->copy_done[b], h->copy_stream));
         if (h->trace) FA_CUDA(cudaEventRecord(h->tr_ev[b][3], h->copy_stream));
       }
@@ -1305,11 +1323,17 @@ static int copy_rows_device(fa_handle* h, int64_t utt_id, const void* dev, size_
   return (int)nr;
 }
 
-int fa_copy_spectrum(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows) {
+int fa_copy_spectrum_raw(fa_handle* h, int64_t utt_id, void* dst, size_t cap_rows) {
   if (!h) return FA_ERR_INVALID_ARG;
   if (!h->want_spec) return fail(h, FA_ERR_INVALID_ARG, "spectrum not materialised (set want_spectrum or output_level <= 2)");
   if (h->frames_mode) return fail(h, FA_ERR_INVALID_ARG, "spectrum not materialised (the batch was submitted as frames)");
-  return copy_rows_device(h, utt_id, h->spec_rows(), (size_t)h->M * sizeof(float), dst, cap_rows);
+  return copy_rows_device(h, utt_id, h->spec_out(), (size_t)h->M * h->spec_elem(), dst, cap_rows);
+}
+
+int fa_copy_spectrum(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  if (h->spec_fmt() != FA_SPECTRUM_F32) return fail(h, FA_ERR_INVALID_ARG, "spectrum_format is not float32: use fa_copy_spectrum_raw");
+  return fa_copy_spectrum_raw(h, utt_id, dst, cap_rows);
 }
 
 int fa_copy_frames(fa_handle* h, int64_t utt_id, uint32_t* dst, size_t cap_rows) {

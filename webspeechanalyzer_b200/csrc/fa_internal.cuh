@@ -43,6 +43,9 @@ struct FaSpectrumParams {
   int scratch_mag;               // 1: spec_db is allocated and may be used as the K1a -> K1b magnitude buffer
   int write_db;                  // 1: the caller wants the dB rows
   int fused;                     // 1: fft_size 2048 in utterance mode runs the fused K1 kernel (no magnitude round trip)
+  int spec_fmt;                  // FA_SPECTRUM_F32 / _U8 / _F16: element type of the rows the caller gets
+  void* spec_q;                  // [F_total][M] uint8 or half rows (spec_fmt != F32); the magnitudes then stay in spec_db
+  float byte_scale;              // 255 / (max_db - min_db)
   long long n_rows;              // frames of the sub-batch
   uint32_t* frames;              // [F_total][B] or nullptr
   int* work_counter;             // dynamic utterance queue

@@ -55,13 +55,18 @@ struct MlpArgs {
   float* out;           // [n_rows][dims[n_layers]]
 };
 
+// kSmemParams: all parameters staged once per CTA in shared memory (the shipped 53-256-64-16-4 model: 31 k floats); otherwise
+// (53-512-512-8: 294 k floats = 1.2 MB) they are read where they are -- consecutive threads read consecutive output units of a
+// kernel row, and the whole model stays in L2.  Same fmaf chain in the same order => same bits either way.
+template <bool kSmemParams>
 __global__ void __launch_bounds__(kMlpThreads) fa_mlp_kernel(const MlpArgs a) {
   extern __shared__ __align__(16) float smem[];
-  float* W = smem;                                   // all parameters
-  float* act0 = W + ((a.n_params + 3) & ~3);         // [kRowsPerCta][max_dim]
+  const float* W = kSmemParams ? smem : a.params;
+  float* act0 = smem + (kSmemParams ? ((a.n_params + 3) & ~3) : 0);   // [kRowsPerCta][max_dim]
   float* act1 = act0 + kRowsPerCta * a.max_dim;
   const int tid = threadIdx.x;
-  for (int i = tid; i < a.n_params; i += kMlpThreads) W[i] = a.params[i];
+  if (kSmemParams)
+    for (int i = tid; i < a.n_params; i += kMlpThreads) smem[i] = a.params[i];
   const int row0 = blockIdx.x * kRowsPerCta;
   const int nin = a.dims[0];
   // ml5 normalisation in double, then float32 (tf.tensor): (x - min) / (max - min)
@@ -87,7 +92,7 @@ __global__ void __launch_bounds__(kMlpThreads) fa_mlp_kernel(const MlpArgs a) {
 #pragma unroll
       for (int r = 0; r < kRowsPerCta; r++) acc[r] = 0.f;
       for (int k = 0; k < ni; k++) {
-        const float w = Wl[k * no + o];
+        const float w = kSmemParams ? Wl[k * no + o] : __ldg(Wl + k * no + o);
 #pragma unroll
         for (int r = 0; r < kRowsPerCta; r++) acc[r] = fmaf(in[r * a.max_dim + k], w, acc[r]);
       }
@@ -136,10 +141,19 @@ int mlp_launch(fa_mlp* m, const double* d_rows, int n_rows, float* d_out, cudaSt
   for (int l = 0; l < m->n_layers; l++) { a.act[l] = m->act[l]; a.w_off[l] = m->w_off[l]; a.b_off[l] = m->b_off[l]; }
   a.n_params = m->n_params; a.max_dim = m->max_dim; a.params = m->d_params; a.norm = m->d_norm;
   a.rows = d_rows; a.n_rows = n_rows; a.out = d_out;
-  const int bytes = (((m->n_params + 3) & ~3) + 2 * kRowsPerCta * m->max_dim) * (int)sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(fa_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e != cudaSuccess) return mlp_fail(m, FA_ERR_CUDA, "mlp shared memory", e);
-  fa_mlp_kernel<<<(n_rows + kRowsPerCta - 1) / kRowsPerCta, kMlpThreads, bytes, s>>>(a);
+  const int act_bytes = 2 * kRowsPerCta * m->max_dim * (int)sizeof(float);
+  const int all_bytes = ((m->n_params + 3) & ~3) * (int)sizeof(float) + act_bytes;
+  const int grid = (n_rows + kRowsPerCta - 1) / kRowsPerCta;
+  cudaError_t e;
+  if (all_bytes <= 200 * 1024) {
+    e = cudaFuncSetAttribute(fa_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, all_bytes);
+    if (e != cudaSuccess) return mlp_fail(m, FA_ERR_CUDA, "mlp shared memory", e);
+    fa_mlp_kernel<true><<<grid, kMlpThreads, all_bytes, s>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(fa_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, act_bytes);
+    if (e != cudaSuccess) return mlp_fail(m, FA_ERR_CUDA, "mlp shared memory", e);
+    fa_mlp_kernel<false><<<grid, kMlpThreads, act_bytes, s>>>(a);
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return mlp_fail(m, FA_ERR_CUDA, "mlp launch", e);
   return FA_OK;

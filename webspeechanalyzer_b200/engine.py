@@ -155,9 +155,9 @@ class Engine:
             self._sink = None
             self._check(self._lib.fa_set_spectrum_sink(self._h, None, 0))
         else:
-            assert dst.dtype == np.float32 and dst.flags.c_contiguous and dst.shape[1] == self.cfg.fft_size // 2
+            assert dst.dtype == self.spectrum_dtype and dst.flags.c_contiguous and dst.shape[1] == self.cfg.fft_size // 2
             self._sink = dst
-            self._check(self._lib.fa_set_spectrum_sink(self._h, dst.ctypes.data, dst.shape[0]))
+            self._check(self._lib.fa_set_spectrum_sink_raw(self._h, dst.ctypes.data, dst.shape[0]))
 
     def run(self):
         self._check(self._lib.fa_run(self._h))
@@ -228,9 +228,14 @@ class Engine:
         n = self._check(fn(self._h, -1 if utt_id is None else utt_id, out.ctypes.data, nrows))
         return out[:n]
 
+    @property
+    def spectrum_dtype(self):
+        """Element type of the spectrum rows: float32 dB, uint8 (getByteFrequencyData) or float16 (cfg.spectrum_format)."""
+        return np.dtype((np.float32, np.uint8, np.float16)[self.cfg.spectrum_format])
+
     def spectrum(self, utt_id: int | None = None) -> np.ndarray:
         c = self.counts(utt_id)
-        return self._rows(self._lib.fa_copy_spectrum, utt_id, c["frames"], (self.cfg.fft_size // 2,), np.float32)
+        return self._rows(self._lib.fa_copy_spectrum_raw, utt_id, c["frames"], (self.cfg.fft_size // 2,), self.spectrum_dtype)
 
     def frames(self, utt_id: int | None = None) -> np.ndarray:
         c = self.counts(utt_id)
