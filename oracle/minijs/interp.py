@@ -857,7 +857,29 @@ class Interp:
             p = JSPromise(self)
             p.resolve(a[0] if a else UNDEF)
             return p
-        pr.props = {'resolve': nat(p_resolve, 'resolve')}
+        def p_all(this, a):
+            # Promise.all over an array: resolves (one micro-task after the last element) with the values in order, rejects
+            # with the first rejection (src/prediction.js:65 waits for one nn_prediction per model this way)
+            items = list(a[0].a) if a and isinstance(a[0], JSArray) else []
+            out = JSPromise(self)
+            vals = [UNDEF] * len(items)
+            left = [len(items)]
+            if not items:
+                out.resolve(JSArray([]))
+                return out
+
+            def settle(i):
+                def ok(v):
+                    vals[i] = v
+                    left[0] -= 1
+                    if left[0] == 0:
+                        out.resolve(JSArray(list(vals)))
+                return ok
+            for i, it_ in enumerate(items):
+                q = it_ if type(it_) is JSPromise else p_resolve(UNDEF, [it_])
+                q._subscribe(settle(i), out.reject)
+            return out
+        pr.props = {'resolve': nat(p_resolve, 'resolve'), 'all': nat(p_all, 'all')}
         g['Promise'] = pr
 
         def logger(level):

@@ -140,3 +140,57 @@ def test_classify_feature_rows_where_they_are(tmp_path):
         with pytest.raises(Exception):
             clf.classify_features(eng)
     clf.close()
+
+
+def test_segment_vote_matches_reference_prediction_js():
+    """SegmentVoter against what the reference's own src/prediction.js passed to its callback (executed by oracle/minijs;
+    tests/golden/make_ref_js_vote_golden.py): label and confidence bit for bit, including the one-syllable quirk (only the top
+    class of the flat list counts), exact ties and zero-duration segments (no callback)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    doc = json.load(open(os.path.join(here, "golden", "ref_js_vote.json")))
+    n = 0
+    for segs in doc["clips"]:
+        v = predict.SegmentVoter((1,))
+        for s in segs:
+            res, st = s["results"], s["seg_time"]
+            got = v.segment({1: [res] if len(st) == 1 else res}, st)
+            want = s["reference_callback"]
+            assert (got is None) == (want is None)
+            if want is not None:
+                assert got[0] == want[0] and got[1] == want[1], (got, want)
+            n += 1
+    assert n >= 20
+    if os.path.exists("/root/reference/src/prediction.js"):      # build container: execute the reference again, live
+        import sys
+        sys.path.insert(0, os.path.join(here, "golden"))
+        from make_ref_js_vote_golden import reference_votes
+        for segs in doc["clips"][:2]:
+            live = reference_votes([(s["results"], s["seg_time"]) for s in segs])
+            assert live == [s["reference_callback"] for s in segs]
+
+
+@pytest.mark.gpu
+def test_shipped_models_against_float64():
+    """The reference's shipped classifiers (dist/nnmodel/{1,2,4..7}/cats_emotion; 4-7 share one weight file) scored by the
+    CUDA kernel on real 53-dim rows of the demo WAV, against an independent float64 forward pass
+    (tests/golden/make_mlp_golden.py): same arg-max on every row, class scores within 1e-5.  Model 4 (53-512-512-8, 1.2 MB of
+    parameters) takes the kernel variant that reads the parameters from L2 instead of shared memory."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    z = np.load(os.path.join(here, "golden", "mlp_shipped.npz"))
+    info = json.load(open(os.path.join(here, "golden", "mlp_shipped.json")))
+    rows = z["rows"]
+    assert rows.shape == (info["rows"], 53) and rows.shape[0] >= 30
+    for db, mi in info["models"].items():
+        n = len(mi["dims"]) - 1
+        model = dict(dims=mi["dims"], activations=mi["activations"], kernels=[z[f"m{db}_k{i}"] for i in range(n)],
+                     biases=[z[f"m{db}_b{i}"] for i in range(n)], in_min=z[f"m{db}_min"], in_max=z[f"m{db}_max"], labels=mi["labels"])
+        clf = predict.Classifier(model)
+        p = clf.probabilities(rows)
+        want = z[f"m{db}_expected"]
+        assert p.shape == want.shape
+        assert np.array_equal(p.argmax(axis=1), want.argmax(axis=1)), db
+        assert np.abs(p.astype(np.float64) - want).max() <= 1e-5, (db, np.abs(p - want).max())
+        assert np.allclose(p.sum(axis=1), 1.0, atol=1e-5)
+        res = clf.classify_multiple(rows[:2])
+        assert res[0][0]["label"] == mi["labels"][int(want[0].argmax())]
+        clf.close()

@@ -162,6 +162,7 @@ struct fa_handle {
   bool frames_mode = false;    // the batch was submitted as uint32 frames (fa_submit_frames): the spectrum stage is skipped
   HostBuf h_frames;            // pinned staging of submitted frames, row order
   long long tot[4] = {0, 0, 0, 0};  // segs, rows, syls, feat
+  bool have_table[5] = {false, false, false, false, false};   // dense tables fetched so far: segs, formants, energy, syls, features
   cudaEvent_t ev[8] = {};
   float stage_ms[5] = {0, 0, 0, 0, 0};
   int launches = 0;
@@ -1138,20 +1139,9 @@ int fa_download(fa_handle* h) {
     FA_CUDA(cudaStreamSynchronize(s));
     const long long* off = h->h_off.as<long long>();
     for (int k = 0; k < 4; k++) h->tot[k] = off[(size_t)k * (n + 1) + n];
-    FA_CUDA(h->h_segs.reserve(std::max<size_t>(16, h->tot[0] * sizeof(fa_segment))));
-    FA_CUDA(h->h_formants.reserve(std::max<size_t>(16, h->tot[1] * 9 * sizeof(float))));
-    FA_CUDA(h->h_energy.reserve(std::max<size_t>(16, h->tot[1] * 3 * sizeof(float))));
-    FA_CUDA(h->h_syls.reserve(std::max<size_t>(16, h->tot[2] * sizeof(fa_syllable))));
-    FA_CUDA(h->h_features.reserve(std::max<size_t>(16, h->tot[3] * h->feat_width() * sizeof(double))));
-    if (h->tot[0]) FA_CUDA(cudaMemcpyAsync(h->h_segs.p, h->g_segs.p, h->tot[0] * sizeof(fa_segment), cudaMemcpyDeviceToHost, s));
-    if (h->tot[1]) {
-      FA_CUDA(cudaMemcpyAsync(h->h_formants.p, h->g_formants.p, h->tot[1] * 9 * sizeof(float), cudaMemcpyDeviceToHost, s));
-      FA_CUDA(cudaMemcpyAsync(h->h_energy.p, h->g_energy.p, h->tot[1] * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
-    }
-    if (h->tot[2]) FA_CUDA(cudaMemcpyAsync(h->h_syls.p, h->g_syls.p, h->tot[2] * sizeof(fa_syllable), cudaMemcpyDeviceToHost, s));
-    if (h->tot[3])
-      FA_CUDA(cudaMemcpyAsync(h->h_features.p, h->g_features.p, h->tot[3] * h->feat_width() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    // the dense tables themselves come on demand (fetch_table): a Syllable-Features caller never pays for the formant rows
   }
+  for (bool& b : h->have_table) b = false;
   FA_CUDA(cudaEventRecord(h->ev[6], s));
   h->downloaded = true;
   return FA_OK;
@@ -1341,11 +1331,33 @@ int fa_copy_frames(fa_handle* h, int64_t utt_id, uint32_t* dst, size_t cap_rows)
   return copy_rows_device(h, utt_id, h->d_frames.p, (size_t)h->B * sizeof(uint32_t), dst, cap_rows);
 }
 
-// dense host tables: kind 0 segs, 1 rows, 2 syls, 3 feat
-static int copy_dense(fa_handle* h, int64_t utt_id, int kind, const void* host, size_t row_bytes, void* dst, size_t cap_rows) {
+// one dense table device -> pinned host, once per run: 0 segs, 1 formants, 2 energy, 3 syls, 4 features
+static int fetch_table(fa_handle* h, int table) {
+  if (h->have_table[table] || h->cfg.output_level < 3) return FA_OK;
+  cudaStream_t s = h->stream;
+  HostBuf* hb[5] = {&h->h_segs, &h->h_formants, &h->h_energy, &h->h_syls, &h->h_features};
+  DevBuf* db[5] = {&h->g_segs, &h->g_formants, &h->g_energy, &h->g_syls, &h->g_features};
+  const size_t rows = (size_t)h->tot[table == 0 ? 0 : table <= 2 ? 1 : table == 3 ? 2 : 3];
+  const size_t row_bytes = table == 0 ? sizeof(fa_segment) : table == 1 ? 9 * sizeof(float) : table == 2 ? 3 * sizeof(float)
+                           : table == 3 ? sizeof(fa_syllable) : (size_t)h->feat_width() * sizeof(double);
+  FA_CUDA(hb[table]->reserve(std::max<size_t>(16, rows * row_bytes)));
+  if (rows) {
+    FA_CUDA(cudaMemcpyAsync(hb[table]->p, db[table]->p, rows * row_bytes, cudaMemcpyDeviceToHost, s));
+    FA_CUDA(cudaStreamSynchronize(s));
+  }
+  h->have_table[table] = true;
+  return FA_OK;
+}
+
+// dense host tables: kind 0 segs, 1 rows, 2 syls, 3 feat (offset tables); table: see fetch_table
+static int copy_dense(fa_handle* h, int64_t utt_id, int kind, int table, size_t row_bytes, void* dst, size_t cap_rows) {
   int rc = need_results(h);
   if (rc != FA_OK) return rc;
   if (h->cfg.output_level < 3) return 0;
+  rc = fetch_table(h, table);
+  if (rc != FA_OK) return rc;
+  HostBuf* hb[5] = {&h->h_segs, &h->h_formants, &h->h_energy, &h->h_syls, &h->h_features};
+  const void* host = hb[table]->p;
   const int n = (int)h->utts.size();
   const long long* off = h->h_off.as<long long>() + (size_t)kind * (n + 1);
   long long r0 = 0, nr = off[n];
@@ -1364,31 +1376,31 @@ static int copy_dense(fa_handle* h, int64_t utt_id, int kind, const void* host, 
 
 int fa_copy_segments(fa_handle* h, int64_t utt_id, fa_segment* dst, size_t cap) {
   if (!h) return FA_ERR_INVALID_ARG;
-  return copy_dense(h, utt_id, 0, h->h_segs.p, sizeof(fa_segment), dst, cap);
+  return copy_dense(h, utt_id, 0, 0, sizeof(fa_segment), dst, cap);
 }
 int fa_copy_formants(fa_handle* h, int64_t utt_id, float* dst, size_t cap) {
   if (!h) return FA_ERR_INVALID_ARG;
-  return copy_dense(h, utt_id, 1, h->h_formants.p, 9 * sizeof(float), dst, cap);
+  return copy_dense(h, utt_id, 1, 1, 9 * sizeof(float), dst, cap);
 }
 int fa_copy_energy(fa_handle* h, int64_t utt_id, float* dst, size_t cap) {
   if (!h) return FA_ERR_INVALID_ARG;
-  return copy_dense(h, utt_id, 1, h->h_energy.p, 3 * sizeof(float), dst, cap);
+  return copy_dense(h, utt_id, 1, 2, 3 * sizeof(float), dst, cap);
 }
 int fa_copy_syllables(fa_handle* h, int64_t utt_id, fa_syllable* dst, size_t cap) {
   if (!h) return FA_ERR_INVALID_ARG;
-  return copy_dense(h, utt_id, 2, h->h_syls.p, sizeof(fa_syllable), dst, cap);
+  return copy_dense(h, utt_id, 2, 3, sizeof(fa_syllable), dst, cap);
 }
 int fa_copy_features(fa_handle* h, int64_t utt_id, double* dst, size_t cap) {
   if (!h) return FA_ERR_INVALID_ARG;
   if (h->cfg.output_level == FA_LEVEL_UTTERANCE)
     return fail(h, FA_ERR_INVALID_ARG, "level 11 rows have 264 entries: use fa_copy_utterance_features");
-  return copy_dense(h, utt_id, 3, h->h_features.p, FA_N_FEATURES * sizeof(double), dst, cap);
+  return copy_dense(h, utt_id, 3, 4, FA_N_FEATURES * sizeof(double), dst, cap);
 }
 
 int fa_copy_utterance_features(fa_handle* h, int64_t utt_id, double* dst, size_t cap) {
   if (!h) return FA_ERR_INVALID_ARG;
   if (h->cfg.output_level != FA_LEVEL_UTTERANCE) return fail(h, FA_ERR_INVALID_ARG, "utterance distributions need output_level 11");
-  return copy_dense(h, utt_id, 3, h->h_features.p, FA_N_UTT_FEATURES * sizeof(double), dst, cap);
+  return copy_dense(h, utt_id, 3, 4, FA_N_UTT_FEATURES * sizeof(double), dst, cap);
 }
 
 int fa_mlp_classify_features(fa_mlp* m, fa_handle* h, int64_t utt_id, float* probs, size_t cap_rows) {

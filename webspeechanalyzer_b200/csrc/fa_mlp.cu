@@ -202,8 +202,8 @@ int fa_mlp_create(int n_layers, const int* dims, const int* activations, const f
     m->b_off[l] = off; off += dims[l + 1];
   }
   m->n_params = off; m->max_dim = mx;
-  const size_t smem = ((size_t)((off + 3) & ~3) + 2 * kRowsPerCta * mx) * sizeof(float);
-  if (smem > 200 * 1024) { delete m; return FA_ERR_UNSUPPORTED; }   // the model must fit one CTA's shared memory
+  // the activations of 8 rows must fit one CTA's shared memory; the parameters are staged there too when they fit (mlp_launch)
+  if ((size_t)2 * kRowsPerCta * mx * sizeof(float) > 200 * 1024) { delete m; return FA_ERR_UNSUPPORTED; }
   std::vector<float> host((size_t)off);
   for (int l = 0; l < n_layers; l++) {
     memcpy(host.data() + m->w_off[l], kernels[l], sizeof(float) * (size_t)dims[l] * dims[l + 1]);

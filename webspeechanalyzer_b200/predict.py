@@ -157,7 +157,9 @@ class SegmentVoter:
     def segment(self, results_by_db: dict, seg_time) -> tuple | None:
         """results_by_db[db] = ml5-shaped results of the segment's syllable rows; seg_time = [[t0, dur] strings ...].
         Returns (top label, confidence / total duration) like the callback of predict_by_multiple_syllables."""
-        seg_weight = sum(float(t[1]) for t in seg_time)
+        seg_weight = 0.0
+        for t in seg_time:          # a plain left-to-right sum like the reference's loop (Python >= 3.12's sum() compensates)
+            seg_weight += float(t[1])
         if not seg_weight > 0:
             return None
         conf_seg = {d: {} for d in self.db_ids}
