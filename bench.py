@@ -376,7 +376,12 @@ def run_c3(args, world, rank, local):
         bd["wait_gpu"] += t1 - t0
         bd["tables"] += t2 - t1
         if gather and world > 1:      # every rank takes part (host-side gloo group); the one-rank-alone pass must not
-            join_gather()
+            # at most two gathers in flight: waiting for the previous one here measured 15 ms per step at 8 ranks -- not the
+            # 16 MB per rank, but the skew between ranks (a gather ends when the slowest rank has joined it)
+            t3 = time.perf_counter()
+            while len(pending) >= 2:
+                pending.pop(0).result()
+            bd["gather_join"] += time.perf_counter() - t3
             pending.append(pool.submit(gather_job, keys, feats))
         else:
             gathered["rows"], gathered["bytes"] = int(feats.shape[0]), int(keys.nbytes + feats.nbytes)
@@ -435,10 +440,11 @@ def run_c3(args, world, rank, local):
                  "e2e_fraction_of_floor": floor_ms / e2e["ms_per_step"],
                  "how": "fa_pcie_probe: 4 back-to-back cudaMemcpyAsync of the step's int16 PCM from the same page-locked buffer, "
                         "CUDA events, all ranks between two barriers, max over ranks"}
-        # ---- would write-combined pinned memory lift the N-rank floor?  1 GB probes of both kinds, all ranks at once ----
+        # ---- would write-combined pinned memory lift the N-rank floor?  1 GB probes of both kinds, all ranks at once
+        #      (--probe-wc; measured on the 8-GPU boxes: 188 vs 190 GB/s aggregate, no) ----
         probe_bytes = 1 << 30
         kinds = {}
-        for name, wc in (("default", 0), ("write_combined", 1)):
+        for name, wc in ((("default", 0), ("write_combined", 1)) if args.probe_wc else ()):
             hb = PinnedBuffer((probe_bytes,), np.uint8, write_combined=bool(wc))
             hb.array[:: 4096] = 1                      # touch every page
             L.fa_pcie_probe(local, C.c_void_p(hb.array.ctypes.data), probe_bytes, 1, 0, C.byref(ms))
@@ -448,7 +454,8 @@ def run_c3(args, world, rank, local):
             barrier()
             kinds[name] = {"ms_per_GiB": t_k, "gbps_per_gpu": probe_bytes / t_k / 1e6, "aggregate_gbps": world * probe_bytes / t_k / 1e6}
             hb.free()
-        floor["h2d_1GiB_probe_all_ranks_at_once"] = kinds
+        if kinds:
+            floor["h2d_1GiB_probe_all_ranks_at_once"] = kinds
         # ---- weak-scaling reference on the same box: rank 0 alone, the other GPUs idle ----
         if world > 1:
             if rank == 0:
@@ -520,6 +527,7 @@ def main():
                     help="auto: C2 on one GPU (the configuration the metric is quoted on), C3 (utterance-sharded Syllable Features) "
                          "when launched with more than one rank")
     ap.add_argument("--wc", type=int, default=0, help="C3: allocate the pinned PCM buffer write-combined (cudaHostAllocWriteCombined)")
+    ap.add_argument("--probe-wc", action="store_true", help="C3: also probe the N-rank H2D floor with write-combined pinned memory")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--serial", action="store_true", help="one sub-batch (profiling: full-batch kernel launches)")
