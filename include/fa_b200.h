@@ -39,6 +39,7 @@ extern "C" {
 #endif
 
 #define FA_N_FEATURES 53 /* /root/reference/src/localstore.js:7 (levels 5 and 13 -> 53) */
+#define FA_N_CURVE_FEATURES 23 /* /root/reference/src/localstore.js:7 (level 12 -> 23): make_coeffs @B34527 */
 #define FA_N_UTT_FEATURES 264 /* get_utterance_features, /root/reference/dist/main.js:2@B107983 (level 11) */
 #define FA_ABI_VERSION 1
 #define FA_ALL_UTTS (-1) /* utt_id of the getters: the whole batch, in submission order (utterance ids themselves are >= 0) */
@@ -77,6 +78,7 @@ typedef enum fa_status {
 #define FA_LEVEL_SEG_FEATURES 5
 #define FA_LEVEL_SYL_FORMANTS 10
 #define FA_LEVEL_UTTERANCE 11      /* "Utterance distributions": 264 doubles, cumulative, one row per stored segment */
+#define FA_LEVEL_SYL_CURVES 12     /* "Syllable curves": 23 doubles per syllable (polynomial fits, numeric.uncmin) */
 #define FA_LEVEL_SYL_FEATURES 13
 
 typedef struct fa_config {
@@ -125,7 +127,8 @@ typedef struct fa_syllable {
   int32_t stored_seg;   /* index of the owning stored segment */
   int32_t start;        /* frame offset inside the segment */
   int32_t len;
-  int32_t reserved;
+  int32_t reserved;     /* level 12: 1 when the reference's make_coeffs threw at or before this syllable of the segment (its
+                           row is NaN and was never handed to the callback), else 0 */
 } fa_syllable;
 
 typedef struct fa_counts {
@@ -245,6 +248,12 @@ FA_API int fa_copy_features(fa_handle* h, int64_t utt_id, double* dst, size_t ca
  * utterance, row k = the distribution over stores 0..k -- what the reference passes to its callback after store k; the
  * last row describes the whole utterance.  fa_counts.feature_rows counts these rows at level 11. */
 FA_API int fa_copy_utterance_features(fa_handle* h, int64_t utt_id, double* dst, size_t cap_rows);
+/* Level 12 (make_coeffs @B34527 -> polyfit @B33793 -> numeric.inv / uncmin): rows of 23 doubles, one per syllable, in syllable
+ * order = [4th-degree fit of the energy in dB: 5 coefficients, residual, points | cubic fit of formant column 0: 4, residual,
+ * points | cubic fit of column 3 | linear fit of column 6: 2, residual, points].  Where the reference's numeric would have
+ * thrown, fa_syllable.reserved is 1 and the row is NaN (the reference's try / catch hands the rows made before the throw to
+ * the callback and skips the rest of the segment).  fa_counts.feature_rows counts these rows at level 12. */
+FA_API int fa_copy_curve_features(fa_handle* h, int64_t utt_id, double* dst, size_t cap_rows);
 
 /* Stage-level taps for parity tests (candidate peaks of stage 2: packed lo | hi<<8 | pk<<16 | last<<24). */
 /* ---- batched MLP inference on feature rows (the web app's emotion classifier) -------------------

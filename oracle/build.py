@@ -17,7 +17,7 @@ ROOT = os.path.dirname(HERE)
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(BUILD, "libfa_oracle.so")
 SRC = os.path.join(HERE, "fa_oracle.c")
-DEPS = [SRC] + [os.path.join(ROOT, "include", h) for h in ("fa_b200.h", "fa_jsmath.h", "fa_tables.h")]
+DEPS = [SRC] + [os.path.join(ROOT, "include", h) for h in ("fa_b200.h", "fa_jsmath.h", "fa_tables.h", "fa_curves.h")]
 
 
 def _cpu_has_fma() -> bool:

@@ -31,6 +31,7 @@
 
 #include "fa_b200.h"
 #include "fa_jsmath.h"
+#include "fa_curves.h"
 #include "fa_tables.h"
 
 #define FAO_API __attribute__((visibility("default")))
@@ -289,6 +290,7 @@ struct fao_result {
   float* energy;   /* rows of 3 */
   int n_rows, cap_rows;
   ivec syl_seg, syl_start, syl_len;
+  ivec syl_flag; /* level 12: non-zero where the reference's make_coeffs would have thrown (its row and the later ones of the segment are dropped) */
   dvec features; /* rows of 53: level 5 -> one per stored segment, level 13 -> one per syllable */
   int n_feature_rows;
   /* callback order (P @B28869): indices into seg_ci, in firing order */
@@ -598,7 +600,8 @@ static int sep_syllables(const float* Eg, int len, double vmin, int* starts, int
 static int finalize_segment(fao_state* st, fao_result* R, int n_arg) {
   int len = n_arg - st->no_fm_segs;
   if (!(len > st->seg_min_frames && st->c_started >= 2)) return 0;
-  if (!(st->level == 3 || st->level == 4 || st->level == 5 || st->level == 10 || st->level == 11 || st->level == 13))
+  if (!(st->level == 3 || st->level == 4 || st->level == 5 || st->level == 10 || st->level == 11 || st->level == 12 ||
+        st->level == 13))
     return -1;
   int start = st->current_frame - len;
   int* ranked = (int*)malloc(sizeof(int) * (size_t)(st->n_tr > 0 ? st->n_tr : 1));
@@ -635,11 +638,26 @@ static int finalize_segment(fao_state* st, fao_result* R, int n_arg) {
       dvec_push(&R->st_cs, cs);
       int nsyl = 0;
       ivec_push(&R->st_first_syl, R->syl_seg.n);
-      if (st->level == 10 || st->level == 11 || st->level == 13) {
+      if (st->level == 10 || st->level == 11 || st->level == 12 || st->level == 13) {
         int* ss = (int*)malloc(sizeof(int) * 2 * (size_t)len);
         nsyl = sep_syllables(Eg, len, st->v, ss, ss + len);
+        int thrown = 0;   /* level 12: make_coeffs' try / catch returns the rows made before a throw inside numeric */
         for (int i = 0; i < nsyl; i++) {
           ivec_push(&R->syl_seg, stored); ivec_push(&R->syl_start, ss[i]); ivec_push(&R->syl_len, ss[len + i]);
+          if (st->level == 12) {
+            /* make_coeffs @B34527: one row of 23 per syllable; a syllable the reference would have thrown on (and every later
+             * one of the segment) keeps a NaN row and a non-zero flag */
+            double row[FA_N_CURVE_FEATURES];
+            const int sl = ss[len + i];
+            double* work = (double*)malloc(sizeof(double) * 11 * (size_t)(sl > 0 ? sl : 1));
+            for (int w = 0; w < 4 && !thrown; w++)
+              thrown = fa_curve_fit_one(F + 9 * (size_t)ss[i], Eg + 3 * (size_t)ss[i], sl, w, work, row + fa_curve_slice_offset(w));
+            free(work);
+            if (thrown) for (int q = 0; q < FA_N_CURVE_FEATURES; q++) row[q] = 0.0 / 0.0;
+            for (int q = 0; q < FA_N_CURVE_FEATURES; q++) dvec_push(&R->features, row[q]);
+            ivec_push(&R->syl_flag, thrown);
+            R->n_feature_rows++;
+          }
           if (st->level == 13) {
             double row[FA_N_FEATURES];
             formant_features(F + 9 * (size_t)ss[i], ss[len + i], st->y, st->v, cs, row);
@@ -873,7 +891,7 @@ static void fire_callbacks(fao_result* R, int* processed) {
   while (*processed < R->st_len.n) {
     int e = (*processed)++;
     int fire = 0;
-    if (R->level == 13) fire = R->st_nsyl.d[e] > 0;
+    if (R->level == 13 || R->level == 12) fire = R->st_nsyl.d[e] > 0;   /* p[e].length > 0 (level 12: unless its first fit threw) */
     else if (R->level == 10) fire = R->st_nsyl.d[e] > 0;
     else if (R->level == 5 || R->level == 4) fire = R->st_len.d[e] > 0;
     else if (R->level == 3) fire = 1;
@@ -932,7 +950,7 @@ FAO_API void fao_free(fao_result* R) {
   free(R->tr_y); free(R->seg_start.d); free(R->seg_len.d); free(R->seg_stored.d); free(R->st_len.d);
   free(R->st_row_off.d); free(R->st_nsyl.d); free(R->st_first_syl.d); free(R->st_y.d); free(R->st_v.d);
   free(R->st_cs.d); free(R->formants); free(R->energy); free(R->syl_seg.d); free(R->syl_start.d);
-  free(R->syl_len.d); free(R->features.d); free(R->cb_si.d); free(R->utt_rows.d);
+  free(R->syl_len.d); free(R->syl_flag.d); free(R->features.d); free(R->cb_si.d); free(R->utt_rows.d);
   free(R);
 }
 
@@ -960,7 +978,8 @@ FAO_API void fao_get_formants(const fao_result* R, float* F9, float* E3) {
 }
 FAO_API void fao_get_syllables(const fao_result* R, fa_syllable* dst) {
   for (int i = 0; i < R->syl_seg.n; i++) {
-    dst[i].stored_seg = R->syl_seg.d[i]; dst[i].start = R->syl_start.d[i]; dst[i].len = R->syl_len.d[i]; dst[i].reserved = 0;
+    dst[i].stored_seg = R->syl_seg.d[i]; dst[i].start = R->syl_start.d[i]; dst[i].len = R->syl_len.d[i];
+    dst[i].reserved = i < R->syl_flag.n ? R->syl_flag.d[i] : 0;
   }
 }
 FAO_API void fao_get_features(const fao_result* R, double* dst) {

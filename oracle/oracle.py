@@ -147,7 +147,7 @@ def analyze_frames(cfg: FaConfig, frames: np.ndarray, trace: bool = False) -> An
         syl = np.zeros(nsyl, SYL_DTYPE)
         if nsyl:
             _lib.fao_get_syllables(R, syl.ctypes.data_as(C.POINTER(FaSyllable)))
-        feat = np.zeros((nfeat, N_FEATURES), np.float64)
+        feat = np.zeros((nfeat, 23 if cfg.output_level == 12 else N_FEATURES), np.float64)
         if nfeat:
             _lib.fao_get_features(R, _p(feat, _f64p))
         cb = np.zeros(ncb, np.int32)

@@ -25,6 +25,8 @@ from webspeechanalyzer_b200.engine import UtteranceResult  # noqa: E402
 
 DOC = json.load(open(os.path.join(GOLDEN, "ref_js.json")))
 CASES = {c["name"]: c for c in DOC["cases"]}
+DOC12 = json.load(open(os.path.join(GOLDEN, "ref_js_l12.json")))      # level 12 (make_coeffs / polyfit / numeric), own fixture
+CASES12 = {c["name"]: c for c in DOC12["cases"]}
 _wav = {}
 
 
@@ -69,6 +71,11 @@ def check_against_reference(case, an, level, step):
         if level == 13:
             assert np.array_equal(np.array(mine[3], np.float64), np.array(ref[3], np.float64), equal_nan=True)
             assert all(len(r) == 53 for r in mine[3])
+        elif level == 12:
+            # 23 numbers per syllable: coefficients from numeric.uncmin, residual, point count -- doubles bit for bit
+            assert [len(r) for r in mine[3]] == [len(r) for r in ref[3]] and all(len(r) == 23 for r in mine[3])
+            a, b = np.array(mine[3], np.float64), np.array(ref[3], np.float64)
+            assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), np.abs(a - b).max()
         elif level == 5:
             assert np.array_equal(np.array(mine[3], np.float64), np.array(ref[3], np.float64), equal_nan=True) and len(mine[3]) == 53
         elif level == 11:
@@ -92,6 +99,18 @@ def test_oracle_matches_reference_js(name):
     assert fr.shape == (case["frames"], case["bands"]) and sha(fr) == case["frames_sha"]   # same input as the reference saw
     an = oracle.analyze_frames(cfg, fr)
     check_against_reference(case, an, cfg.output_level, cfg.window_step_ms)
+
+
+@pytest.mark.parametrize("name", list(CASES12))
+def test_oracle_level12_matches_reference_js(name):
+    """make_coeffs @B34527 / polyfit @B33793 with numeric.inv / uncmin / gradient (include/fa_curves.h) against what the
+    reference's own code returned to its callback."""
+    case = CASES12[name]
+    cfg = FaConfig.default(**case["kwargs"])
+    fr = frames_for(case["input"], cfg)
+    assert fr.shape == (case["frames"], case["bands"]) and sha(fr) == case["frames_sha"]
+    an = oracle.analyze_frames(cfg, fr)
+    check_against_reference(case, an, 12, cfg.window_step_ms)
 
 
 def test_fixture_covers_the_quirks():

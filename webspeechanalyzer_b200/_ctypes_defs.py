@@ -5,6 +5,7 @@ import ctypes as C
 
 N_FEATURES = 53  # /root/reference/src/localstore.js:7
 SPECTRUM_F32, SPECTRUM_U8, SPECTRUM_F16 = 0, 1, 2   # fa_config.spectrum_format
+N_CURVE_FEATURES = 23  # /root/reference/src/localstore.js:7 (level 12): make_coeffs @B34527
 N_UTT_FEATURES = 264  # get_utterance_features, /root/reference/dist/main.js:2@B107983 (level 11)
 
 

@@ -127,12 +127,23 @@ def segment_callbacks(level: int, step_ms: float, labels: list, res) -> list[tup
     for e, s in enumerate(stored):
         ci = segs[e]
         rows = res.formants[s["row_offset"]: s["row_offset"] + s["len"]]
-        if level in (13, 10):
+        if level in (13, 12, 10):
             syl = res.syllables[s["first_syllable"]: s["first_syllable"] + s["n_syllables"]]
             if len(syl) == 0:
                 continue
+            if level == 12:
+                # make_coeffs @B34527 returns the rows made before numeric threw (try / catch around the loop); P() fires when
+                # there is at least one, with the time stamps of ALL the segment's syllables (j(e) @B31114)
+                f0 = int(s["first_syllable"])
+                bad = [k for k, y in enumerate(syl) if int(y["reserved"])]
+                n_ok = bad[0] if bad else len(syl)
+                if n_ok == 0:
+                    continue
+                payload = [list(map(float, r)) for r in res.features[f0: f0 + n_ok]]
             times = [[to_fixed3((int(ci["start"]) + int(y["start"])) * step), to_fixed3((int(y["len"]) + 1) * step)] for y in syl]
-            if level == 13:
+            if level == 12:
+                pass
+            elif level == 13:
                 # feature rows of an utterance are in syllable order
                 f0 = int(s["first_syllable"])
                 payload = [list(map(float, r)) for r in res.features[f0: f0 + len(syl)]]

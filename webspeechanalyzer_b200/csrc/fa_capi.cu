@@ -155,9 +155,12 @@ struct fa_handle {
                             // 2.79 GB through HBM and needs no 4 KB-per-frame magnitude buffer when no dB rows are wanted
   bool use_fused() const { return k1_fused != 0 && N == 2048 && chunk_frames <= 0 && !frames_mode; }
   DevBuf g_segs, g_syls, g_formants, g_energy, g_features;
+  DevBuf d_curve_work, d_curve_status;   // level 12 (K8)
   int n_weights = 0;
   long long track_total = 0, urow_total = 0;
-  int feat_width() const { return cfg.output_level == FA_LEVEL_UTTERANCE ? FA_N_UTT_FEATURES : FA_N_FEATURES; }
+  int feat_width() const {
+    return cfg.output_level == FA_LEVEL_UTTERANCE ? FA_N_UTT_FEATURES : cfg.output_level == FA_LEVEL_SYL_CURVES ? FA_N_CURVE_FEATURES : FA_N_FEATURES;
+  }
   bool uploaded = false, ran = false, downloaded = false, want_spec = false, from_host = false;
   bool frames_mode = false;    // the batch was submitted as uint32 frames (fa_submit_frames): the spectrum stage is skipped
   HostBuf h_frames;            // pinned staging of submitted frames, row order
@@ -186,12 +189,12 @@ int fail(fa_handle* h, int code, const char* what, cudaError_t e = cudaSuccess) 
 
 bool level_supported(int lvl) {
   return lvl == FA_LEVEL_BARS || lvl == FA_LEVEL_SPECTRUM || lvl == FA_LEVEL_FORMANTS || lvl == FA_LEVEL_SEG_FEATURES ||
-         lvl == FA_LEVEL_SYL_FORMANTS || lvl == FA_LEVEL_UTTERANCE || lvl == FA_LEVEL_SYL_FEATURES;
+         lvl == FA_LEVEL_SYL_FORMANTS || lvl == FA_LEVEL_UTTERANCE || lvl == FA_LEVEL_SYL_CURVES || lvl == FA_LEVEL_SYL_FEATURES;
 }
 
 int validate(const fa_config* c, std::string* why) {
   if (!fa_tab_valid_fft(c->fft_size)) { *why = "fft_size must be a power of two in [256, 16384]"; return FA_ERR_UNSUPPORTED; }
-  if (!level_supported(c->output_level)) { *why = "output_level not supported (levels 1, 2, 4, 5, 10, 11, 13)"; return FA_ERR_UNSUPPORTED; }
+  if (!level_supported(c->output_level)) { *why = "output_level not supported (levels 1, 2, 4, 5, 10, 11, 12, 13)"; return FA_ERR_UNSUPPORTED; }
   if (c->spec_type < 1 || c->spec_type > 3) { *why = "Invalid reset_nodes config"; return FA_ERR_INVALID_ARG; }
   const int B = fa_tab_bands(c);
   if (B < 8 || B > FA_MAX_BANDS) { *why = "Invalid spec_bands"; return FA_ERR_INVALID_ARG; }
@@ -351,7 +354,7 @@ int fa_destroy(fa_handle* h) {
                     &h->d_win, &h->d_tw, &h->d_tws, &h->d_ws, &h->d_bmi, &h->d_bmw, &h->d_emph, &h->d_spill, &h->d_trkbase, &h->d_trk_i,
                     &h->d_trk_d, &h->d_trk_slot, &h->d_pt_i, &h->d_pt_e, &h->d_rows, &h->d_rowlist, &h->d_segs, &h->d_syls,
                     &h->d_formants, &h->d_energy, &h->d_features, &h->d_counts, &h->d_off, &h->g_segs, &h->g_syls,
-                    &h->g_formants, &h->g_energy, &h->g_features, &h->d_chunks, &h->d_state, &h->d_specdb, &h->d_specq, &h->d_fix, &h->d_cchunks, &h->d_cstate, &h->d_frT, &h->d_frk, &h->d_frthr, &h->d_frctl, &h->d_frv, &h->d_epochs, &h->d_work, &h->d_k3q})
+                    &h->g_formants, &h->g_energy, &h->g_features, &h->d_chunks, &h->d_state, &h->d_specdb, &h->d_specq, &h->d_fix, &h->d_cchunks, &h->d_cstate, &h->d_frT, &h->d_frk, &h->d_frthr, &h->d_frctl, &h->d_frv, &h->d_epochs, &h->d_work, &h->d_k3q, &h->d_curve_work, &h->d_curve_status})
     b->release();
   for (HostBuf* b : {&h->h_pcm, &h->h_frames, &h->h_meta, &h->h_counts, &h->h_off, &h->h_segs, &h->h_syls, &h->h_formants, &h->h_energy,
                      &h->h_features})
@@ -736,8 +739,12 @@ static int prepare(fa_handle* h) {
     FA_CUDA(h->d_syls.reserve((Fz + nz) * sizeof(fa_syllable)));
     FA_CUDA(h->d_formants.reserve(Fz * 9 * sizeof(float)));
     FA_CUDA(h->d_energy.reserve(Fz * 3 * sizeof(float)));
-    if (h->cfg.output_level == 5 || h->cfg.output_level == 13)
-      FA_CUDA(h->d_features.reserve((Fz + nz) * FA_N_FEATURES * sizeof(double)));
+    if (h->cfg.output_level == 5 || h->cfg.output_level == 13 || h->cfg.output_level == FA_LEVEL_SYL_CURVES)
+      FA_CUDA(h->d_features.reserve((Fz + nz) * h->feat_width() * sizeof(double)));
+    if (h->cfg.output_level == FA_LEVEL_SYL_CURVES) {
+      FA_CUDA(h->d_curve_work.reserve(Fz * 34 * sizeof(double)));
+      FA_CUDA(h->d_curve_status.reserve((Fz + nz) * 4 * sizeof(int)));
+    }
     if (h->cfg.output_level == FA_LEVEL_UTTERANCE) {
       FA_CUDA(h->d_features.reserve((size_t)ub * FA_N_UTT_FEATURES * sizeof(double)));
       FA_CUDA(h->g_features.reserve((size_t)ub * FA_N_UTT_FEATURES * sizeof(double)));
@@ -748,8 +755,8 @@ static int prepare(fa_handle* h) {
     FA_CUDA(h->g_syls.reserve((Fz + nz) * sizeof(fa_syllable)));
     FA_CUDA(h->g_formants.reserve(Fz * 9 * sizeof(float)));
     FA_CUDA(h->g_energy.reserve(Fz * 3 * sizeof(float)));
-    if (h->cfg.output_level == 5 || h->cfg.output_level == 13)
-      FA_CUDA(h->g_features.reserve((Fz + nz) * FA_N_FEATURES * sizeof(double)));
+    if (h->cfg.output_level == 5 || h->cfg.output_level == 13 || h->cfg.output_level == FA_LEVEL_SYL_CURVES)
+      FA_CUDA(h->g_features.reserve((Fz + nz) * h->feat_width() * sizeof(double)));
   }
   if (h->ctl_chunk > 0 && h->cfg.output_level >= 3) {
     const int CH = h->ctl_chunk;
@@ -1002,6 +1009,16 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
       // rows of one utterance are spread over `row_slices` CTAs (a one-hour stream has ~2000 rows in ONE utterance)
       fp.row_slices = (int)std::min<long long>(64, std::max<long long>(1, (sb.r1 - sb.r0) / std::max(1, sb.u1 - sb.u0) / 256));
       FA_CUDA(fa_launch_features(fp, s3, &h->launches));
+    }
+    if (c.output_level == FA_LEVEL_SYL_CURVES) {
+      FaCurveParams cp;
+      cp.frame_off = meta + 2 * n; cp.n_utt = n; cp.utt_begin = sb.u0; cp.utt_count = sb.u1 - sb.u0;
+      cp.segs = g.segs; cp.n_segs = g.n_segs; cp.syls = g.syls; cp.n_syls = g.n_syls; cp.formants = g.formants; cp.energy = g.energy;
+      cp.epochs = h->k3_mode == 1 ? h->d_epochs.as<FaEpoch>() : nullptr;
+      cp.row_slices = (int)std::min<long long>(64, std::max<long long>(1, (sb.r1 - sb.r0) / std::max(1, sb.u1 - sb.u0) / 2048));
+      cp.work = h->d_curve_work.as<double>(); cp.status = h->d_curve_status.as<int>();
+      cp.rows = h->d_features.as<double>(); cp.n_feat = cnt + 4 * n;
+      FA_CUDA(fa_launch_curves(cp, s3, &h->launches));
     }
     if (c.output_level == FA_LEVEL_UTTERANCE) {
       FaUtteranceParams up;
@@ -1394,7 +1411,15 @@ int fa_copy_features(fa_handle* h, int64_t utt_id, double* dst, size_t cap) {
   if (!h) return FA_ERR_INVALID_ARG;
   if (h->cfg.output_level == FA_LEVEL_UTTERANCE)
     return fail(h, FA_ERR_INVALID_ARG, "level 11 rows have 264 entries: use fa_copy_utterance_features");
+  if (h->cfg.output_level == FA_LEVEL_SYL_CURVES)
+    return fail(h, FA_ERR_INVALID_ARG, "level 12 rows have 23 entries: use fa_copy_curve_features");
   return copy_dense(h, utt_id, 3, 4, FA_N_FEATURES * sizeof(double), dst, cap);
+}
+
+int fa_copy_curve_features(fa_handle* h, int64_t utt_id, double* dst, size_t cap) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  if (h->cfg.output_level != FA_LEVEL_SYL_CURVES) return fail(h, FA_ERR_INVALID_ARG, "syllable curves need output_level 12");
+  return copy_dense(h, utt_id, 3, 4, FA_N_CURVE_FEATURES * sizeof(double), dst, cap);
 }
 
 int fa_copy_utterance_features(fa_handle* h, int64_t utt_id, double* dst, size_t cap) {

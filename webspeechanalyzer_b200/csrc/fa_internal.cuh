@@ -171,6 +171,22 @@ struct FaFeatureParams {
   int* n_feat;                        // [n_utt]
 };
 
+// K8 (level 12): 23-dim polynomial-curve rows, one per syllable (fa_curves.cu)
+struct FaCurveParams {
+  const long long* frame_off;
+  int n_utt;
+  int utt_begin, utt_count;
+  const fa_segment* segs; const int* n_segs;
+  fa_syllable* syls; const int* n_syls;  // .reserved is set where the reference's make_coeffs would have thrown
+  const float* formants; const float* energy;
+  const FaEpoch* epochs;              // see FaFeatureParams
+  int row_slices;                     // CTAs per utterance (grid.y)
+  double* work;                       // [F_total][34] powers / ordinates of the four fits of the syllable that owns the row
+  int* status;                        // [(F_total + n_utt)][4] FA_CURVE_* of every fit
+  double* rows;                       // [(F_total + n_utt)][23] per-utterance rows at base frame_off[u] + u
+  int* n_feat;                        // [n_utt]
+};
+
 // K6 (level 11): cumulative 264-dim utterance distributions, one row per stored segment
 struct FaUtteranceParams {
   const long long* frame_off;
@@ -210,5 +226,6 @@ int fa_mlp_in_dim(const fa_mlp* m);
 int fa_mlp_device(const fa_mlp* m);
 int fa_mlp_out_dim(const fa_mlp* m);
 cudaError_t fa_launch_utterance(const FaUtteranceParams& p, cudaStream_t s, int* launches);
+cudaError_t fa_launch_curves(const FaCurveParams& p, cudaStream_t s, int* launches);
 cudaError_t fa_launch_prefix(const FaGatherArgs& a, cudaStream_t s, int* launches);
 cudaError_t fa_launch_gather(const FaGatherArgs& a, cudaStream_t s, int* launches);

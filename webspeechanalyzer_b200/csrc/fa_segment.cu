@@ -568,7 +568,7 @@ __device__ __noinline__ int finalize_fast(const FaSegmentParams p, WarpShared& S
   seg.first_syllable = st.n_syls;
   // sep_syllables @B34757
   int nsyl = 0;
-  if (p.level == 10 || p.level == 11 || p.level == 13) {
+  if (p.level == 10 || p.level == 11 || p.level == 12 || p.level == 13) {
     int sstart = -1, quiet = 0, loud = 0;
     for (int e0 = 0; e0 < len; e0 += 32) {
       const int e = e0 + lane;
@@ -753,7 +753,7 @@ __device__ __noinline__ int finalize_segment(const FaSegmentParams p, ScanState&
   seg.first_syllable = st.n_syls;
   // sep_syllables @B34757
   int nsyl = 0;
-  if (p.level == 10 || p.level == 11 || p.level == 13) {
+  if (p.level == 10 || p.level == 11 || p.level == 12 || p.level == 13) {
     int sstart = -1, quiet = 0, loud = 0;
     for (int e0 = 0; e0 < len; e0 += 32) {
       const int e = e0 + lane;

@@ -8,7 +8,7 @@ import numpy as np
 
 from . import _capi
 from ._capi import FaError
-from ._ctypes_defs import FaConfig, FaCounts, N_FEATURES, N_UTT_FEATURES
+from ._ctypes_defs import FaConfig, FaCounts, N_CURVE_FEATURES, N_FEATURES, N_UTT_FEATURES
 
 SEG_DTYPE = np.dtype([("start", "<i4"), ("len", "<i4"), ("stored", "<i4"), ("n_syllables", "<i4"),
                       ("first_syllable", "<i4"), ("row_offset", "<i4"), ("ymax", "<f8"), ("vmin", "<f8"),
@@ -221,6 +221,8 @@ class Engine:
         c = self.counts()
         if self.cfg.output_level == 11:
             return self._rows(self._lib.fa_copy_utterance_features, None, c["feature_rows"], (N_UTT_FEATURES,), np.float64)
+        if self.cfg.output_level == 12:
+            return self._rows(self._lib.fa_copy_curve_features, None, c["feature_rows"], (N_CURVE_FEATURES,), np.float64)
         return self._rows(self._lib.fa_copy_features, None, c["feature_rows"], (N_FEATURES,), np.float64)
 
     def _rows(self, fn, utt_id, nrows, shape_tail, dtype):
@@ -266,5 +268,8 @@ class Engine:
         if self.cfg.output_level == 11:
             ut = self._rows(L.fa_copy_utterance_features, utt_id, c["feature_rows"], (N_UTT_FEATURES,), np.float64)
             return UtteranceResult(c, segs, fm, en, sy, np.zeros((0, N_FEATURES)), ut)
-        ft = self._rows(L.fa_copy_features, utt_id, c["feature_rows"], (N_FEATURES,), np.float64)
+        if self.cfg.output_level == 12:
+            ft = self._rows(L.fa_copy_curve_features, utt_id, c["feature_rows"], (N_CURVE_FEATURES,), np.float64)
+        else:
+            ft = self._rows(L.fa_copy_features, utt_id, c["feature_rows"], (N_FEATURES,), np.float64)
         return UtteranceResult(c, segs, fm, en, sy, ft)
