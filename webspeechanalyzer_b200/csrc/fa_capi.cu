@@ -329,7 +329,7 @@ int fa_create(const fa_config* cfg, int device, fa_handle** out) {
   if (const char* ev = getenv("FA_K3_WARPS")) { const int v = atoi(ev); if (v >= 1 && v <= 4) h->k3_warps = v; }
   if (const char* ev = getenv("FA_K3_REGS")) h->k3_regs = atoi(ev);
   if (getenv("FA_K3_FINALIZE_HBM")) h->k3_finalize_smem = 0;
-  if (const char* ev = getenv("FA_K2_STAGED")) h->k2_staged = atoi(ev) != 0;
+  if (const char* ev = getenv("FA_K2_IMPL")) h->k2_staged = atoi(ev);   // -1: the direct kernel (A/B), 0: v2
   if (getenv("FA_DEBUG_SYNC")) h->debug_sync = true;
   if (const char* ev = getenv("FA_K1_FUSED")) h->k1_fused = atoi(ev) != 0;
 
@@ -938,7 +938,7 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
     FaPeaksParams pp;
     pp.frames = h->d_frames.as<uint32_t>(); pp.B = h->B; pp.maxp = h->maxp; pp.n_frames = sb.r1 - sb.r0; pp.row_begin = sb.r0;
     pp.cand = h->d_cand.as<FaCand>(); pp.ncand = h->d_ncand.as<int>(); pp.gsum = h->d_gsum.as<double>();
-    pp.staged = h->k2_staged;   // measured slower: knob only
+    pp.staged = h->k2_staged;
     FA_CUDA(fa_launch_peaks(pp, s, &h->launches));
     if (h->debug_sync) FA_CUDA(cudaStreamSynchronize(s));
   }
