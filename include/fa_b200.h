@@ -131,6 +131,28 @@ typedef struct fa_syllable {
                            row is NaN and was never handed to the callback), else 0 */
 } fa_syllable;
 
+/* Level 3 ("Segments"): the reference hands its callback the ranked formant tracks themselves (get_ranked_formants @B35670:
+ * arrays of 18 fields, accumulate_fm @B35952).  Here: one fa_track per ranked track, in rank order, segment after segment, and
+ * its points in time order.  The 18 fields of the reference's track array follow from the points (webspeechanalyzer_b200/api.py
+ * track_arrays): [0] / [1] / [2] = [3] / [5] / [6] = lo / hi / frame / bin / amp of the LAST point, [4] the slope of the last
+ * (up to four) bins, [7]..[12] the six point lists, [13] sum of the energies, [14] n_points, [15] sum of energy * bin, [16] 0,
+ * [17] sum of (hi - lo + 1).  At level 3 fa_segment.n_syllables / first_syllable count and locate the segment's tracks,
+ * fa_segment.row_offset its first point; fa_counts.syllables / formant_rows count the utterance's tracks / points. */
+typedef struct fa_track {
+  int32_t stored_seg;   /* index of the owning stored segment */
+  int32_t first_point;  /* index of its first point in the utterance's point table */
+  int32_t n_points;     /* [14] */
+  int32_t reserved;
+} fa_track;
+
+typedef struct fa_track_point {
+  int32_t frame;        /* [7]: the frame label c_ci inside the segment (the first one may be stale: quirk 1) */
+  int16_t lo, hi, bin;  /* [8] [9] [10]: merged bounds and the loudest merged peak */
+  int16_t reserved;
+  uint32_t amp;         /* [11]: amplitude of the FIRST merged peak (quirk 8) */
+  double energy;        /* [12]: sum of the frame over [lo, hi] (exact integer) */
+} fa_track_point;
+
 typedef struct fa_counts {
   int64_t samples;
   int32_t sample_rate;
@@ -244,6 +266,9 @@ FA_API int fa_copy_formants(fa_handle* h, int64_t utt_id, float* dst, size_t cap
 FA_API int fa_copy_energy(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows);        /* rows of 3 float32 */
 FA_API int fa_copy_syllables(fa_handle* h, int64_t utt_id, fa_syllable* dst, size_t cap_rows);
 FA_API int fa_copy_features(fa_handle* h, int64_t utt_id, double* dst, size_t cap_rows);     /* rows of 53 doubles */
+/* Level 3 (P() @B28869 / O() @B27088, level-3 branches): the points of the ranked tracks; their fa_track headers come from
+ * fa_copy_syllables (same 16-byte layout), fa_counts.syllables / formant_rows count tracks / points.  See fa_track. */
+FA_API int fa_copy_track_points(fa_handle* h, int64_t utt_id, fa_track_point* dst, size_t cap_rows);
 /* Level 11 (get_utterance_features @B107983, called from P() @B28869): rows of 264 doubles, one per stored segment of the
  * utterance, row k = the distribution over stores 0..k -- what the reference passes to its callback after store k; the
  * last row describes the whole utterance.  fa_counts.feature_rows counts these rows at level 11. */

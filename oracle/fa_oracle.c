@@ -252,7 +252,7 @@ typedef struct {
   int last_bin;
   double last_amp;
   ivec frames, los, his, bins;
-  dvec energies;
+  dvec energies, amps;
   double sum_e, sum_eb;
   int count, sum_span;
 } fao_track;
@@ -293,6 +293,10 @@ struct fao_result {
   ivec syl_flag; /* level 12: non-zero where the reference's make_coeffs would have thrown (its row and the later ones of the segment are dropped) */
   dvec features; /* rows of 53: level 5 -> one per stored segment, level 13 -> one per syllable */
   int n_feature_rows;
+  /* level 3: the ranked tracks of every stored segment (array s) and their points, in rank / point order */
+  ivec trk_seg, trk_first, trk_n;
+  ivec pt_frame, pt_lo, pt_hi, pt_bin;
+  dvec pt_amp, pt_e;
   /* callback order (P @B28869): indices into seg_ci, in firing order */
   ivec cb_si;
   /* level 11: one 264-dim row per callback = get_utterance_features(u, h) over the stores that exist at that time */
@@ -302,7 +306,7 @@ struct fao_result {
 };
 typedef struct fao_result fao_result;
 
-static void track_free(fao_track* t) { free(t->frames.d); free(t->los.d); free(t->his.d); free(t->bins.d); free(t->energies.d); }
+static void track_free(fao_track* t) { free(t->frames.d); free(t->los.d); free(t->his.d); free(t->bins.d); free(t->energies.d); free(t->amps.d); }
 
 /* clear_fm @B35919 */
 static void clear_fm(fao_state* st) {
@@ -395,7 +399,7 @@ static void accumulate_fm(fao_state* st, const uint32_t* e, const fao_peak* pk, 
       else if (h == 1) t->velocity = (double)(o_bin - bn[h - 1]);
       t->lo = lo; t->hi = hi; t->frame = n; t->last_frame = n; t->last_bin = o_bin; t->last_amp = amp;
       ivec_push(&t->frames, n); ivec_push(&t->los, lo); ivec_push(&t->his, hi); ivec_push(&t->bins, o_bin);
-      dvec_push(&t->energies, E);
+      dvec_push(&t->energies, E); dvec_push(&t->amps, amp);
       t->sum_e += E; t->count += 1; t->sum_eb += E * (double)o_bin; t->sum_span += hi - lo + 1;
       st->s_energy -= E;
       st->c_energy += E;
@@ -411,7 +415,7 @@ static void accumulate_fm(fao_state* st, const uint32_t* e, const fao_peak* pk, 
       fao_track* t = track_new(st);
       t->lo = lo; t->hi = hi; t->frame = n; t->last_frame = n; t->velocity = 0; t->last_bin = i; t->last_amp = amp;
       ivec_push(&t->frames, n); ivec_push(&t->los, lo); ivec_push(&t->his, hi); ivec_push(&t->bins, i);
-      dvec_push(&t->energies, E);
+      dvec_push(&t->energies, E); dvec_push(&t->amps, amp);
       t->sum_e = E; t->count = 1; t->sum_eb = E * (double)i; t->sum_span = hi - lo + 1;
     }
   }
@@ -680,8 +684,17 @@ static int finalize_segment(fao_state* st, fao_result* R, int n_arg) {
     /* level 3: raw ranked tracks only; record the segment with an empty store entry */
     int stored = R->st_len.n;
     R->seg_stored.d[si] = stored;
-    ivec_push(&R->st_len, 0); ivec_push(&R->st_row_off, R->n_rows); dvec_push(&R->st_y, st->y); dvec_push(&R->st_v, st->v);
-    dvec_push(&R->st_cs, st->c_energy / st->s_energy); ivec_push(&R->st_first_syl, R->syl_seg.n); ivec_push(&R->st_nsyl, 0);
+    ivec_push(&R->st_len, 0); ivec_push(&R->st_row_off, R->pt_frame.n); dvec_push(&R->st_y, st->y); dvec_push(&R->st_v, st->v);
+    dvec_push(&R->st_cs, st->c_energy / st->s_energy); ivec_push(&R->st_first_syl, R->trk_seg.n); ivec_push(&R->st_nsyl, nr);
+    /* s.push(get_ranked_formants()): the track arrays themselves (18 fields, @B35952), kept here as headers + points */
+    for (int r = 0; r < nr; r++) {
+      const fao_track* t = &st->tr[ranked[r]];
+      ivec_push(&R->trk_seg, stored); ivec_push(&R->trk_first, R->pt_frame.n); ivec_push(&R->trk_n, t->count);
+      for (int i = 0; i < t->count; i++) {
+        ivec_push(&R->pt_frame, t->frames.d[i]); ivec_push(&R->pt_lo, t->los.d[i]); ivec_push(&R->pt_hi, t->his.d[i]);
+        ivec_push(&R->pt_bin, t->bins.d[i]); dvec_push(&R->pt_amp, t->amps.d[i]); dvec_push(&R->pt_e, t->energies.d[i]);
+      }
+    }
   }
   free(ranked);
   return rc;
@@ -894,7 +907,7 @@ static void fire_callbacks(fao_result* R, int* processed) {
     if (R->level == 13 || R->level == 12) fire = R->st_nsyl.d[e] > 0;   /* p[e].length > 0 (level 12: unless its first fit threw) */
     else if (R->level == 10) fire = R->st_nsyl.d[e] > 0;
     else if (R->level == 5 || R->level == 4) fire = R->st_len.d[e] > 0;
-    else if (R->level == 3) fire = 1;
+    else if (R->level == 3) fire = R->st_nsyl.d[e] > 0;   /* s[e].length > 0: at least one ranked track */
     if (fire) ivec_push(&R->cb_si, e);
   }
 }
@@ -951,6 +964,8 @@ FAO_API void fao_free(fao_result* R) {
   free(R->st_row_off.d); free(R->st_nsyl.d); free(R->st_first_syl.d); free(R->st_y.d); free(R->st_v.d);
   free(R->st_cs.d); free(R->formants); free(R->energy); free(R->syl_seg.d); free(R->syl_start.d);
   free(R->syl_len.d); free(R->syl_flag.d); free(R->features.d); free(R->cb_si.d); free(R->utt_rows.d);
+  free(R->trk_seg.d); free(R->trk_first.d); free(R->trk_n.d); free(R->pt_frame.d); free(R->pt_lo.d); free(R->pt_hi.d);
+  free(R->pt_bin.d); free(R->pt_amp.d); free(R->pt_e.d);
   free(R);
 }
 
@@ -958,6 +973,19 @@ FAO_API void fao_free(fao_result* R) {
 FAO_API void fao_counts(const fao_result* R, int* out /*[8]*/) {
   out[0] = R->F; out[1] = R->seg_start.n; out[2] = R->st_len.n; out[3] = R->n_rows; out[4] = R->syl_seg.n;
   out[5] = R->n_feature_rows; out[6] = R->cb_si.n; out[7] = R->B;
+}
+/* level 3: [0] ranked tracks, [1] their points */
+FAO_API void fao_track_counts(const fao_result* R, int* out /*[2]*/) { out[0] = R->trk_seg.n; out[1] = R->pt_frame.n; }
+FAO_API void fao_get_tracks(const fao_result* R, fa_track* dst) {
+  for (int i = 0; i < R->trk_seg.n; i++) {
+    dst[i].stored_seg = R->trk_seg.d[i]; dst[i].first_point = R->trk_first.d[i]; dst[i].n_points = R->trk_n.d[i]; dst[i].reserved = 0;
+  }
+}
+FAO_API void fao_get_track_points(const fao_result* R, fa_track_point* dst) {
+  for (int i = 0; i < R->pt_frame.n; i++) {
+    dst[i].frame = R->pt_frame.d[i]; dst[i].lo = (int16_t)R->pt_lo.d[i]; dst[i].hi = (int16_t)R->pt_hi.d[i];
+    dst[i].bin = (int16_t)R->pt_bin.d[i]; dst[i].reserved = 0; dst[i].amp = (uint32_t)R->pt_amp.d[i]; dst[i].energy = R->pt_e.d[i];
+  }
 }
 FAO_API void fao_track_stats(const fao_result* R, int* out /*[2]*/) { out[0] = R->max_live; out[1] = R->max_peaks; }
 FAO_API void fao_get_segments(const fao_result* R, fa_segment* dst) {

@@ -35,6 +35,9 @@ _lib.fao_track_stats.argtypes = [C.c_void_p, _i32p]
 _lib.fao_get_formants.argtypes = [C.c_void_p, _f32p, _f32p]
 _lib.fao_get_syllables.argtypes = [C.c_void_p, C.POINTER(FaSyllable)]
 _lib.fao_get_features.argtypes = [C.c_void_p, _f64p]
+_lib.fao_track_counts.argtypes = [C.c_void_p, _i32p]
+_lib.fao_get_tracks.argtypes = [C.c_void_p, C.c_void_p]
+_lib.fao_get_track_points.argtypes = [C.c_void_p, C.c_void_p]
 _lib.fao_get_callbacks.argtypes = [C.c_void_p, _i32p]
 _lib.fao_utterance_rows.argtypes = [C.c_void_p]
 _lib.fao_get_utterance_features.argtypes = [C.c_void_p, _f64p]
@@ -115,6 +118,7 @@ class Analysis:
     utterance: np.ndarray = None    # [callbacks, 264] float64 (level 11)
     max_live_tracks: int = 0        # most tracks still matchable after one accumulate_fm call (GPU slot demand)
     max_peaks: int = 0              # most accepted peaks in one accumulate_fm call
+    track_points: np.ndarray = None  # level 3: TRACK_POINT_DTYPE rows; `syllables` then holds the fa_track headers
 
     @property
     def seg_ci(self):
@@ -125,7 +129,9 @@ SEG_DTYPE = np.dtype([("start", "<i4"), ("len", "<i4"), ("stored", "<i4"), ("n_s
                       ("first_syllable", "<i4"), ("row_offset", "<i4"), ("ymax", "<f8"), ("vmin", "<f8"),
                       ("cs_ratio", "<f8")])
 SYL_DTYPE = np.dtype([("stored_seg", "<i4"), ("start", "<i4"), ("len", "<i4"), ("reserved", "<i4")])
-assert SEG_DTYPE.itemsize == C.sizeof(FaSegment) and SYL_DTYPE.itemsize == C.sizeof(FaSyllable)
+TRACK_POINT_DTYPE = np.dtype([("frame", "<i4"), ("lo", "<i2"), ("hi", "<i2"), ("bin", "<i2"), ("reserved", "<i2"), ("amp", "<u4"),
+                              ("energy", "<f8")], align=True)
+assert SEG_DTYPE.itemsize == C.sizeof(FaSegment) and SYL_DTYPE.itemsize == C.sizeof(FaSyllable) and TRACK_POINT_DTYPE.itemsize == 24
 
 
 def analyze_frames(cfg: FaConfig, frames: np.ndarray, trace: bool = False) -> Analysis:
@@ -165,7 +171,16 @@ def analyze_frames(cfg: FaConfig, frames: np.ndarray, trace: bool = False) -> An
             _lib.fao_get_utterance_features(R, _p(utt, _f64p))
         ts = (C.c_int * 2)()
         _lib.fao_track_stats(R, ts)
-        return Analysis(F, B, segs, Fm, Eg, syl, feat, cb, tr, utt, int(ts[0]), int(ts[1]))
+        pts = None
+        if cfg.output_level == 3:      # the ranked tracks (headers in the fa_syllable layout) and their points
+            tc = (C.c_int * 2)()
+            _lib.fao_track_counts(R, tc)
+            syl = np.zeros(tc[0], SYL_DTYPE)
+            pts = np.zeros(tc[1], TRACK_POINT_DTYPE)
+            if tc[0]:
+                _lib.fao_get_tracks(R, syl.ctypes.data)
+                _lib.fao_get_track_points(R, pts.ctypes.data)
+        return Analysis(F, B, segs, Fm, Eg, syl, feat, cb, tr, utt, int(ts[0]), int(ts[1]), pts)
     finally:
         _lib.fao_free(R)
 

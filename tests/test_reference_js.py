@@ -27,6 +27,8 @@ DOC = json.load(open(os.path.join(GOLDEN, "ref_js.json")))
 CASES = {c["name"]: c for c in DOC["cases"]}
 DOC12 = json.load(open(os.path.join(GOLDEN, "ref_js_l12.json")))      # level 12 (make_coeffs / polyfit / numeric), own fixture
 CASES12 = {c["name"]: c for c in DOC12["cases"]}
+DOC3 = json.load(open(os.path.join(GOLDEN, "ref_js_l3.json")))        # level 3 (raw ranked tracks), own fixture
+CASES3 = {c["name"]: c for c in DOC3["cases"]}
 _wav = {}
 
 
@@ -62,11 +64,21 @@ def check_against_reference(case, an, level, step):
         mine = [[[int(y["start"]), int(y["len"])] for y in an.syllables[s["first_syllable"]: s["first_syllable"] + s["n_syllables"]]]
                 for s in stored]
         assert mine == case["syl_ci"]
-    res = UtteranceResult({}, an.segments, an.formants, an.energy, an.syllables, an.features, getattr(an, "utterance", None))
+    res = UtteranceResult({}, an.segments, an.formants, an.energy, an.syllables, an.features, getattr(an, "utterance", None),
+                          getattr(an, "track_points", None))
     calls = api.segment_callbacks(level, step, DOC["labels"], res)
     assert len(calls) == len(case["events"])
     for mine, ref in zip(calls, case["events"]):
         assert mine[0] == ref[0] and mine[1] == ref[1]
+        if level == 3:
+            # b(e, label, s[e]): the ranked 18-field track arrays -- every number of every track (canonical JSON checksum)
+            sys.path.insert(0, GOLDEN)
+            from make_ref_js_golden import tracks_digest
+            assert len(mine) == 3
+            d = tracks_digest(mine[2])
+            assert (d["tracks"], d["points"]) == (ref[2]["tracks"], ref[2]["points"]) and d["first"] == ref[2]["first"]
+            assert d["sha"] == ref[2]["sha"]
+            continue
         assert mine[2] == ref[2]                       # time stamps: numbers (4, 5) or toFixed(3) strings (10, 13)
         if level == 13:
             assert np.array_equal(np.array(mine[3], np.float64), np.array(ref[3], np.float64), equal_nan=True)
@@ -111,6 +123,18 @@ def test_oracle_level12_matches_reference_js(name):
     assert fr.shape == (case["frames"], case["bands"]) and sha(fr) == case["frames_sha"]
     an = oracle.analyze_frames(cfg, fr)
     check_against_reference(case, an, 12, cfg.window_step_ms)
+
+
+@pytest.mark.parametrize("name", list(CASES3))
+def test_oracle_level3_matches_reference_js(name):
+    """Level 3: what the reference handed to its callback -- get_ranked_formants @B35670 -- rebuilt from fa_track headers and
+    fa_track_point rows by api.track_arrays."""
+    case = CASES3[name]
+    cfg = FaConfig.default(**case["kwargs"])
+    fr = frames_for(case["input"], cfg)
+    assert fr.shape == (case["frames"], case["bands"]) and sha(fr) == case["frames_sha"]
+    an = oracle.analyze_frames(cfg, fr)
+    check_against_reference(case, an, 3, cfg.window_step_ms)
 
 
 def test_fixture_covers_the_quirks():

@@ -102,6 +102,32 @@ def to_fixed3(x: float) -> str:
     return str(Decimal(float(x)).quantize(Decimal("0.001"), rounding=ROUND_HALF_UP))
 
 
+def track_arrays(tracks, points) -> list[list]:
+    """Level 3: the reference's 18-field track arrays (accumulate_fm @B35952) rebuilt from fa_track headers and fa_track_point
+    rows -- what get_ranked_formants @B35670 returns and P() hands to the callback."""
+    out = []
+    for t in tracks:
+        p = points[int(t["start"]): int(t["start"]) + int(t["len"])]
+        bins = [int(x) for x in p["bin"]]
+        h = len(bins) - 1                      # points before the last update
+        o = bins[-1]
+        if h >= 3:
+            vel = (o - bins[h - 1] + (bins[h - 2] - bins[h - 1]) + (bins[h - 3] - bins[h - 2])) / 3
+        elif h == 2:
+            vel = (o - bins[h - 1] + (bins[h - 2] - bins[h - 1])) / 2
+        elif h == 1:
+            vel = float(o - bins[h - 1])
+        else:
+            vel = 0.0
+        e = [float(x) for x in p["energy"]]
+        last = p[-1]
+        out.append([float(last["lo"]), float(last["hi"]), float(last["frame"]), float(last["frame"]), float(vel), float(o),
+                    float(last["amp"]), [float(x) for x in p["frame"]], [float(x) for x in p["lo"]], [float(x) for x in p["hi"]],
+                    [float(b) for b in bins], [float(x) for x in p["amp"]], e, float(sum(e)), float(len(bins)),
+                    float(sum(x * b for x, b in zip(e, bins))), 0.0, float(sum(int(a["hi"]) - int(a["lo"]) + 1 for a in p))])
+    return out
+
+
 def segment_callbacks(level: int, step_ms: float, labels: list, res) -> list[tuple]:
     """P() @B28869 on the tables of one utterance: the argument tuples of every callback, in firing order.
 
@@ -123,6 +149,13 @@ def segment_callbacks(level: int, step_ms: float, labels: list, res) -> list[tup
             t = sum(int(x["len"]) for x in segs[: si + 1])
             out.append((0, labels, [int(segs[0]["start"]) * step, (t + 1) * step], list(map(float, res.utterance[k]))))
             k += 1
+        return out
+    if level == 3:
+        # b(e, label, s[e]) when s[e].length > 0: three arguments, no time stamps (P() @B28869, level-3 branch)
+        for e, s in enumerate(stored):
+            tr = res.syllables[s["first_syllable"]: s["first_syllable"] + s["n_syllables"]]     # fa_track headers at level 3
+            if len(tr):
+                out.append((e, labels, track_arrays(tr, res.track_points)))
         return out
     for e, s in enumerate(stored):
         ci = segs[e]

@@ -156,6 +156,8 @@ struct fa_handle {
   bool use_fused() const { return k1_fused != 0 && N == 2048 && chunk_frames <= 0 && !frames_mode; }
   DevBuf g_segs, g_syls, g_formants, g_energy, g_features;
   DevBuf d_curve_work, d_curve_status;   // level 12 (K8)
+  DevBuf d_pt_amp;                       // level 3: amplitudes of the pool points
+  size_t row_bytes() const { return cfg.output_level == FA_LEVEL_SEGMENTS ? sizeof(fa_track_point) : 9 * sizeof(float); }
   int n_weights = 0;
   long long track_total = 0, urow_total = 0;
   int feat_width() const {
@@ -188,13 +190,13 @@ int fail(fa_handle* h, int code, const char* what, cudaError_t e = cudaSuccess) 
   } while (0)
 
 bool level_supported(int lvl) {
-  return lvl == FA_LEVEL_BARS || lvl == FA_LEVEL_SPECTRUM || lvl == FA_LEVEL_FORMANTS || lvl == FA_LEVEL_SEG_FEATURES ||
+  return lvl == FA_LEVEL_BARS || lvl == FA_LEVEL_SPECTRUM || lvl == FA_LEVEL_SEGMENTS || lvl == FA_LEVEL_FORMANTS || lvl == FA_LEVEL_SEG_FEATURES ||
          lvl == FA_LEVEL_SYL_FORMANTS || lvl == FA_LEVEL_UTTERANCE || lvl == FA_LEVEL_SYL_CURVES || lvl == FA_LEVEL_SYL_FEATURES;
 }
 
 int validate(const fa_config* c, std::string* why) {
   if (!fa_tab_valid_fft(c->fft_size)) { *why = "fft_size must be a power of two in [256, 16384]"; return FA_ERR_UNSUPPORTED; }
-  if (!level_supported(c->output_level)) { *why = "output_level not supported (levels 1, 2, 4, 5, 10, 11, 12, 13)"; return FA_ERR_UNSUPPORTED; }
+  if (!level_supported(c->output_level)) { *why = "output_level not supported (levels 1, 2, 3, 4, 5, 10, 11, 12, 13)"; return FA_ERR_UNSUPPORTED; }
   if (c->spec_type < 1 || c->spec_type > 3) { *why = "Invalid reset_nodes config"; return FA_ERR_INVALID_ARG; }
   const int B = fa_tab_bands(c);
   if (B < 8 || B > FA_MAX_BANDS) { *why = "Invalid spec_bands"; return FA_ERR_INVALID_ARG; }
@@ -354,7 +356,7 @@ int fa_destroy(fa_handle* h) {
                     &h->d_win, &h->d_tw, &h->d_tws, &h->d_ws, &h->d_bmi, &h->d_bmw, &h->d_emph, &h->d_spill, &h->d_trkbase, &h->d_trk_i,
                     &h->d_trk_d, &h->d_trk_slot, &h->d_pt_i, &h->d_pt_e, &h->d_rows, &h->d_rowlist, &h->d_segs, &h->d_syls,
                     &h->d_formants, &h->d_energy, &h->d_features, &h->d_counts, &h->d_off, &h->g_segs, &h->g_syls,
-                    &h->g_formants, &h->g_energy, &h->g_features, &h->d_chunks, &h->d_state, &h->d_specdb, &h->d_specq, &h->d_fix, &h->d_cchunks, &h->d_cstate, &h->d_frT, &h->d_frk, &h->d_frthr, &h->d_frctl, &h->d_frv, &h->d_epochs, &h->d_work, &h->d_k3q, &h->d_curve_work, &h->d_curve_status})
+                    &h->g_formants, &h->g_energy, &h->g_features, &h->d_chunks, &h->d_state, &h->d_specdb, &h->d_specq, &h->d_fix, &h->d_cchunks, &h->d_cstate, &h->d_frT, &h->d_frk, &h->d_frthr, &h->d_frctl, &h->d_frv, &h->d_epochs, &h->d_work, &h->d_k3q, &h->d_curve_work, &h->d_curve_status, &h->d_pt_amp})
     b->release();
   for (HostBuf* b : {&h->h_pcm, &h->h_frames, &h->h_meta, &h->h_counts, &h->h_off, &h->h_segs, &h->h_syls, &h->h_formants, &h->h_energy,
                      &h->h_features})
@@ -637,6 +639,7 @@ static int prepare(fa_handle* h) {
   // segments -- measured on B200: C2 (200 frames, 1.75 segments per utterance) 1.18 ms serial vs 1.38 ms split, the
   // one-hour stream (144 000 frames, 541 segments) 641 ms serial vs 124 ms split
   h->k3_mode = h->k3_cfg >= 0 ? h->k3_cfg : (F / std::max(n, 1) >= 1000 ? 1 : 0);
+  if (h->cfg.output_level == FA_LEVEL_SEGMENTS) h->k3_mode = 0;   // the raw-track export lives in the serial scan's finalisation
   // K1b stream mode for the same long utterances: chunks of 2048 frames, warm-up long enough for tau^W << 2^-24 plus a
   // margin for the last-ulp coalescence (FA_K1B_CHUNK=0 disables, FA_K1B_WARMUP overrides W -- the tests force W = 8 to
   // exercise the fix-up pass); tau close to 1 would need a warm-up as long as a chunk: one pass per utterance then
@@ -735,10 +738,15 @@ static int prepare(fa_handle* h) {
       FA_CUDA(h->d_work.reserve((Fz + nz) * sizeof(int2)));
       FA_CUDA(h->d_k3q.reserve(2 * kMaxSub * sizeof(int)));
     }
+    const bool l3 = h->cfg.output_level == FA_LEVEL_SEGMENTS;
+    // level 3: the "syllable" table holds the fa_track headers and the "formant row" table the fa_track_point rows of the
+    // ranked tracks, both with the capacity (and base) of the point pool
+    static_assert(sizeof(fa_track) == sizeof(fa_syllable) && sizeof(fa_track_point) == 24, "level-3 tables reuse the row plumbing");
     FA_CUDA(h->d_segs.reserve((Fz + nz) * sizeof(fa_segment)));
-    FA_CUDA(h->d_syls.reserve((Fz + nz) * sizeof(fa_syllable)));
-    FA_CUDA(h->d_formants.reserve(Fz * 9 * sizeof(float)));
+    FA_CUDA(h->d_syls.reserve(l3 ? P * sizeof(fa_track) : (Fz + nz) * sizeof(fa_syllable)));
+    FA_CUDA(h->d_formants.reserve(l3 ? P * sizeof(fa_track_point) : Fz * 9 * sizeof(float)));
     FA_CUDA(h->d_energy.reserve(Fz * 3 * sizeof(float)));
+    if (l3) FA_CUDA(h->d_pt_amp.reserve(P * sizeof(int)));
     if (h->cfg.output_level == 5 || h->cfg.output_level == 13 || h->cfg.output_level == FA_LEVEL_SYL_CURVES)
       FA_CUDA(h->d_features.reserve((Fz + nz) * h->feat_width() * sizeof(double)));
     if (h->cfg.output_level == FA_LEVEL_SYL_CURVES) {
@@ -752,8 +760,8 @@ static int prepare(fa_handle* h) {
     FA_CUDA(h->d_counts.reserve(nz * 6 * sizeof(int)));      // n_segs, n_stored, n_rows, n_syls, n_feat, overflow
     FA_CUDA(h->d_off.reserve((nz + 1) * 4 * sizeof(long long)));
     FA_CUDA(h->g_segs.reserve((Fz + nz) * sizeof(fa_segment)));
-    FA_CUDA(h->g_syls.reserve((Fz + nz) * sizeof(fa_syllable)));
-    FA_CUDA(h->g_formants.reserve(Fz * 9 * sizeof(float)));
+    FA_CUDA(h->g_syls.reserve(l3 ? P * sizeof(fa_track) : (Fz + nz) * sizeof(fa_syllable)));
+    FA_CUDA(h->g_formants.reserve(l3 ? P * sizeof(fa_track_point) : Fz * 9 * sizeof(float)));
     FA_CUDA(h->g_energy.reserve(Fz * 3 * sizeof(float)));
     if (h->cfg.output_level == 5 || h->cfg.output_level == 13 || h->cfg.output_level == FA_LEVEL_SYL_CURVES)
       FA_CUDA(h->g_features.reserve((Fz + nz) * h->feat_width() * sizeof(double)));
@@ -970,6 +978,8 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
     g.trk_slot = h->d_trk_slot.as<signed char>();
     g.pt_track = h->d_pt_i.as<int>(); g.pt_ord = g.pt_track + P; g.pt_frame = g.pt_ord + P; g.pt_binspan = g.pt_frame + P;
     g.pt_e = h->d_pt_e.as<double>();
+    g.pt_amp = c.output_level == FA_LEVEL_SEGMENTS ? h->d_pt_amp.as<int>() : nullptr;
+    g.track_points = c.output_level == FA_LEVEL_SEGMENTS ? h->d_formants.as<fa_track_point>() : nullptr;
     g.row_count = h->d_rows.as<int>(); g.row_off = g.row_count + R; g.row_list = h->d_rowlist.as<int>();
     g.cs_spill = h->d_spill.as<unsigned long long>();
     g.finalize_in_smem = h->k3_finalize_smem;
@@ -1100,6 +1110,7 @@ static int run_device(fa_handle* h, bool with_h2d, bool with_sink) {
     int* cnt = h->d_counts.as<int>();
     FaGatherArgs ga;
     ga.feat_width = h->feat_width();
+    ga.l3_mult = c.output_level == FA_LEVEL_SEGMENTS ? h->maxp : 0;
     ga.epochs = h->k3_mode == 1 ? h->d_epochs.as<FaEpoch>() : nullptr;
     ga.row_slices = (int)std::min<long long>(64, std::max<long long>(1, h->total_frames / std::max(1, n) / 256));
     ga.feat_base = c.output_level == FA_LEVEL_UTTERANCE ? meta + 4 * n + 2 : nullptr;
@@ -1355,7 +1366,8 @@ static int fetch_table(fa_handle* h, int table) {
   HostBuf* hb[5] = {&h->h_segs, &h->h_formants, &h->h_energy, &h->h_syls, &h->h_features};
   DevBuf* db[5] = {&h->g_segs, &h->g_formants, &h->g_energy, &h->g_syls, &h->g_features};
   const size_t rows = (size_t)h->tot[table == 0 ? 0 : table <= 2 ? 1 : table == 3 ? 2 : 3];
-  const size_t row_bytes = table == 0 ? sizeof(fa_segment) : table == 1 ? 9 * sizeof(float) : table == 2 ? 3 * sizeof(float)
+  if (h->cfg.output_level == FA_LEVEL_SEGMENTS && table == 2) { h->have_table[table] = true; return FA_OK; }   // no energy rows
+  const size_t row_bytes = table == 0 ? sizeof(fa_segment) : table == 1 ? h->row_bytes() : table == 2 ? 3 * sizeof(float)
                            : table == 3 ? sizeof(fa_syllable) : (size_t)h->feat_width() * sizeof(double);
   FA_CUDA(hb[table]->reserve(std::max<size_t>(16, rows * row_bytes)));
   if (rows) {
@@ -1397,10 +1409,17 @@ int fa_copy_segments(fa_handle* h, int64_t utt_id, fa_segment* dst, size_t cap) 
 }
 int fa_copy_formants(fa_handle* h, int64_t utt_id, float* dst, size_t cap) {
   if (!h) return FA_ERR_INVALID_ARG;
+  if (h->cfg.output_level == FA_LEVEL_SEGMENTS) return 0;   // level 3 stores no straightened rows (fa_copy_track_points)
   return copy_dense(h, utt_id, 1, 1, 9 * sizeof(float), dst, cap);
+}
+int fa_copy_track_points(fa_handle* h, int64_t utt_id, fa_track_point* dst, size_t cap) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  if (h->cfg.output_level != FA_LEVEL_SEGMENTS) return fail(h, FA_ERR_INVALID_ARG, "raw tracks need output_level 3");
+  return copy_dense(h, utt_id, 1, 1, sizeof(fa_track_point), dst, cap);
 }
 int fa_copy_energy(fa_handle* h, int64_t utt_id, float* dst, size_t cap) {
   if (!h) return FA_ERR_INVALID_ARG;
+  if (h->cfg.output_level == FA_LEVEL_SEGMENTS) return 0;
   return copy_dense(h, utt_id, 1, 2, 3 * sizeof(float), dst, cap);
 }
 int fa_copy_syllables(fa_handle* h, int64_t utt_id, fa_syllable* dst, size_t cap) {

@@ -226,7 +226,13 @@ __global__ void __launch_bounds__(128) fa_gather_kernel(const FaGatherArgs g) {
     uint32_t* d = reinterpret_cast<uint32_t*>(g.d_segs + o);
     for (int i = tid; i < words; i += 128) d[i] = s[i];
   }
-  if (g.epochs) {   // stream mode: segment by segment from the epochs' frame ranges, segments dealt over the row slices
+  if (g.l3_mult) {   // level 3: fa_track_point rows (6 words) from the point-pool base; no energy rows
+    const int n = g.n_rows[u];
+    const long long o = off[N1 + u];
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(g.formants) + (size_t)row0 * g.l3_mult * 6;
+    uint32_t* d = reinterpret_cast<uint32_t*>(g.d_formants) + (size_t)o * 6;
+    for (int i = tid; i < n * 6; i += 128) d[i] = s[i];
+  } else if (g.epochs) {   // stream mode: segment by segment from the epochs' frame ranges, segments dealt over the row slices
     const long long o = off[N1 + u];
     const int nseg = g.n_segs[u];
     for (int sgi = blockIdx.y; sgi < nseg; sgi += gridDim.y) {
@@ -254,7 +260,7 @@ __global__ void __launch_bounds__(128) fa_gather_kernel(const FaGatherArgs g) {
   {
     const int n = g.n_syls[u];
     const long long o = off[2 * N1 + u];
-    const uint32_t* s = reinterpret_cast<const uint32_t*>(g.syls + sb);
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(g.syls + (g.l3_mult ? row0 * g.l3_mult : sb));
     uint32_t* d = reinterpret_cast<uint32_t*>(g.d_syls + o);
     for (int i = tid; i < n * 4; i += 128) d[i] = s[i];
   }

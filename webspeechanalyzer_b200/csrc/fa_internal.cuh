@@ -118,7 +118,10 @@ struct FaSegmentParams {
   long long* track_base;              // [n_utt + 1] prefix of capacities
   int* trk_count; double* trk_sum_e; double* trk_sum_eb; double* trk_mean; int* trk_order; int* trk_rank; signed char* trk_slot;
   // point pool: capacity F_u * maxp, base = frame_off[u] * maxp
-  int* pt_track; int* pt_ord; int* pt_frame; int* pt_binspan; double* pt_e;
+  int* pt_track; int* pt_ord; int* pt_frame; int* pt_binspan; double* pt_e;   // binspan = bin | lo << 8 | (hi - lo + 1) << 16
+  int* pt_amp;                        // level 3 only (else nullptr): amplitude of the point ([11] of the reference's track array)
+  fa_track_point* track_points;       // level 3 only: exported points, base = frame_off[u] * maxp (and fa_track headers in `syls`
+                                      // at the same base instead of frame_off[u] + u)
   int* row_count; int* row_off;       // [F_total + n_utt] scratch (per utterance F_u + 1)
   int* row_list;                      // [F_total * maxp]
   unsigned long long* cs_spill;       // [n_utt][6][128] candidate scores beyond the three kept in shared memory
@@ -208,7 +211,9 @@ struct FaGatherArgs {
   const FaEpoch* epochs;              // K3 stream mode: formant / energy rows are gathered segment by segment from the
                                       // epochs' frame ranges, several CTAs per utterance (row_slices); nullptr: contiguous
   int row_slices;
-  int feat_width;                     // doubles per feature row: 53 (levels 5, 13) or 264 (level 11)
+  int feat_width;                     // doubles per feature row: 53 (levels 5, 13), 23 (level 12) or 264 (level 11)
+  int l3_mult;                        // level 3: maxp (the track headers in `syls` and the fa_track_point rows in `formants`
+                                      // sit at base frame_off[u] * maxp); else 0
   const long long* feat_base;         // level 11: first row of every utterance in `features`; nullptr: frame_off[u] + u
   const int *n_segs, *n_rows, *n_syls, *n_feat;
   long long* off;  // [4][n_utt + 1] exclusive prefixes: segs, rows, syls, feat

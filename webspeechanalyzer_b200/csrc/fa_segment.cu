@@ -306,7 +306,8 @@ __device__ __forceinline__ void accumulate_fm(const FaSegmentParams& p, WarpShar
       S.t_se[r] = se; S.t_seb[r] = seb;
       const long long q = bs.pb + st.n_pts + __popc(um & lt);
       p.pt_track[q] = id; p.pt_ord[q] = h; p.pt_frame[q] = n_label;
-      p.pt_binspan[q] = ob | ((hi_b - lo_b + 1) << 16); p.pt_e[q] = E;
+      p.pt_binspan[q] = ob | (lo_b << 8) | ((hi_b - lo_b + 1) << 16); p.pt_e[q] = E;
+      if (p.pt_amp) p.pt_amp[q] = amp0;
       const long long ti = bs.tb + id;
       p.trk_count[ti] = h + 1; p.trk_sum_e[ti] = se; p.trk_sum_eb[ti] = seb;
     }
@@ -346,7 +347,8 @@ __device__ __forceinline__ void accumulate_fm(const FaSegmentParams& p, WarpShar
         S.t_se[r] = E; S.t_seb[r] = E * (double)pk; S.t_wm[r] = 0u;
         const long long q = bs.pb + st.n_pts + i;
         p.pt_track[q] = id; p.pt_ord[q] = 0; p.pt_frame[q] = n_label;
-        p.pt_binspan[q] = pk | (((int)((pa.x >> 8) & 0xff) - (int)(pa.x & 0xff) + 1) << 16); p.pt_e[q] = E;
+        p.pt_binspan[q] = pk | ((int)(pa.x & 0xff) << 8) | (((int)((pa.x >> 8) & 0xff) - (int)(pa.x & 0xff) + 1) << 16); p.pt_e[q] = E;
+        if (p.pt_amp) p.pt_amp[q] = pa.y;
         const long long ti = bs.tb + id;
         p.trk_count[ti] = 1; p.trk_sum_e[ti] = E; p.trk_sum_eb[ti] = E * (double)pk;
       }
@@ -543,7 +545,7 @@ __device__ __noinline__ int finalize_fast(const FaSegmentParams p, WarpShared& S
       const int bq = (int)((bestkey >> 2) & 4095);
       int sl = (int)(bestkey & 3);
       const int bs_ = p.pt_binspan[bs.pb + bq];
-      const int bin = bs_ & 0xffff, span = bs_ >> 16;
+      const int bin = bs_ & 0xff, span = bs_ >> 16;   // bits 8..15: the point's lower bound (level 3)
       const double E = p.pt_e[bs.pb + bq];
       const float cur = sl == 0 ? f0 : sl == 1 ? f3 : f6;
       if ((double)cur > vmin && (double)cur < (double)bin && sl < 2) sl++;
@@ -640,6 +642,54 @@ __device__ __noinline__ int finalize_segment(const FaSegmentParams p, ScanState&
     }
   }
   __syncwarp();
+  if (p.level == 3) {
+    // O() @B27088, level-3 branch: u.push([e, a]), s.push(get_ranked_formants()), no straighten_formants (nothing can throw).
+    // The ranked tracks leave as headers (rank order) + points (time order); tables: base = the utterance's point-pool base.
+    const int si3 = st.n_segs;
+    fa_track* th = reinterpret_cast<fa_track*>(p.syls) + bs.pb + st.n_syls;
+    fa_track_point* tp = p.track_points + bs.pb + st.n_rows;
+    int run = 0;
+    for (int r0 = 0; r0 < nr; r0 += 32) {
+      const int r = r0 + lane;
+      const int i = r < nr ? p.trk_order[bs.tb + r] : 0;
+      const int c = r < nr ? p.trk_count[bs.tb + i] : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (r < nr) {
+        const int off = run + incl - c;
+        fa_track h3;
+        h3.stored_seg = st.n_stored; h3.first_point = st.n_rows + off; h3.n_points = c; h3.reserved = 0;
+        th[r] = h3;
+        p.trk_rank[bs.tb + i] = off;      // the rank has done its job: from here on the track's first point
+      }
+      run += __shfl_sync(FULL, incl, 31);
+    }
+    __syncwarp();
+    for (int q = lane; q < st.n_pts; q += 32) {
+      const int i = p.pt_track[bs.pb + q];
+      if (p.trk_mean[bs.tb + i] >= 7) {
+        const int bs_ = p.pt_binspan[bs.pb + q];
+        const int lo_b = (bs_ >> 8) & 0xff;
+        fa_track_point o;
+        o.frame = p.pt_frame[bs.pb + q]; o.lo = (int16_t)lo_b; o.hi = (int16_t)(lo_b + (bs_ >> 16) - 1); o.bin = (int16_t)(bs_ & 0xff);
+        o.reserved = 0; o.amp = (uint32_t)p.pt_amp[bs.pb + q]; o.energy = p.pt_e[bs.pb + q];
+        tp[p.trk_rank[bs.tb + i] + p.pt_ord[bs.pb + q]] = o;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      fa_segment sg;
+      sg.start = start; sg.len = len; sg.stored = st.n_stored; sg.n_syllables = nr; sg.first_syllable = st.n_syls; sg.row_offset = st.n_rows;
+      sg.ymax = st.y; sg.vmin = st.v; sg.cs_ratio = st.c_energy / st.s_energy;
+      p.segs[bs.sb + si3] = sg;
+    }
+    st.n_segs++; st.n_stored++; st.n_syls += nr; st.n_rows += run;
+    return 1;
+  }
   // slot assignment of straighten_formants @B35074 (sequential over the ranking)
   {
     double anchor = 0;
@@ -730,7 +780,7 @@ __device__ __noinline__ int finalize_segment(const FaSegmentParams p, ScanState&
       const int i = p.pt_track[bs.pb + bq];
       int sl = p.trk_slot[bs.tb + i];
       const int bs_ = p.pt_binspan[bs.pb + bq];
-      const int bin = bs_ & 0xffff, span = bs_ >> 16;
+      const int bin = bs_ & 0xff, span = bs_ >> 16;   // bits 8..15: the point's lower bound (level 3)
       const double E = p.pt_e[bs.pb + bq];
       const float cur = sl == 0 ? f0 : sl == 1 ? f3 : f6;
       if ((double)cur > vmin && (double)cur < (double)bin && sl < 2) sl++;
@@ -795,7 +845,7 @@ __device__ __forceinline__ int finalize_copy(const FaSegmentParams& p, WarpShare
   if (!(len > p.seg_min_frames && st.c_started >= 2)) return 0;
   ScanState cp = st;
   int r = -3;
-  if (p.finalize_in_smem && finalize_fits(st, len, p.smem_per_warp - kScratchOff)) {
+  if (p.level != 3 && p.finalize_in_smem && finalize_fits(st, len, p.smem_per_warp - kScratchOff)) {
     r = finalize_fast(p, S, cp, bs, n_arg, lane);
     st.n_slots = ACAP;  // the track slots were used as scratch: the seg_reset that follows clears all of them
   }
@@ -1113,7 +1163,8 @@ __device__ __forceinline__ void accumulate_fm2(const FaSegmentParams& p, WarpSha
     S.t_se[q] = se; S.t_seb[q] = seb;
     const long long pq = bs.pb + st.n_pts + __popc(um & lt);
     p.pt_track[pq] = best_id; p.pt_ord[pq] = h; p.pt_frame[pq] = n_label;
-    p.pt_binspan[pq] = ob | ((hi_b - lo_b + 1) << 16); p.pt_e[pq] = E;
+    p.pt_binspan[pq] = ob | (lo_b << 8) | ((hi_b - lo_b + 1) << 16); p.pt_e[pq] = E;
+    if (p.pt_amp) p.pt_amp[pq] = my_amp;
     const long long ti = bs.tb + best_id;
     p.trk_count[ti] = h + 1; p.trk_sum_e[ti] = se; p.trk_sum_eb[ti] = seb;
   }
@@ -1142,7 +1193,8 @@ __device__ __forceinline__ void accumulate_fm2(const FaSegmentParams& p, WarpSha
       S.t_se[q] = E; S.t_seb[q] = E * (double)my_pk;
       const long long pq = bs.pb + st.n_pts + i;
       p.pt_track[pq] = id; p.pt_ord[pq] = 0; p.pt_frame[pq] = n_label;
-      p.pt_binspan[pq] = my_pk | (((int)((my_pkd >> 8) & 0xffu) - (int)(my_pkd & 0xffu) + 1) << 16); p.pt_e[pq] = E;
+      p.pt_binspan[pq] = my_pk | ((int)(my_pkd & 0xffu) << 8) | (((int)((my_pkd >> 8) & 0xffu) - (int)(my_pkd & 0xffu) + 1) << 16); p.pt_e[pq] = E;
+      if (p.pt_amp) p.pt_amp[pq] = my_amp;
       const long long ti = bs.tb + id;
       p.trk_count[ti] = 1; p.trk_sum_e[ti] = E; p.trk_sum_eb[ti] = E * (double)my_pk;
     }

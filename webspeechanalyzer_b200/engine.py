@@ -14,6 +14,8 @@ SEG_DTYPE = np.dtype([("start", "<i4"), ("len", "<i4"), ("stored", "<i4"), ("n_s
                       ("first_syllable", "<i4"), ("row_offset", "<i4"), ("ymax", "<f8"), ("vmin", "<f8"),
                       ("cs_ratio", "<f8")])
 SYL_DTYPE = np.dtype([("stored_seg", "<i4"), ("start", "<i4"), ("len", "<i4"), ("reserved", "<i4")])
+TRACK_POINT_DTYPE = np.dtype([("frame", "<i4"), ("lo", "<i2"), ("hi", "<i2"), ("bin", "<i2"), ("reserved", "<i2"), ("amp", "<u4"),
+                              ("energy", "<f8")], align=True)     # fa_track_point (include/fa_b200.h)
 COUNTS_DTYPE = np.dtype([("samples", "<i8"), ("sample_rate", "<i4"), ("hop", "<i4"), ("frames", "<i4"), ("bands", "<i4"),
                          ("segments", "<i4"), ("stored_segments", "<i4"), ("formant_rows", "<i4"), ("syllables", "<i4"),
                          ("feature_rows", "<i4"), ("overflow", "<i4")])
@@ -28,6 +30,7 @@ class UtteranceResult:
     syllables: np.ndarray     # SYL_DTYPE
     features: np.ndarray      # [rows, 53] float64
     utterance: np.ndarray | None = None   # [stored segments, 264] float64, cumulative (level 11)
+    track_points: np.ndarray | None = None   # level 3: TRACK_POINT_DTYPE rows; `syllables` then holds the fa_track headers
 
     @property
     def seg_ci(self):
@@ -262,9 +265,14 @@ class Engine:
         c = self.counts(utt_id)
         L = self._lib
         segs = self._rows(L.fa_copy_segments, utt_id, c["segments"], (), SEG_DTYPE)
-        fm = self._rows(L.fa_copy_formants, utt_id, c["formant_rows"], (9,), np.float32)
-        en = self._rows(L.fa_copy_energy, utt_id, c["formant_rows"], (3,), np.float32)
+        lvl3 = self.cfg.output_level == 3
+        fm = self._rows(L.fa_copy_formants, utt_id, 0 if lvl3 else c["formant_rows"], (9,), np.float32)
+        en = self._rows(L.fa_copy_energy, utt_id, 0 if lvl3 else c["formant_rows"], (3,), np.float32)
         sy = self._rows(L.fa_copy_syllables, utt_id, c["syllables"], (), SYL_DTYPE)
+        if self.cfg.output_level == 3:      # ranked tracks (headers in the syllable table) + their points
+            tp = self._rows(L.fa_copy_track_points, utt_id, c["formant_rows"], (), TRACK_POINT_DTYPE)
+            return UtteranceResult(c, segs, np.zeros((0, 9), np.float32), np.zeros((0, 3), np.float32), sy, np.zeros((0, N_FEATURES)),
+                                   None, tp)
         if self.cfg.output_level == 11:
             ut = self._rows(L.fa_copy_utterance_features, utt_id, c["feature_rows"], (N_UTT_FEATURES,), np.float64)
             return UtteranceResult(c, segs, fm, en, sy, np.zeros((0, N_FEATURES)), ut)
