@@ -119,14 +119,26 @@ def bind_to_gpu_numa_node(local: int):
 
 def ncu_traffic(kernel: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
-    (profiles/r1_ncu_kernels.json, written by profiles/ncu_kernels.py); None if there is no capture."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_kernels.json")
-    if not os.path.exists(p):
+    (profiles/r<round>_ncu_kernels.json, written by profiles/ncu_kernels.py; the newest one); None if there is no capture."""
+    import glob
+    found = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_kernels.json")))     # the newest round's capture
+    if not found:
         return None
-    for name, d in json.load(open(p)).items():   # kernel names carry template arguments ("void fa_segment_kernel<128>")
+    for name, d in json.load(open(found[-1])).items():   # kernel names carry template arguments ("void fa_segment_kernel<128>")
         if kernel in name:
             return d.get("dram_bytes")
     return None
+
+
+def mean_candidates_per_frame(eng, utt_ids, sample: int = 16) -> float:
+    """Stage 2 emits 32 bytes per candidate peak: measured on a sample of the batch (the algorithmic bytes of K2 / K3)."""
+    tot, fr = 0, 0
+    utt_ids = list(utt_ids)
+    for i in utt_ids[:: max(1, len(utt_ids) // sample)]:
+        _, cnt = eng.peak_candidates(int(i))
+        tot += int(cnt.sum())
+        fr += int(cnt.size)
+    return tot / max(fr, 1)
 
 
 def measured_peaks():
@@ -332,6 +344,7 @@ def run_c3(args, world, rank, local):
     eng.download()
     eng.sync()
     tot = eng.counts()
+    cand_per_frame = mean_candidates_per_frame(eng, utt_ids)
     value = world * audio_per_step * args.steps / (ms_max / 1e3)
 
     # ---- end to end: host PCM -> device -> feature rows -> host -> gathered on rank 0 ----
@@ -474,8 +487,8 @@ def run_c3(args, world, rank, local):
         N, B, hop = cfg.fft_size, cfg.bands, C3_HOP
         alg = {
             "spectrum": frames_per_step * (2 * hop + 4 * B),                                       # int16 PCM once + u32 frame (no dB rows)
-            "peaks": frames_per_step * (4 * B + 4 * 6 + 12),
-            "segment": frames_per_step * (4 * B + 4 * 6 + 12) + tot["formant_rows"] * 48,
+            "peaks": frames_per_step * (4 * B + 32 * cand_per_frame + 12),                         # u32 frame in, 32 B per candidate + (n, g) out
+            "segment": frames_per_step * (32 * cand_per_frame + 12) + tot["formant_rows"] * 48,    # candidates in, formant + energy rows out
             "features": tot["formant_rows"] * 36 + tot["feature_rows"] * 424,
         }
         names = ["spectrum", "peaks", "segment", "features"]
@@ -485,7 +498,7 @@ def run_c3(args, world, rank, local):
                       "achieved_gbs": alg[k] / (stage_ms[i] * 1e-3) / 1e9 if stage_ms[i] > 0 else None,
                       "frac_of_hbm_peak": alg[k] / (stage_ms[i] * 1e-3) / 1e9 / peak if stage_ms[i] > 0 else None}
                   for i, k in enumerate(names)}
-        kern = {"spectrum": "fa_fftmag_2048_kernel", "peaks": "fa_peaks_kernel", "segment": "fa_segment2_kernel",
+        kern = {"spectrum": "fa_fftmag_2048_kernel", "peaks": "fa_peaks2_kernel", "segment": "fa_segment2_kernel",
                 "features": "fa_features_kernel"}[top]
         ach = stages[top]["achieved_gbs"]
         line = {
@@ -621,6 +634,7 @@ def main():
     eng.download()
     eng.sync()
     tot = eng.counts()
+    cand_per_frame = mean_candidates_per_frame(eng, range(n_utt))
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -814,15 +828,15 @@ def main():
         seg_rows = max(tot["formant_rows"] // max(world, 1), 1) if False else tot["formant_rows"]
         alg = {
             "spectrum": frames_per_step * (4 * hop + 4 * (N // 2) + 4 * B),                       # PCM once + dB row + u32 frame
-            "peaks": frames_per_step * (4 * B + 4 * 6 + 12),                                        # frame read + ~6 candidates + header
-            "segment": frames_per_step * (4 * B + 4 * 6 + 12) + tot["formant_rows"] * 48,          # frame + candidates read, formant + energy rows written
+            "peaks": frames_per_step * (4 * B + 32 * cand_per_frame + 12),                         # u32 frame in, 32 B per candidate (measured count) + (n, g) out
+            "segment": frames_per_step * (32 * cand_per_frame + 12) + tot["formant_rows"] * 48,    # candidates in, formant + energy rows out
             "features": tot["formant_rows"] * 36 + tot["feature_rows"] * 424,
         }
         names = ["spectrum", "peaks", "segment", "features"]
         shares = {k: float(stage_ms[i] / max(stage_ms[4], 1e-9)) for i, k in enumerate(names)}
         top = max(names, key=lambda k: stage_ms[names.index(k)])
-        stage_kernels = {"spectrum": ["fa_fftmag_2048_kernel", "fa_smooth_bands_kernel"], "peaks": ["fa_peaks_kernel"],
-                         "segment": ["fa_segment_kernel"], "features": ["fa_features_kernel"]}
+        stage_kernels = {"spectrum": ["fa_fftmag_2048_kernel", "fa_smooth_bands_kernel"], "peaks": ["fa_peaks2_kernel"],
+                         "segment": ["fa_segment2_kernel"], "features": ["fa_features_kernel"]}
 
         def stage_traffic(k):     # DRAM bytes per launch of the stage's kernels from the committed ncu --set full capture
             vals = [ncu_traffic(name) for name in stage_kernels[k]]
@@ -842,11 +856,11 @@ def main():
             "config": {"workload": WORKLOAD, "utterances_per_gpu": n_utt, "parallelism": f"shard-by-utterance x{world}",
                        "batches_in_flight": depth,
                        "l2": "inputs (320 MB PCM + 819 MB spectrum rows per step) exceed the 126 MB L2; no flush needed"},
-            "roofline": {"bound": "hbm", "kernel": {"spectrum": "fa_fftmag_2048_kernel", "peaks": "fa_peaks_kernel",
-                                                    "segment": "fa_segment_kernel", "features": "fa_features_kernel"}[top],
+            "roofline": {"bound": "hbm", "kernel": {"spectrum": "fa_fftmag_2048_kernel", "peaks": "fa_peaks2_kernel",
+                                                    "segment": "fa_segment2_kernel", "features": "fa_features_kernel"}[top],
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": ncu_traffic({"spectrum": "fa_fftmag_2048_kernel", "peaks": "fa_peaks_kernel",
-                                                 "segment": "fa_segment_kernel", "features": "fa_features_kernel"}[top]),
+                         "traffic": ncu_traffic({"spectrum": "fa_fftmag_2048_kernel", "peaks": "fa_peaks2_kernel",
+                                                 "segment": "fa_segment2_kernel", "features": "fa_features_kernel"}[top]),
                          "peak_source": peak_src, "share_of_step": shares[top],
                          "note": "segment scan / features are latency bound (sequential state machine), spectrum is FP32-issue bound; see DESIGN.md"},
             "stages": stages,

@@ -38,6 +38,17 @@ struct DevBuf {
     if (e == cudaSuccess) cap = want;
     return e;
   }
+  // as reserve(), and a NEW allocation is cleared once: for tables whose unused slots are loaded speculatively (K3 prefetches
+  // candidate slot `lane` of the next frame before it knows the frame's count; the value is masked out, but the load would
+  // read never-written memory -- compute-sanitizer initcheck)
+  cudaError_t reserve_zeroed(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    cudaError_t e = reserve(bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(p, 0, cap);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(cudaStreamLegacy);
+  }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
@@ -147,7 +158,7 @@ struct fa_handle {
   int k3_mode = 0;
   int k3_workers = 0;    // warps of the epoch-tracking grid
   int k3_impl = 2;       // FA_K3_IMPL: 2 = accumulate_fm2 kernel + redo launch (default), 1 = the general kernel alone
-  int k3_warps = 0, k3_regs = 0, k3_finalize_smem = 1, k2_staged = 0;   // FA_K3_WARPS, FA_K3_REGS, FA_K3_FINALIZE_HBM, FA_K2_STAGED
+  int k3_warps = 0, k3_regs = 0, k3_finalize_smem = 1;   // FA_K3_WARPS, FA_K3_REGS, FA_K3_FINALIZE_HBM
   bool debug_sync = false;  // FA_DEBUG_SYNC
   int k1_fused = 0;         // FA_K1_FUSED=1: the fused K1 kernel (fft_size 2048, utterance mode) instead of K1a + K1b.  Measured
                             // slower on B200 (C2: 0.99 vs 0.94 ms with dB rows, 0.93 vs 0.86 ms without; the stage is FP32-issue
@@ -331,7 +342,6 @@ int fa_create(const fa_config* cfg, int device, fa_handle** out) {
   if (const char* ev = getenv("FA_K3_WARPS")) { const int v = atoi(ev); if (v >= 1 && v <= 4) h->k3_warps = v; }
   if (const char* ev = getenv("FA_K3_REGS")) h->k3_regs = atoi(ev);
   if (getenv("FA_K3_FINALIZE_HBM")) h->k3_finalize_smem = 0;
-  if (const char* ev = getenv("FA_K2_IMPL")) h->k2_staged = atoi(ev);   // -1: the direct kernel (A/B), 0: v2
   if (getenv("FA_DEBUG_SYNC")) h->debug_sync = true;
   if (const char* ev = getenv("FA_K1_FUSED")) h->k1_fused = atoi(ev) != 0;
 
@@ -718,7 +728,7 @@ static int prepare(fa_handle* h) {
   FA_CUDA(h->d_frames.reserve(Fz * h->B * sizeof(uint32_t)));
   FA_CUDA(h->d_counter.reserve(2 * kMaxSub * sizeof(int)));
   if (h->cfg.output_level >= 3) {
-    FA_CUDA(h->d_cand.reserve(Fz * h->maxp * sizeof(FaCand)));
+    FA_CUDA(h->d_cand.reserve_zeroed(Fz * h->maxp * sizeof(FaCand)));
     FA_CUDA(h->d_ncand.reserve(Fz * sizeof(int)));
     FA_CUDA(h->d_gsum.reserve(Fz * sizeof(double)));
     const size_t T = (size_t)std::max<long long>(tb, 1);
@@ -946,7 +956,6 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
     FaPeaksParams pp;
     pp.frames = h->d_frames.as<uint32_t>(); pp.B = h->B; pp.maxp = h->maxp; pp.n_frames = sb.r1 - sb.r0; pp.row_begin = sb.r0;
     pp.cand = h->d_cand.as<FaCand>(); pp.ncand = h->d_ncand.as<int>(); pp.gsum = h->d_gsum.as<double>();
-    pp.staged = h->k2_staged;
     FA_CUDA(fa_launch_peaks(pp, s, &h->launches));
     if (h->debug_sync) FA_CUDA(cudaStreamSynchronize(s));
   }

@@ -78,7 +78,6 @@ struct FaPeaksParams {
   int B, maxp;
   long long n_frames;            // frames of the sub-batch
   long long row_begin;
-  int staged;                    // 1: rows go through shared memory (coalesced); 0: every lane streams its own row
   FaCand* cand;                  // [F_total][maxp]
   int* ncand;                    // [F_total]
   double* gsum;                  // [F_total] sum e[1..B-1]

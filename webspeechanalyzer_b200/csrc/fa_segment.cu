@@ -870,7 +870,6 @@ __global__ void __launch_bounds__(kBound, 1) fa_segment_kernel(const FaSegmentPa
   bs.tb = p.track_base[u];
   bs.tcap = (int)(p.track_base[u + 1] - bs.tb);
   int maxp = p.maxp;
-  asm volatile("" : "+r"(maxp));  // keep it in an ordinary register (ptxas uniform-register hazard, see fa_peaks.cu)
   bs.pb = bs.row0 * maxp;
   bs.sb = bs.row0 + u;
   bs.rb = bs.sb;
@@ -1228,7 +1227,6 @@ __global__ void __launch_bounds__(kBound, 1) fa_segment2_kernel(const FaSegmentP
   bs.tb = p.track_base[u];
   bs.tcap = (int)(p.track_base[u + 1] - bs.tb);
   int maxp = p.maxp;
-  asm volatile("" : "+r"(maxp));  // keep it in an ordinary register (ptxas uniform-register hazard, see fa_peaks.cu)
   bs.pb = bs.row0 * maxp;
   bs.sb = bs.row0 + u;
   bs.rb = bs.sb;
@@ -1567,7 +1565,6 @@ __global__ void __launch_bounds__(kCtlWarps * 32) fa_segctl_kernel(const FaSegme
   const long long row0 = p.frame_off[u], sb = row0 + u;
   const int F = (int)(p.frame_off[u + 1] - row0);
   int maxp = p.maxp;
-  asm volatile("" : "+r"(maxp));
   ScanState st;
   ctl_init(p, st);
   int epoch_first = 0, fired = 0;
@@ -1592,7 +1589,6 @@ __global__ void __launch_bounds__(kCtlWarps * 32) fa_segctl_chunk_kernel(const F
   const long long row0 = p.frame_off[u], sb = row0 + u;
   const int F = (int)(p.frame_off[u + 1] - row0);
   int maxp = p.maxp;
-  asm volatile("" : "+r"(maxp));
   const int a = j * p.ctl_chunk, b = min(F, a + p.ctl_chunk);
   const long long slot = p.cchunk_base[u] + j;
   ScanState st;
@@ -1619,7 +1615,6 @@ __global__ void __launch_bounds__(kCtlWarps * 32) fa_segctl_verify_kernel(const 
   const long long row0 = p.frame_off[u], sb = row0 + u;
   const int F = (int)(p.frame_off[u + 1] - row0);
   int maxp = p.maxp;
-  asm volatile("" : "+r"(maxp));
   const int nc = (int)(p.cchunk_base[u + 1] - p.cchunk_base[u]);
   ScanState st;          // the TRUE state at the current chunk boundary
   ctl_init(p, st);
@@ -1703,7 +1698,6 @@ __global__ void __launch_bounds__(kBound, 1) fa_segtrack_kernel(const FaSegmentP
   WarpShared& S = *reinterpret_cast<WarpShared*>(smem_raw + (size_t)wib * p.smem_per_warp);
   const int worker = blockIdx.x * (int)(blockDim.x >> 5) + wib;
   int maxp = p.maxp;
-  asm volatile("" : "+r"(maxp));
   const unsigned lt = (1u << lane) - 1u;
   const int n_work = *reinterpret_cast<volatile int*>(p.work_count);
   for (;;) {
