@@ -141,6 +141,25 @@ def mean_candidates_per_frame(eng, utt_ids, sample: int = 16) -> float:
     return tot / max(fr, 1)
 
 
+def ncu_warp_instructions(kernels):
+    """Warp-instructions per launch of the listed kernels (the newest profiles/r*_ncu_kernels.json), or None."""
+    import glob
+    found = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_kernels.json")))
+    if not found:
+        return None
+    d = json.load(open(found[-1]))
+    tot = 0.0
+    for k in kernels:
+        hit = [v.get("warp_instructions") for name, v in d.items() if k in name]
+        if not hit or hit[0] is None:
+            return None
+        tot += hit[0]
+    return tot
+
+
+ISSUE_PEAK = 148 * 4 * 1.965e9     # warp-instructions per second: 148 SMs x 4 schedulers x 1 per clock at 1965 MHz
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -711,12 +730,15 @@ def main():
     # ---- the same end-to-end loop for the FEATURE modes alone (Segment Features, no spectrum output), 16-bit PCM in ----
     # What a WAV-file workload looks like: int16 samples cross PCIe as they are (fa_submit_pcm_i16_batch, converted on the
     # device) and only the result tables come back.  Reported beside `e2e`; the headline `e2e` above keeps the spectrum.
+    # three batches in flight here: upload, kernels and download of three different batches overlap (the float32 headline above
+    # is bound by its 829 MB download alone; these modes move 160 MB in and 9 / 214 MB out, comparable to the 2 ms of kernels)
+    edepth3 = max(1, min(depth, int(os.environ.get("FA_BENCH_EDEPTH", "3"))))
     e2e_feat = None
     if not args.no_e2e:
         from webspeechanalyzer_b200 import FaConfig
         cfg2 = FaConfig.default(output_level=5, want_spectrum=0)
         engs2, pcm16_hosts = [], []
-        for j in range(edepth):
+        for j in range(edepth3):
             e = Engine(cfg2, device=local)
             e.set_stream(streams[j].cuda_stream)
             e.set_pipeline(1 if args.serial else args.e2e_pipeline)
@@ -740,15 +762,15 @@ def main():
         def steps2(k_steps):
             inflight = []
             for k in range(k_steps):
-                j = k % edepth
-                if len(inflight) == edepth:
+                j = k % edepth3
+                if len(inflight) == edepth3:
                     collect2(inflight.pop(0))
                 launch2(j)
                 inflight.append(j)
             while inflight:
                 collect2(inflight.pop(0))
 
-        steps2(2 * edepth)
+        steps2(2 * edepth3)
         barrier()
         t0 = time.perf_counter()
         steps2(args.steps)
@@ -759,7 +781,7 @@ def main():
             dist.all_reduce(tt2, op=dist.ReduceOp.MAX)
         e2e_feat = {"value": world * audio_per_step * args.steps / float(tt2.item()), "unit": "audio-s/s",
                     "h2d_bytes_per_step": int(pcm16_hosts[0].nbytes), "d2h_bytes_per_step": int(seen2[-1]),
-                    "ms_per_step": 1e3 * float(tt2.item()) / args.steps, "batches_in_flight": edepth,
+                    "ms_per_step": 1e3 * float(tt2.item()) / args.steps, "batches_in_flight": edepth3,
                     "path": "Segment Features only (output_level 5, no spectrum output): fa_reset + fa_submit_pcm_i16_batch (pinned int16 "
                             "PCM, converted on the device) + fa_run ... fa_sync + fa_copy_{segments,formants,energy,syllables,features}"}
         for e in engs2:
@@ -772,7 +794,7 @@ def main():
         M = cfg.fft_size // 2
         cfg3 = FaConfig.default(output_level=5, want_spectrum=1, spectrum_format=1)
         engs3, sinks3 = [], []
-        for j in range(edepth):
+        for j in range(edepth3):
             e = Engine(cfg3, device=local)
             e.set_stream(streams[j].cuda_stream)
             e.set_pipeline(1 if args.serial else args.e2e_pipeline)
@@ -795,15 +817,15 @@ def main():
         def steps3(k_steps):
             inflight = []
             for k in range(k_steps):
-                j = k % edepth
-                if len(inflight) == edepth:
+                j = k % edepth3
+                if len(inflight) == edepth3:
                     collect3(inflight.pop(0))
                 launch3(j)
                 inflight.append(j)
             while inflight:
                 collect3(inflight.pop(0))
 
-        steps3(2 * edepth)
+        steps3(2 * edepth3)
         barrier()
         t0 = time.perf_counter()
         steps3(args.steps)
@@ -814,7 +836,7 @@ def main():
             dist.all_reduce(tt3, op=dist.ReduceOp.MAX)
         e2e_byte = {"value": world * audio_per_step * args.steps / float(tt3.item()), "unit": "audio-s/s",
                     "h2d_bytes_per_step": int(pcm16_hosts[0].nbytes), "d2h_bytes_per_step": int(seen3[-1]),
-                    "ms_per_step": 1e3 * float(tt3.item()) / args.steps, "batches_in_flight": edepth,
+                    "ms_per_step": 1e3 * float(tt3.item()) / args.steps, "batches_in_flight": edepth3,
                     "path": "the C2 outputs with the spectrum as getByteFrequencyData rows (spectrum_format FA_SPECTRUM_U8) and int16 PCM in: "
                             "fa_reset + fa_submit_pcm_i16_batch + fa_set_spectrum_sink_raw + fa_run ... fa_sync + fa_copy_*"}
         for e in engs3:
@@ -842,8 +864,15 @@ def main():
             vals = [ncu_traffic(name) for name in stage_kernels[k]]
             return None if any(v is None for v in vals) else float(sum(vals))
 
+        def issue_floor_ms(k):    # the stage's executed warp-instructions (ncu) at one per scheduler and clock
+            wi = ncu_warp_instructions(stage_kernels[k])
+            return None if wi is None else 1e3 * wi / ISSUE_PEAK
+
         stages = {k: {"ms": float(stage_ms[i]), "share": shares[k], "algorithmic_bytes": int(alg[k]),
                       "ncu_dram_bytes": stage_traffic(k),
+                      "hbm_floor_ms": 1e3 * alg[k] / (peak * 1e9),
+                      "issue_floor_ms": issue_floor_ms(k),
+                      "frac_of_min_bound": (max(1e3 * alg[k] / (peak * 1e9), issue_floor_ms(k) or 0.0) / stage_ms[i]) if stage_ms[i] > 0 else None,
                       "achieved_gbs": alg[k] / (stage_ms[i] * 1e-3) / 1e9 if stage_ms[i] > 0 else None,
                       "frac_of_hbm_peak": alg[k] / (stage_ms[i] * 1e-3) / 1e9 / peak if stage_ms[i] > 0 else None}
                   for i, k in enumerate(names)}

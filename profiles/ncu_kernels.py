@@ -1,5 +1,5 @@
-"""Extract per-kernel facts from an `ncu --set full` report into profiles/r1_ncu_kernels.json.
-usage: ncu -i gpurun_out/prof.ncu-rep --page raw --csv | python profiles/ncu_kernels.py profiles/r1_ncu_kernels.json"""
+"""Extract per-kernel facts from an `ncu --set full` report into profiles/r<round>_ncu_kernels.json.
+usage: ncu -i gpurun_out/prof.ncu-rep --page raw --csv | python profiles/ncu_kernels.py profiles/r<round>_ncu_kernels.json"""
 import csv
 import json
 import sys

@@ -166,7 +166,7 @@ struct fa_handle {
                             // 2.79 GB through HBM and needs no 4 KB-per-frame magnitude buffer when no dB rows are wanted
   bool use_fused() const { return k1_fused != 0 && N == 2048 && chunk_frames <= 0 && !frames_mode; }
   DevBuf g_segs, g_syls, g_formants, g_energy, g_features;
-  DevBuf d_curve_work, d_curve_status;   // level 12 (K8)
+  DevBuf d_curve_work, d_curve_status, d_curve_list, d_curve_count;   // level 12 (K8)
   DevBuf d_pt_amp;                       // level 3: amplitudes of the pool points
   size_t row_bytes() const { return cfg.output_level == FA_LEVEL_SEGMENTS ? sizeof(fa_track_point) : 9 * sizeof(float); }
   int n_weights = 0;
@@ -366,7 +366,7 @@ int fa_destroy(fa_handle* h) {
                     &h->d_win, &h->d_tw, &h->d_tws, &h->d_ws, &h->d_bmi, &h->d_bmw, &h->d_emph, &h->d_spill, &h->d_trkbase, &h->d_trk_i,
                     &h->d_trk_d, &h->d_trk_slot, &h->d_pt_i, &h->d_pt_e, &h->d_rows, &h->d_rowlist, &h->d_segs, &h->d_syls,
                     &h->d_formants, &h->d_energy, &h->d_features, &h->d_counts, &h->d_off, &h->g_segs, &h->g_syls,
-                    &h->g_formants, &h->g_energy, &h->g_features, &h->d_chunks, &h->d_state, &h->d_specdb, &h->d_specq, &h->d_fix, &h->d_cchunks, &h->d_cstate, &h->d_frT, &h->d_frk, &h->d_frthr, &h->d_frctl, &h->d_frv, &h->d_epochs, &h->d_work, &h->d_k3q, &h->d_curve_work, &h->d_curve_status, &h->d_pt_amp})
+                    &h->g_formants, &h->g_energy, &h->g_features, &h->d_chunks, &h->d_state, &h->d_specdb, &h->d_specq, &h->d_fix, &h->d_cchunks, &h->d_cstate, &h->d_frT, &h->d_frk, &h->d_frthr, &h->d_frctl, &h->d_frv, &h->d_epochs, &h->d_work, &h->d_k3q, &h->d_curve_work, &h->d_curve_status, &h->d_curve_list, &h->d_curve_count, &h->d_pt_amp})
     b->release();
   for (HostBuf* b : {&h->h_pcm, &h->h_frames, &h->h_meta, &h->h_counts, &h->h_off, &h->h_segs, &h->h_syls, &h->h_formants, &h->h_energy,
                      &h->h_features})
@@ -762,6 +762,8 @@ static int prepare(fa_handle* h) {
     if (h->cfg.output_level == FA_LEVEL_SYL_CURVES) {
       FA_CUDA(h->d_curve_work.reserve(Fz * 34 * sizeof(double)));
       FA_CUDA(h->d_curve_status.reserve((Fz + nz) * 4 * sizeof(int)));
+      FA_CUDA(h->d_curve_list.reserve((Fz + nz) * sizeof(int2)));
+      FA_CUDA(h->d_curve_count.reserve(kMaxSub * sizeof(int)));
     }
     if (h->cfg.output_level == FA_LEVEL_UTTERANCE) {
       FA_CUDA(h->d_features.reserve((size_t)ub * FA_N_UTT_FEATURES * sizeof(double)));
@@ -1034,7 +1036,8 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
       cp.frame_off = meta + 2 * n; cp.n_utt = n; cp.utt_begin = sb.u0; cp.utt_count = sb.u1 - sb.u0;
       cp.segs = g.segs; cp.n_segs = g.n_segs; cp.syls = g.syls; cp.n_syls = g.n_syls; cp.formants = g.formants; cp.energy = g.energy;
       cp.epochs = h->k3_mode == 1 ? h->d_epochs.as<FaEpoch>() : nullptr;
-      cp.row_slices = (int)std::min<long long>(64, std::max<long long>(1, (sb.r1 - sb.r0) / std::max(1, sb.u1 - sb.u0) / 2048));
+      cp.list = h->d_curve_list.as<int2>() + (sb.r0 + sb.u0); cp.list_count = h->d_curve_count.as<int>() + slot;
+      cp.list_cap = (sb.r1 - sb.r0) / 2 + (sb.u1 - sb.u0);
       cp.work = h->d_curve_work.as<double>(); cp.status = h->d_curve_status.as<int>();
       cp.rows = h->d_features.as<double>(); cp.n_feat = cnt + 4 * n;
       FA_CUDA(fa_launch_curves(cp, s3, &h->launches));
@@ -1067,6 +1070,7 @@ static int run_device(fa_handle* h, bool with_h2d, bool with_sink) {
   h->launches = 0;
   if (c.output_level >= 3) FA_CUDA(cudaMemsetAsync(h->d_counts.p, 0, sizeof(int) * 6 * (size_t)n, s));
   if (c.output_level >= 3 && h->k3_mode == 1) FA_CUDA(cudaMemsetAsync(h->d_k3q.p, 0, 2 * kMaxSub * sizeof(int), s));
+  if (c.output_level == FA_LEVEL_SYL_CURVES) FA_CUDA(cudaMemsetAsync(h->d_curve_count.p, 0, kMaxSub * sizeof(int), s));
   FA_CUDA(cudaMemsetAsync(h->d_fix.p, 0, 3 * sizeof(int), s));
   h->fixups[0] = h->fixups[1] = h->fixups[2] = -1;
   FA_CUDA(cudaEventRecord(h->ev[0], s));

@@ -182,7 +182,8 @@ struct FaCurveParams {
   fa_syllable* syls; const int* n_syls;  // .reserved is set where the reference's make_coeffs would have thrown
   const float* formants; const float* energy;
   const FaEpoch* epochs;              // see FaFeatureParams
-  int row_slices;                     // CTAs per utterance (grid.y)
+  int2* list; int* list_count;        // work list of this sub-batch: (utterance, syllable) pairs, and its length (zeroed per run)
+  long long list_cap;                 // upper bound of the list length (frames / 2 + utterances of the sub-batch)
   double* work;                       // [F_total][34] powers / ordinates of the four fits of the syllable that owns the row
   int* status;                        // [(F_total + n_utt)][4] FA_CURVE_* of every fit
   double* rows;                       // [(F_total + n_utt)][23] per-utterance rows at base frame_off[u] + u

@@ -1065,8 +1065,7 @@ __device__ __forceinline__ void accumulate_fm2(const FaSegmentParams& p, WarpSha
   //      bit into the peak's claimant mask wmask[set][bin] (one shared-memory atomic per claim, all claims in parallel) ----
   int idA = S.t_id[lane], idB = -1;
   {
-    int B = p.B;
-    asm volatile("" : "+r"(B));   // ordinary register (ptxas uniform-register hazard, see fa_peaks.cu)
+    const int B = p.B;
     auto window = [&](const int slot, int& id, int& wlo) -> unsigned {
       if (id < 0) return 0u;
       const int gap = n_label - S.t_lf[slot];
