@@ -716,6 +716,12 @@ class Interp:
         def filter_(this, a):
             return JSArray([v for i, v in enumerate(list(this.a)) if truthy(call(a[0], UNDEF, [v, float(i), this]))])
 
+        def find_index(this, a):
+            for i, v in enumerate(list(this.a)):
+                if truthy(call(a[0], UNDEF, [v, float(i), this])):
+                    return float(i)
+            return -1.0
+
         def join(this, a):
             sep = ',' if not a or a[0] is UNDEF else to_str(a[0])
             return sep.join('' if (e is None or e is UNDEF) else to_str(e) for e in this.a)
@@ -735,7 +741,7 @@ class Interp:
 
         return {k: Native(f, k) for k, f in dict(
             push=push, pop=pop, shift=shift, slice=slice_, splice=splice, concat=concat, reduce=reduce, fill=fill,
-            indexOf=index_of, map=map_, forEach=for_each, filter=filter_, join=join, sort=sort,
+            indexOf=index_of, findIndex=find_index, map=map_, forEach=for_each, filter=filter_, join=join, sort=sort,
             toString=lambda this, a: to_str(this)).items()}
 
     def _make_typed_proto(self):
@@ -749,7 +755,8 @@ class Interp:
             n = len(this.a)
             return JSTyped(this.kind, this.a[_slice_idx(a, 0, n):_slice_idx(a, 1, n)])
 
-        return {'fill': Native(fill, 'fill'), 'slice': Native(slice_, 'slice')}
+        # subarray: a view in JS; the callers here only read it, so a copy is equivalent
+        return {'fill': Native(fill, 'fill'), 'slice': Native(slice_, 'slice'), 'subarray': Native(slice_, 'subarray')}
 
     def _make_promise_proto(self):
         return {
@@ -824,7 +831,9 @@ class Interp:
                 return JSArray([UNDEF] * int(a[0]))
             return JSArray(list(a))
         arr = nat(array_ctor, 'Array')
-        arr.props = {'isArray': nat(lambda this, a: type(a[0]) is JSArray if a else False, 'isArray')}
+        arr.props = {'isArray': nat(lambda this, a: type(a[0]) is JSArray if a else False, 'isArray'),
+                     # Array.from(arrayLike): a plain array of the elements (the Node shim copies typed-array rows with it)
+                     'from': nat(lambda this, a: JSArray(list(a[0].a)) if a and type(a[0]) in (JSArray, JSTyped) else JSArray([]), 'from')}
         g['Array'] = arr
 
         def typed_ctor(kind):

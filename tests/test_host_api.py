@@ -1,5 +1,6 @@
 """Host-side mirror of the formantanalyzer API: configure() truthiness rules, string rejections, WAV decoding,
 toFixed(3), and the callback shapes / order of P() checked against the literal transliteration."""
+import json
 import numpy as np
 import pytest
 
@@ -169,3 +170,95 @@ def test_export_rows_json_csv_follow_localstore():
     # level 4 is not stored by the app; rows of the wrong width are refused
     assert export.stored_rows(4, 1, "f.wav", [(0, [], [0.0, 1.0], [np.zeros(9, np.float32)])]) == []
     assert export.stored_rows(5, 1, "f.wav", [(0, [], [0.0, 1.0], [1.0] * 52)]) == []
+
+
+# ---------------------------------------------------------------------------- the Node shim's JavaScript, executed
+def _norm(x):
+    """callback payloads -> nested lists of floats / strings (numpy rows, tuples and JS arrays alike)."""
+    import numpy as _np
+    if isinstance(x, _np.ndarray):
+        return [_norm(v) for v in x.tolist()]
+    if isinstance(x, (list, tuple)):
+        return [_norm(v) for v in x]
+    if isinstance(x, (int, float, _np.integer, _np.floating)):
+        return float(x)
+    return x
+
+
+@pytest.mark.parametrize("level", [3, 4, 5, 10, 11, 12, 13])
+def test_node_shim_segment_callbacks_executed_by_minijs(level):
+    """webspeechanalyzer_b200/node/index.js cannot run here (no Node), but its segmentCallbacks() -- the function that turns
+    the addon's tables into the reference's callback arguments at every level -- is plain JavaScript: oracle/minijs executes it
+    on the oracle's tables and the result must equal the Python twin's (which is pinned to the reference's own P())."""
+    import os
+    from oracle import oracle
+    from oracle.minijs.interp import Interp, JSArray, JSObject, JSTyped, UNDEF
+    from oracle.minijs.run_reference import _to_py
+    from webspeechanalyzer_b200 import FaConfig, synth_speech
+    from webspeechanalyzer_b200.engine import UtteranceResult
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "webspeechanalyzer_b200", "node", "index.js")).read()
+    fn = src[src.index("function segmentCallbacks"): src.index("function LaunchAudioNodes")]
+    sr, step = 16000, 15.0
+    pcm = np.concatenate([synth_speech(4 * sr, sr, 5, k) for k in range(2)])
+    cfg = FaConfig.default(output_level=level, window_step_ms=step)
+    an = oracle.analyze_frames(cfg, oracle.frontend(cfg, pcm, sr, spectrum=False)["frames"])
+    res = UtteranceResult({}, an.segments, an.formants, an.energy, an.syllables, an.features, an.utterance, an.track_points)
+    labels = [3.0, 1.0]
+    want = api.segment_callbacks(level, step, labels, res)
+    assert len(want) >= 2
+    it = Interp()
+    it.run("var a={window_step:%r};" % step + fn)
+    segs = JSArray([JSObject({"start": float(s["start"]), "len": float(s["len"]), "stored": float(s["stored"]),
+                              "nSyllables": float(s["n_syllables"]), "firstSyllable": float(s["first_syllable"]),
+                              "rowOffset": float(s["row_offset"])}) for s in an.segments])
+    syls = JSArray([JSObject({"storedSeg": float(y["stored_seg"]), "start": float(y["start"]), "len": float(y["len"]),
+                              "flag": float(y["reserved"])}) for y in an.syllables])
+    feats = an.utterance if level == 11 else an.features
+    props = {"segments": segs, "syllables": syls, "formants": JSTyped("Float32Array", [float(x) for x in an.formants.ravel()]),
+             "features": JSTyped("Float64Array", [float(x) for x in feats.ravel()])}
+    if level == 3:
+        tp = an.track_points
+        props["trackPoints"] = JSTyped("Float64Array", [float(x) for c in ("frame", "lo", "hi", "bin", "amp", "energy") for x in tp[c]])
+    got = _to_py(it.call(it.globals.vars["segmentCallbacks"], UNDEF, [float(level), JSObject(props), JSArray(list(labels))]))
+    a, b = _norm(got), _norm(want)
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert np.array_equal(np.array(x[0]), np.array(y[0])) and x[1] == y[1]
+        assert json.dumps(x[2:], allow_nan=True) == json.dumps(y[2:], allow_nan=True)
+
+
+def test_node_shim_configure_executed_by_minijs_matches_the_reference_module():
+    """node/index.js configure() run by oracle/minijs on the settings objects of tests/golden/ref_js_api.json: it must leave
+    what the reference's own configure() (@B3292, executed the same way) left -- same rule as the Python mirror's test: for
+    partial objects the reference stores `undefined` into the `null !== x` fields, the shims keep the previous value."""
+    import os
+    from conftest import GOLDEN
+    from oracle.minijs.interp import Interp, JSObject, UNDEF
+    from oracle.minijs.run_reference import _to_py
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "webspeechanalyzer_b200", "node", "index.js")).read()
+    defaults = src[src.index("const DEFAULTS = Object.freeze({"): src.index("let a = Object.assign")]
+    defaults = defaults.replace("const DEFAULTS = Object.freeze({", "var a = {").replace("});", "};")
+    fn = src[src.index("function configure(e)"): src.index("function decodeWav")]
+    doc = json.load(open(os.path.join(GOLDEN, "ref_js_api.json")))
+    fields = ("plot_enable", "spec_type", "output_level", "plot_len", "f_min", "f_max", "N_fft_bins", "N_mel_bins", "window_width",
+              "window_step", "pause_length", "min_seg_length", "auto_noise_gate", "voiced_max_dB", "voiced_min_dB", "pre_norm_gain",
+              "high_f_emph")
+    nullable = ("spec_type", "f_min", "high_f_emph", "auto_noise_gate", "voiced_min_dB")
+
+    def js(v):
+        return float(v) if isinstance(v, (int, float)) and not isinstance(v, bool) else (None if v is None else v)
+
+    for case in doc["configure"]:
+        it = Interp()
+        it.run(defaults + fn)
+        before = _to_py(it.globals.vars["a"])
+        it.call(it.globals.vars["configure"], UNDEF, [JSObject({k: js(v) for k, v in case["cfg"].items()})])
+        mine, ref = _to_py(it.globals.vars["a"]), case["settings"]
+        partial = not all(f in case["cfg"] for f in nullable)
+        for f in fields:
+            if partial and ref[f] is None and f in nullable:
+                assert mine[f] == before[f]
+                continue
+            assert mine[f] == ref[f], (f, mine[f], ref[f])

@@ -131,6 +131,8 @@ typedef struct {
   fa_syllable* syls;
   float *formants, *energy, *spectrum;
   double* features;
+  fa_track_point* points;   /* level 3: the points of the ranked tracks (their headers come in `syls`) */
+  int level;
 } job_t;
 
 static void job_execute(napi_env env, void* data) {
@@ -150,7 +152,9 @@ static void job_execute(napi_env env, void* data) {
     fa_config cfg;
     fa_get_config(h, &cfg);
     j->fft_half = cfg.fft_size / 2;
-    j->feat_width = cfg.output_level == FA_LEVEL_UTTERANCE ? FA_N_UTT_FEATURES : FA_N_FEATURES;
+    j->level = cfg.output_level;
+    j->feat_width = cfg.output_level == FA_LEVEL_UTTERANCE ? FA_N_UTT_FEATURES
+                    : cfg.output_level == FA_LEVEL_SYL_CURVES ? FA_N_CURVE_FEATURES : FA_N_FEATURES;
     j->want_spec = j->want_spec && !j->is_frames && (cfg.want_spectrum || cfg.output_level <= 2);
     j->segs = (fa_segment*)malloc(sizeof(fa_segment) * (size_t)(c->segments + 1));
     j->syls = (fa_syllable*)malloc(sizeof(fa_syllable) * (size_t)(c->syllables + 1));
@@ -159,16 +163,23 @@ static void job_execute(napi_env env, void* data) {
     /* level 11 rows are the 264-dim utterance distributions (cumulative, one per stored segment) */
     j->features = (double*)malloc(sizeof(double) * (size_t)j->feat_width * (size_t)(c->feature_rows + 1));
     if (j->want_spec) j->spectrum = (float*)malloc(sizeof(float) * (size_t)j->fft_half * (size_t)(c->frames + 1));
-    if (!j->segs || !j->syls || !j->formants || !j->energy || !j->features || (j->want_spec && !j->spectrum)) {
+    if (j->level == FA_LEVEL_SEGMENTS) j->points = (fa_track_point*)malloc(sizeof(fa_track_point) * (size_t)(c->formant_rows + 1));
+    if (!j->segs || !j->syls || !j->formants || !j->energy || !j->features || (j->want_spec && !j->spectrum) ||
+        (j->level == FA_LEVEL_SEGMENTS && !j->points)) {
       j->rc = FA_ERR_OUT_OF_MEMORY;
       snprintf(j->err, sizeof(j->err), "out of memory");
       return;
     }
     rc = fa_copy_segments(h, 0, j->segs, (size_t)c->segments);
     if (rc >= 0) rc = fa_copy_syllables(h, 0, j->syls, (size_t)c->syllables);
-    if (rc >= 0) rc = fa_copy_formants(h, 0, j->formants, (size_t)c->formant_rows);
-    if (rc >= 0) rc = fa_copy_energy(h, 0, j->energy, (size_t)c->formant_rows);
+    if (j->level == FA_LEVEL_SEGMENTS) {   /* raw ranked tracks: fa_track headers in `syls`, their points here; no formant rows */
+      if (rc >= 0) rc = fa_copy_track_points(h, 0, j->points, (size_t)c->formant_rows);
+    } else {
+      if (rc >= 0) rc = fa_copy_formants(h, 0, j->formants, (size_t)c->formant_rows);
+      if (rc >= 0) rc = fa_copy_energy(h, 0, j->energy, (size_t)c->formant_rows);
+    }
     if (rc >= 0) rc = j->feat_width == FA_N_UTT_FEATURES ? fa_copy_utterance_features(h, 0, j->features, (size_t)c->feature_rows)
+                  : j->feat_width == FA_N_CURVE_FEATURES ? fa_copy_curve_features(h, 0, j->features, (size_t)c->feature_rows)
                                                          : fa_copy_features(h, 0, j->features, (size_t)c->feature_rows);
     if (rc >= 0 && j->want_spec) rc = fa_copy_spectrum(h, 0, j->spectrum, (size_t)c->frames);
     if (rc >= 0) rc = FA_OK;
@@ -227,18 +238,33 @@ static void job_complete(napi_env env, napi_status status, void* data) {
       napi_value o;
       napi_create_object(env, &o);
       set_i(env, o, "storedSeg", j->syls[i].stored_seg); set_i(env, o, "start", j->syls[i].start); set_i(env, o, "len", j->syls[i].len);
+      set_i(env, o, "flag", j->syls[i].reserved);     /* level 12: make_coeffs threw at or before this syllable */
       napi_set_element(env, syls, (uint32_t)i, o);
     }
-    napi_set_named_property(env, res, "syllables", syls);
-    napi_set_named_property(env, res, "formants", make_f32(env, j->formants, 9 * (size_t)c->formant_rows));
-    napi_set_named_property(env, res, "energy", make_f32(env, j->energy, 3 * (size_t)c->formant_rows));
+    napi_set_named_property(env, res, "syllables", syls);     /* level 3: the fa_track headers (start = first point, len = points) */
+    const size_t frows = j->level == FA_LEVEL_SEGMENTS ? 0 : (size_t)c->formant_rows;
+    napi_set_named_property(env, res, "formants", make_f32(env, j->formants, 9 * frows));
+    napi_set_named_property(env, res, "energy", make_f32(env, j->energy, 3 * frows));
+    if (j->level == FA_LEVEL_SEGMENTS) {
+      /* track points as six parallel columns: frame, lo, hi, bin, amp, energy */
+      const size_t np = (size_t)c->formant_rows;
+      double* col = (double*)malloc(sizeof(double) * 6 * (np + 1));
+      if (col) {
+        for (size_t i = 0; i < np; i++) {
+          col[i] = j->points[i].frame; col[np + i] = j->points[i].lo; col[2 * np + i] = j->points[i].hi;
+          col[3 * np + i] = j->points[i].bin; col[4 * np + i] = j->points[i].amp; col[5 * np + i] = j->points[i].energy;
+        }
+        napi_set_named_property(env, res, "trackPoints", make_f64(env, col, 6 * np));
+        free(col);
+      }
+    }
     napi_set_named_property(env, res, "features", make_f64(env, j->features, (size_t)j->feat_width * (size_t)c->feature_rows));
     if (j->want_spec) napi_set_named_property(env, res, "spectrum", make_f32(env, j->spectrum, (size_t)j->fft_half * (size_t)c->frames));
     napi_resolve_deferred(env, j->deferred, res);
   }
   napi_delete_reference(env, j->pcm_ref);
   napi_delete_async_work(env, j->work);
-  free(j->segs); free(j->syls); free(j->formants); free(j->energy); free(j->features); free(j->spectrum);
+  free(j->segs); free(j->syls); free(j->formants); free(j->energy); free(j->features); free(j->spectrum); free(j->points);
   free(j);
 }
 

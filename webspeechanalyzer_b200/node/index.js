@@ -9,7 +9,9 @@
  * the extension context_source 4 takes {pcm: Float32Array, sampleRate}; 2 (<audio>) and 3 (mic) reject with
  * "Invalid audio source".  Levels 1-2 (canvas only in the reference) call back once with the dB spectrum.
  *
- * Status: written against the C-ABI and compile-checked; NOT executed in the build image (no node there).
+ * Status: written against the C-ABI and compile-checked; no Node in the build image, so the file as a whole has not run --
+ * but its two pure functions have: configure() and segmentCallbacks() are executed by oracle/minijs in
+ * tests/test_host_api.py (against the reference's own configure() and against the Python twin at every output level).
  */
 const native = require('./fa_b200.node');
 
@@ -110,13 +112,48 @@ function segmentCallbacks(level, res, labels) {
     });
     return calls;
   }
+  if (level === 3) {
+    // b(e, label, s[e]) when s[e].length > 0 (P() @B28869, level-3 branch): the ranked 18-field track arrays of
+    // accumulate_fm @B35952, rebuilt from the fa_track headers (in `syllables`) and the six point columns
+    const P = res.trackPoints, np = P.length / 6;
+    stored.forEach((s, e) => {
+      const tracks = [];
+      for (let k = 0; k < s.nSyllables; k++) {
+        const t = res.syllables[s.firstSyllable + k];
+        const col = (c) => Array.from(P.subarray(c * np + t.start, c * np + t.start + t.len));
+        const fr = col(0), lo = col(1), hi = col(2), bins = col(3), amp = col(4), en = col(5);
+        const h = bins.length - 1, o = bins[h];
+        let vel = 0;
+        if (h >= 3) vel = (o - bins[h - 1] + (bins[h - 2] - bins[h - 1]) + (bins[h - 3] - bins[h - 2])) / 3;
+        else if (h === 2) vel = (o - bins[h - 1] + (bins[h - 2] - bins[h - 1])) / 2;
+        else if (h === 1) vel = o - bins[h - 1];
+        let se = 0, seb = 0, span = 0;
+        for (let i = 0; i <= h; i++) { se += en[i]; seb += en[i] * bins[i]; span += hi[i] - lo[i] + 1; }
+        tracks.push([lo[h], hi[h], fr[h], fr[h], vel, o, amp[h], fr, lo, hi, bins, amp, en, se, h + 1, seb, 0, span]);
+      }
+      if (tracks.length) calls.push([e, labels, tracks]);
+    });
+    return calls;
+  }
   stored.forEach((s, e) => {
     const ci = res.segments[e];
     const rows = [];
     for (let r = 0; r < s.len; r++) rows.push(res.formants.subarray(9 * (s.rowOffset + r), 9 * (s.rowOffset + r + 1)));
-    if (level === 13 || level === 10) {
+    if (level === 13 || level === 12 || level === 10) {
       const syl = res.syllables.slice(s.firstSyllable, s.firstSyllable + s.nSyllables);
       if (!syl.length) return;
+      if (level === 12) {
+        // make_coeffs @B34527 returns the rows made before numeric threw; P() fires when there is at least one, with the time
+        // stamps of ALL the segment's syllables
+        let ok = syl.findIndex((y) => y.flag);
+        if (ok < 0) ok = syl.length;
+        if (!ok) return;
+        const t12 = syl.map((y) => [((ci.start + y.start) * step).toFixed(3), ((y.len + 1) * step).toFixed(3)]);
+        const rows12 = [];
+        for (let k = 0; k < ok; k++) rows12.push(Array.from(res.features.subarray(23 * (s.firstSyllable + k), 23 * (s.firstSyllable + k + 1))));
+        calls.push([e, labels, t12, rows12]);
+        return;
+      }
       const times = syl.map((y) => [((ci.start + y.start) * step).toFixed(3), ((y.len + 1) * step).toFixed(3)]);
       const payload = level === 13
         ? syl.map((_, k) => Array.from(res.features.subarray(53 * (s.firstSyllable + k), 53 * (s.firstSyllable + k + 1))))
