@@ -10,7 +10,7 @@
  * "Invalid audio source".  Levels 1-2 (canvas only in the reference) call back once with the dB spectrum.
  *
  * Status: written against the C-ABI and compile-checked; no Node in the build image, so the file as a whole has not run --
- * but its two pure functions have: configure() and segmentCallbacks() are executed by oracle/minijs in
+ * but its two pure functions have: configure() and segmentCallbacks() are executed by the test suite's JavaScript interpreter in
  * tests/test_host_api.py (against the reference's own configure() and against the Python twin at every output level).
  */
 const native = require('./fa_b200.node');
