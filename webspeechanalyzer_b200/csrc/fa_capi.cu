@@ -338,7 +338,7 @@ int fa_create(const fa_config* cfg, int device, fa_handle** out) {
   h->k3_workers = prop.multiProcessorCount * 14;   // 7 CTAs x 2 warps per SM (shared memory bound)
   if (const char* ev = getenv("FA_K3_WORKERS")) { const int v = atoi(ev); if (v >= 32 && v <= 1 << 16) h->k3_workers = v; }
   // every environment knob is read here, once per handle -- nothing on the launch path calls getenv
-  if (const char* ev = getenv("FA_K3_IMPL")) h->k3_impl = atoi(ev) == 1 ? 1 : 2;
+  if (const char* ev = getenv("FA_K3_IMPL")) { const int v = atoi(ev); h->k3_impl = v == 1 ? 1 : v == 3 ? 3 : 2; }
   if (const char* ev = getenv("FA_K3_WARPS")) { const int v = atoi(ev); if (v >= 1 && v <= 4) h->k3_warps = v; }
   if (const char* ev = getenv("FA_K3_REGS")) h->k3_regs = atoi(ev);
   if (getenv("FA_K3_FINALIZE_HBM")) h->k3_finalize_smem = 0;

@@ -145,19 +145,25 @@ __device__ __forceinline__ void seg_reset(ScanState& st, WarpShared& S, int star
 //   e > x/100  <=>  100 e > x        T/k < 30 v  <=>  T < 30 v k        v > v0/10  <=>  10 v > v0
 //   parseInt(v0/20) = floor(v0/20)   (v0 < 2^32: unsigned division by a constant)
 // flags: bit 0 = the T/k test asked for L(0), bit 1 = the test was evaluated; Tb, kb = T and k in front of the test
+// v(y) of C() @B28506: fdlibm log10 + pow, a few thousand instructions when inlined -- and only reached when the gate's maximum
+// moves.  Out of line: it keeps the scan kernels' hot loops inside the instruction cache.
+__device__ __noinline__ double gate_v_of_y(const double y) {
+  const double t = fa_js_log10(y);
+  if (t > 7) return fa_js_parse_int(fa_js_pow(10, t - 3) / 20);
+  if (t > 6) return fa_js_parse_int(fa_js_pow(10, t - 3) / 2);
+  if (t > 4) return fa_js_parse_int(fa_js_pow(10, t - 2) / 2);
+  if (t > 2) return fa_js_parse_int(fa_js_pow(10, t / 3));
+  if (t > 1) return fa_js_parse_int(y / 10);
+  return 1;
+}
+
 __device__ __forceinline__ int gate_update_rec(ScanState& st, double e, double& Tb, int& kb) {
   int flags = 0;
   st.w++;
   if (e > st.y || (st.w > 40 && e > 2 * st.v)) {
     if (e >= st.y) { st.w = 0; st.x = st.y = e; }
     else if (100 * e > st.x) { st.y -= fa_js_parse_int(st.y / 8); st.w = 35; }
-    const double t = fa_js_log10(st.y);
-    if (t > 7) st.v = fa_js_parse_int(fa_js_pow(10, t - 3) / 20);
-    else if (t > 6) st.v = fa_js_parse_int(fa_js_pow(10, t - 3) / 2);
-    else if (t > 4) st.v = fa_js_parse_int(fa_js_pow(10, t - 2) / 2);
-    else if (t > 2) st.v = fa_js_parse_int(fa_js_pow(10, t / 3));
-    else if (t > 1) st.v = fa_js_parse_int(st.y / 10);
-    else st.v = 1;
+    st.v = gate_v_of_y(st.y);
     st.v0 = st.v;
     Tb = st.T; kb = st.k;
     flags = 2;
@@ -1373,6 +1379,313 @@ __global__ void __launch_bounds__(kBound, 1) fa_segment2_kernel(const FaSegmentP
 
 
 // =====================================================================================================================
+// K3 v3 (impl 3): the serial scan as a two-warp pipeline per utterance -- warp specialisation inside the CTA.
+//
+// Only the CONTROL part of D() is sequential on its own (candidate filter by the gate, the start / pause tests, the adaptive
+// gate): it never reads what accumulate_fm writes (see Mode 1 below).  So one warp (the PRODUCER) runs the control part of every
+// frame and hands the tracker one 64-byte record per frame through a ring in shared memory: which clears happen, whether the
+// frame reaches accumulate_fm, with which label and thresholds, and the scalars of a finalisation.  The second warp (the
+// CONSUMER) only tracks: accept mask from the recorded gate value, accumulate_fm2, finalize_copy, clears -- the same device
+// functions as fa_segment2_kernel, called with the same arguments in the same order => the same bits.  The producer runs up to
+// kRing frames ahead; the tracker's chain loses the filter's ballots / reductions and the gate's FP64 tests (0.8 of 3.7 us per
+// frame on C2), and the kernel has twice the resident warps.
+// A CTA = 4 producer warps (warpgroup 0) + 4 consumer warps (warpgroup 1) for 4 utterances; the producers give registers back
+// (setmaxnreg.dec) and the consumers take them (setmaxnreg.inc), so that two CTAs stay resident per SM.
+// Overflow rules as in fa_segment2_kernel: > 32 accepted peaks in a frame or > 64 live tracks => overflow = 2 => the general
+// kernel redoes the utterance in the second launch.
+// =====================================================================================================================
+constexpr int kRing = 256;                // frames the control warp may run ahead (an utterance of <= 256 frames never blocks it:
+                                          // it finishes early and leaves the schedulers to the tracking warps -- with a 32-frame
+                                          // ring the producers' wait loop was 28 % of the kernel's instructions)
+constexpr int kFins = 80;                 // finalisations in flight: two of them are >= 4 frames apart (2 voiced + 2 pause frames), so
+                                          // <= kRing / 4 = 64 lie inside the ring; a slot is reused only after its frame was consumed
+constexpr int kPipeUtts = 4;              // utterances per CTA (one producer + one consumer warp each)
+constexpr int kPipeRegsProducer = 88, kPipeRegsConsumer = 168;   // 128 * (88 + 168) = the 256 * 128 registers of the launch
+constexpr unsigned kRecClearPre = 1u, kRecVoiced = 2u, kRecFin = 4u, kRecClearPost = 8u, kRecEnd = 16u, kRecStop = 32u;
+
+struct __align__(16) PipeRec {
+  unsigned flags;        // kRec*; kRecStop: overflow code in bits 8..15
+  int label;             // the (possibly stale) frame label accumulate_fm receives
+  int nc;                // candidates of the frame (min(count, maxp))
+  int fin;               // kRecFin / kRecEnd: slot of the finalisation's scalars
+  double v_filter;       // gate at the start of the frame: a candidate is accepted when its amplitude exceeds it
+  double vmin;           // gate after C(h): what accumulate_fm receives
+};
+static_assert(sizeof(PipeRec) == 32, "one record = two 16-byte words");
+
+struct __align__(16) PipeFin {   // what O() @B27088 reads of the control state
+  int n_arg, no_fm_segs, current_frame, c_started;
+  double y, v;
+};
+
+struct PipeShared {
+  PipeRec ring[kRing];
+  PipeFin fins[kFins];
+  volatile int prod;     // records published
+  volatile int cons;     // records consumed
+  volatile int abort_;   // the consumer gave up (capacity): the producer stops
+  int pad;
+};
+
+__device__ __forceinline__ void pipe_producer(const FaSegmentParams& p, PipeShared& Q, const int u, const int lane) {
+  const long long row0 = p.frame_off[u];
+  const int F = (int)(p.frame_off[u + 1] - row0);
+  const int maxp = p.maxp;
+  ScanState st;
+  st.current_frame = 0; st.no_fm_segs = 0; st.c_ci = 0; st.c_started = -1; st.w = 0; st.k = 0;
+  st.y = p.y0; st.v = p.v0; st.x = p.y0; st.v0 = p.v0; st.T = 0;
+  uint32_t pkd_next = 0, amp_next = 0;
+  int nc_next = 0;
+  double g_next = 0;
+  auto prefetch = [&](int t) {
+    const size_t row = (size_t)(row0 + t);
+    nc_next = __ldg(p.ncand + row);
+    g_next = __ldg(p.gsum + row);
+    if (lane < maxp) {
+      const uint2 a = __ldg(reinterpret_cast<const uint2*>(p.cand + row * maxp + lane));
+      pkd_next = a.x; amp_next = a.y;
+    }
+  };
+  auto ctl_reset = [&](int started) { st.c_ci = 0; st.c_started = started; st.no_fm_segs = 0; };   // L() without clear_fm
+  int n_fin = 0;
+  auto put_fin = [&](const int n_arg) -> int {   // (a slot is reused only kFins finalisations later: see kFins)
+    const int slot = n_fin++ % kFins;
+    if (lane == 0) {
+      PipeFin f;
+      f.n_arg = n_arg; f.no_fm_segs = st.no_fm_segs; f.current_frame = st.current_frame; f.c_started = st.c_started;
+      f.y = st.y; f.v = st.v;
+      Q.fins[slot] = f;
+    }
+    return slot;
+  };
+  auto publish = [&](const int slot_t, const PipeRec& r) -> bool {
+    // ring full: the producer is far ahead of the tracker -- sleep instead of spinning (a spinning warp shares its scheduler's
+    // issue slots with a tracking warp)
+    while (slot_t - Q.cons >= kRing) { if (Q.abort_) return false; __nanosleep(400); }
+    if (lane == 0) Q.ring[slot_t % kRing] = r;
+    __syncwarp();
+    __threadfence_block();
+    if (lane == 0) Q.prod = slot_t + 1;
+    return true;
+  };
+  if (F > 0) prefetch(0);
+  int t = 0, stop = 0;
+  for (; t < F; t++) {
+    st.current_frame++;
+    const uint32_t pkd0 = pkd_next, amp0 = amp_next;
+    const int nc = min(nc_next, maxp);
+    if (nc_next > maxp) { stop = 1; break; }
+    const double g = g_next;
+    if (t + 1 < F) prefetch(t + 1);
+    // ---- D() @B25717: filter the candidates of K2 by the gate v (value at frame start) ----
+    const double v = st.v;
+    PipeRec r;
+    r.flags = 0u; r.label = st.c_ci; r.v_filter = v; r.vmin = 0; r.nc = nc; r.fin = 0;
+    int n = 0, pbin = 0;
+    unsigned long long dsum = 0;
+    double h = 2 * v;
+    auto filter = [&](const int c0, const uint32_t pkd, const uint32_t amp) {
+      const bool acc = c0 + lane < nc && (double)amp > v;
+      const unsigned mm = __ballot_sync(FULL, acc);
+      if (mm == 0u) return;
+      const int pk = (pkd >> 16) & 0xff;
+      n += __popc(mm);
+      const uint32_t a = acc ? amp : 0u;
+      dsum += (unsigned long long)__reduce_add_sync(FULL, a & 0xffffu) +
+              ((unsigned long long)__reduce_add_sync(FULL, a >> 16) << 16);
+      const bool hp = acc && !((pkd >> 24) & 1u);
+      const uint32_t mx = __reduce_max_sync(FULL, hp ? amp : 0u);
+      const unsigned who = __ballot_sync(FULL, hp && amp == mx);
+      if (who && (double)mx > h) {
+        h = (double)mx;
+        pbin = __shfl_sync(FULL, pk, __ffs(who) - 1);
+      }
+    };
+    filter(0, pkd0, amp0);
+    for (int c0 = 32; c0 < nc; c0 += 32) {
+      uint2 a = make_uint2(0u, 0u);
+      if (c0 + lane < nc) a = __ldg(reinterpret_cast<const uint2*>(p.cand + (size_t)(row0 + t) * maxp + c0 + lane));
+      filter(c0, a.x, a.y);
+    }
+    if (n > 32) { stop = 2; break; }
+    const double d = (double)dsum;
+    const unsigned long long gi = (unsigned long long)g;
+    const bool weak = gi > dsum && 10ull * dsum < gi - dsum;       // d / (g - d) < 0.1
+    if (st.c_started < 0) {
+      bool strong;                                                  // h (n - 1) / (d - h) > 4
+      if (p.auto_gate) strong = d > h && h * (double)(n - 1) > 4 * (d - h);
+      else strong = (d > h ? h * (double)(n - 1) / (d - h) : 0) > 4;
+      if (n > 0 && pbin > 7 && pbin < p.max_voiced_bin && n > 4 && strong) { ctl_reset(0); r.flags |= kRecClearPre; }
+      else st.no_fm_segs++;
+    }
+    bool fin = false;
+    if (st.c_started >= 0) {
+      if (n == 0 || pbin < 7 || pbin >= p.max_voiced_bin || (n > 3 && weak)) {
+        st.no_fm_segs++;
+        if (st.c_started < 2) st.c_started--;
+        else if ((double)st.no_fm_segs >= p.seg_breaker) {
+          fin = true;
+          r.flags |= kRecFin;
+          r.fin = put_fin(st.c_ci + 1);
+        } else if (p.auto_gate && gate_update(st, h)) { ctl_reset(0); r.flags |= kRecClearPost; }
+      } else {
+        if (p.auto_gate && gate_update(st, h)) { ctl_reset(0); r.flags |= kRecClearPre; }
+        r.flags |= kRecVoiced;
+        r.vmin = st.v;
+        if (st.c_started < 2) st.c_started++; else st.no_fm_segs = 0;
+      }
+    }
+    st.c_ci++;
+    if (fin) ctl_reset(-1);      // the promise's micro-task runs before the next frame
+    if (!publish(t, r)) return;
+  }
+  PipeRec e;
+  e.label = 0; e.nc = 0; e.fin = 0; e.v_filter = 0; e.vmin = 0;
+  if (stop) e.flags = kRecStop | ((unsigned)stop << 8);
+  else { e.flags = kRecEnd; e.fin = put_fin(st.c_ci); }   // segment_truncate @B30800
+  publish(t, e);
+}
+
+__device__ __forceinline__ void pipe_consumer(const FaSegmentParams& p, WarpShared& S, PipeShared& Q, const int u, const int lane) {
+  Bases bs;
+  bs.row0 = p.frame_off[u];
+  bs.F = (int)(p.frame_off[u + 1] - bs.row0);
+  bs.tb = p.track_base[u];
+  bs.tcap = (int)(p.track_base[u + 1] - bs.tb);
+  const int maxp = p.maxp;
+  bs.pb = bs.row0 * maxp;
+  bs.sb = bs.row0 + u;
+  bs.rb = bs.sb;
+  bs.u = u;
+  bs.spill = u;
+  const unsigned lt = (1u << lane) - 1u;
+  ScanState st;
+  st.current_frame = 0; st.no_fm_segs = 0; st.c_ci = 0; st.c_started = -1; st.w = 0; st.k = 0;
+  st.y = p.y0; st.v = p.v0; st.x = p.y0; st.v0 = p.v0; st.T = 0; st.s_energy = 0; st.c_energy = 0;
+  st.n_tr = 0; st.n_pts = 0; st.n_slots = 0; st.n_segs = 0; st.n_stored = 0; st.n_rows = 0; st.n_syls = 0;
+  st.overflow = 0;
+  for (int r = lane; r < ACAP; r += 32) { S.t_id[r] = -1; S.t_wm[r] = 0u; }
+  if (lane <= FA_MAX_BANDS / 32) S.pmask[lane] = 0u;
+  for (int r = lane; r < 2 * FA_MAX_BANDS; r += 32) (&S.wmask[0][0])[r] = 0u;
+  __syncwarp();
+  uint32_t pkd_next = 0, amp_next = 0;
+  unsigned long long pl_next = 0, ph_next = 0;
+  double g_next = 0;
+  auto prefetch = [&](int t) {
+    const size_t row = (size_t)(bs.row0 + t);
+    g_next = __ldg(p.gsum + row);
+    if (lane < maxp) {
+      const uint4* c4 = reinterpret_cast<const uint4*>(p.cand + row * maxp + lane);
+      const uint4 a = __ldg(c4), b = __ldg(c4 + 1);
+      pkd_next = a.x; amp_next = a.y; pl_next = a.z | ((unsigned long long)a.w << 32); ph_next = b.x | ((unsigned long long)b.y << 32);
+    }
+  };
+  // clear_fm @B35919 (the tracker's half of L())
+  auto clear_tracks = [&]() {
+    st.n_tr = 0; st.n_pts = 0; st.s_energy = 0.0; st.c_energy = 0.0;
+    for (int r = lane; r < st.n_slots; r += 32) S.t_id[r] = -1;
+    st.n_slots = 0;
+    __syncwarp();
+  };
+  auto finalize = [&](const int slot) {
+    const PipeFin f = Q.fins[slot];
+    st.no_fm_segs = f.no_fm_segs; st.current_frame = f.current_frame; st.c_started = f.c_started; st.y = f.y; st.v = f.v;
+    finalize_copy(p, S, st, bs, f.n_arg, lane);
+    S.t_wm[lane] = 0u; S.t_wm[lane + 32] = 0u;   // the finalisation used the track slots as scratch
+    clear_tracks();
+  };
+  if (bs.F > 0) prefetch(0);
+  for (int t = 0;; t++) {
+    while (Q.prod <= t) __nanosleep(40);
+    __threadfence_block();
+    const PipeRec r = Q.ring[t % kRing];
+    if (r.flags & kRecStop) { st.overflow = (int)((r.flags >> 8) & 0xffu); break; }
+    if (r.flags & kRecEnd) { finalize(r.fin); break; }
+    const uint32_t pkd0 = pkd_next, amp0 = amp_next;
+    const unsigned long long pl0 = pl_next, ph0 = ph_next;
+    const double g = g_next;
+    if (t + 1 < bs.F) prefetch(t + 1);
+    if (t + 4 < bs.F && lane < maxp)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.cand + (size_t)(bs.row0 + t + 4) * maxp + lane));
+    if (r.flags & kRecClearPre) clear_tracks();
+    if (r.flags & kRecVoiced) {
+      const int nc = r.nc;
+      const double v = r.v_filter;
+      PeakRegs pr;
+      pr.m = 0u; pr.pkd = pkd0; pr.amp = amp0; pr.pl = pl0; pr.ph = ph0;
+      if (nc <= 32) {
+        pr.m = __ballot_sync(FULL, lane < nc && (double)amp0 > v);
+      } else {   // more than 32 candidates (noise frames): the <= 32 accepted ones are compacted through shared memory
+        int n = 0;
+        for (int c0 = 0; c0 < nc; c0 += 32) {
+          uint4 a = make_uint4(pkd0, amp0, (uint32_t)pl0, (uint32_t)(pl0 >> 32)), b = make_uint4((uint32_t)ph0, (uint32_t)(ph0 >> 32), 0u, 0u);
+          if (c0 > 0) {
+            a = make_uint4(0u, 0u, 0u, 0u); b = a;
+            if (c0 + lane < nc) {
+              const uint4* c4 = reinterpret_cast<const uint4*>(p.cand + (size_t)(bs.row0 + t) * maxp + c0 + lane);
+              a = __ldg(c4); b = __ldg(c4 + 1);
+            }
+          }
+          const bool acc = c0 + lane < nc && (double)a.y > v;
+          const unsigned mm = __ballot_sync(FULL, acc);
+          if (acc) {
+            const int pos = n + __popc(mm & lt);
+            if (pos < 32) {
+              S.pa[pos] = make_uint2(a.x, a.y);
+              S.plh[pos] = make_ulonglong2(a.z | ((unsigned long long)a.w << 32), b.x | ((unsigned long long)b.y << 32));
+            }
+          }
+          n += __popc(mm);
+        }
+        __syncwarp();
+        pr.m = n >= 32 ? FULL : ((1u << n) - 1u);    // n <= 32: the producer stopped the scan otherwise
+        if (lane < n) {
+          const uint2 a = S.pa[lane];
+          const ulonglong2 e2 = S.plh[lane];
+          pr.pkd = a.x; pr.amp = a.y; pr.pl = e2.x; pr.ph = e2.y;
+        }
+        __syncwarp();
+      }
+      accumulate_fm2(p, S, st, bs, pr.m, pr.pkd, pr.amp, pr.pl, pr.ph, r.label, g, r.vmin, lane);
+      if (st.overflow) { Q.abort_ = 1; break; }
+    }
+    if (r.flags & kRecFin) finalize(r.fin);
+    if (r.flags & kRecClearPost) clear_tracks();
+    __syncwarp();
+    if (lane == 0) Q.cons = t + 1;     // (after the finalisation: its PipeFin slot is free again)
+  }
+  if (lane == 0) {
+    p.n_segs[u] = st.n_segs;
+    p.n_stored[u] = st.n_stored;
+    p.n_rows[u] = st.n_rows;
+    p.n_syls[u] = st.n_syls;
+    p.overflow[u] = st.overflow;
+    if (st.overflow == 2 && p.redo_count) atomicAdd(p.redo_count, 1);
+  }
+}
+
+__global__ void __launch_bounds__(2 * kPipeUtts * 32, 2) fa_segment3_kernel(const FaSegmentParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int k = wib & (kPipeUtts - 1);
+  const bool consumer = wib >= kPipeUtts;
+  const int ui = blockIdx.x * kPipeUtts + k;
+  const size_t per_utt = (size_t)p.smem_per_warp + sizeof(PipeShared);
+  WarpShared& S = *reinterpret_cast<WarpShared*>(smem_raw + (size_t)k * per_utt);
+  PipeShared& Q = *reinterpret_cast<PipeShared*>(smem_raw + (size_t)k * per_utt + p.smem_per_warp);
+  if (!consumer && lane == 0) { Q.prod = 0; Q.cons = 0; Q.abort_ = 0; }
+  __syncthreads();
+  if (consumer) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kPipeRegsConsumer));
+    if (ui < p.utt_count) pipe_consumer(p, S, Q, p.utt_begin + ui, lane);
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kPipeRegsProducer));
+    if (ui < p.utt_count) pipe_producer(p, Q, p.utt_begin + ui, lane);
+  }
+}
+
+
+// =====================================================================================================================
 // Mode 1: the scan split in three.  Only the CONTROL state is sequential in time -- the start / pause tests, c_started,
 // no_fm_segs, c_ci and the adaptive gate (y, v, ...) depend on the frame's (n, d, h, p, g) and on each other, never on
 // the tracks: accumulate_fm has no way back into D() (its only outputs are the track table and the c/s energies read at
@@ -1876,7 +2189,17 @@ cudaError_t fa_launch_segment(const FaSegmentParams& p_in, cudaStream_t s, int* 
     return cudaGetLastError();
   };
   cudaError_t e = cudaSuccess;
-  if (p.impl == 2) {
+  if (p.impl == 3) {   // the two-warp pipeline; whatever it hands back (overflow == 2) is redone by the general kernel below
+    p.redo_only = 0;
+    const int pbytes = kPipeUtts * (p.smem_per_warp + (int)sizeof(PipeShared));
+    e = cudaFuncSetAttribute(fa_segment3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pbytes);
+    if (e != cudaSuccess) return e;
+    fa_segment3_kernel<<<(p.utt_count + kPipeUtts - 1) / kPipeUtts, 2 * kPipeUtts * 32, pbytes, s>>>(p);
+    e = cudaGetLastError();
+    if (launches) (*launches)++;
+    if (e != cudaSuccess) return e;
+    p.redo_only = 1;
+  } else if (p.impl == 2) {
     p.redo_only = 0;
     e = regs <= 64 ? launch(fa_segment2_kernel<1024>) : regs <= 96 ? launch(fa_segment2_kernel<640>) : launch(fa_segment2_kernel<128>);
     if (launches) (*launches)++;
