@@ -2031,76 +2031,110 @@ __global__ void __launch_bounds__(kBound, 1) fa_segtrack_kernel(const FaSegmentP
     bs.u = u;
     bs.spill = worker;
     ScanState st;
-    st.current_frame = E.current_frame; st.no_fm_segs = E.no_fm_segs; st.c_ci = E.c_ci; st.c_started = 2;
-    st.w = 0; st.k = 0; st.y = E.y; st.v = E.v; st.x = E.y; st.v0 = E.v; st.T = 0; st.s_energy = 0; st.c_energy = 0;
-    st.n_tr = 0; st.n_pts = 0; st.n_slots = 0;
-    st.n_segs = wk.y;         // -> segs[sb + seg_ci index]
-    st.n_stored = 0;          // provisional: K3c numbers the stores
-    st.n_rows = E.first;      // provisional row offset: rows land inside the epoch's frame range (len <= its frames)
-    st.n_syls = E.first;      // provisional syllable offset, same argument
-    st.overflow = 0;
-    for (int r = lane; r < ACAP; r += 32) S.t_id[r] = -1;
-    if (lane <= FA_MAX_BANDS / 32) S.pmask[lane] = 0u;
-    __syncwarp();
-    // software prefetch of the next frame's control record, thresholds, count, g and first 32 candidates
-    unsigned ctl_n = 0u;
-    double v_n = 0, vmin_n = 0, g_n = 0;
-    int nc_n = 0;
-    uint4 a_n = make_uint4(0u, 0u, 0u, 0u), b_n = a_n;
-    auto prefetch = [&](const int t) {
-      const size_t row = (size_t)(bs.row0 + t);
-      ctl_n = __ldg(p.fr_ctl + row);
-      v_n = t > 0 ? __ldg(p.fr_v + row - 1) : p.v0;   // the gate at the start of the frame
-      vmin_n = __ldg(p.fr_v + row);                   // ... and after C(h): what accumulate_fm receives
-      nc_n = __ldg(p.ncand + row);
-      g_n = __ldg(p.gsum + row);
-      if (lane < maxp) {
-        const uint4* c4 = reinterpret_cast<const uint4*>(p.cand + row * maxp + lane);
-        a_n = __ldg(c4); b_n = __ldg(c4 + 1);
-      }
-    };
-    if (E.first <= E.last) prefetch(E.first);
-    for (int t = E.first; t <= E.last && !st.overflow; t++) {
-      const size_t row = (size_t)(bs.row0 + t);
-      const unsigned ctl = ctl_n;
-      const double v = v_n, vmin = vmin_n, g = g_n;
-      const int nc = min(nc_n, maxp);
-      const uint4 a0 = a_n, b0 = b_n;
-      if (t < E.last) prefetch(t + 1);
-      if (!(ctl >> 31)) continue;
-      int n = 0;
-      for (int c0 = 0; c0 < nc; c0 += 32) {
-        uint4 a = a0, b = b0;
-        if (c0 > 0) {
-          a = make_uint4(0u, 0u, 0u, 0u); b = a;
-          if (c0 + lane < nc) {
-            const uint4* c4 = reinterpret_cast<const uint4*>(p.cand + row * maxp + c0 + lane);
-            a = __ldg(c4); b = __ldg(c4 + 1);
-          }
-        }
-        const uint32_t pkd = a.x, amp = a.y;
-        const bool acc = c0 + lane < nc && (double)amp > v;
-        const unsigned m = __ballot_sync(FULL, acc);
-        if (m == 0u) continue;
-        if (acc) {
-          const int pk = (pkd >> 16) & 0xff;
-          const int pos = n + __popc(m & lt);
-          if (pos < PCAP) {
-            S.pa[pos] = make_uint2(pkd, amp);
-            S.plh[pos] = make_ulonglong2(a.z | ((unsigned long long)a.w << 32), b.x | ((unsigned long long)b.y << 32));
-            S.best[pos] = 0ull; S.owner[pos] = BIG;
-            S.pidx[pk] = (unsigned char)pos;
-            atomicOr(&S.pmask[pk >> 5], 1u << (pk & 31));
-          }
-        }
-        n += __popc(m);
-      }
-      if (n > PCAP) { st.overflow = 1; break; }
-      __syncwarp();
-      accumulate_fm(p, S, st, bs, n, (int)(ctl & kCtlLabel), g, vmin, lane);
-      __syncwarp();
+    // pass 0: tracking with peak-lane ownership (accumulate_fm2: <= 64 live tracks, <= 32 accepted peaks per frame); an epoch
+    // that needs more (overflow == 2) is replayed by pass 1, the general accumulate_fm -- same rule as the serial kernels
+    for (int pass = p.impl == 1 ? 1 : 0; pass < 2; pass++) {
+      const bool fast = pass == 0;
+      st.current_frame = E.current_frame; st.no_fm_segs = E.no_fm_segs; st.c_ci = E.c_ci; st.c_started = 2;
+      st.w = 0; st.k = 0; st.y = E.y; st.v = E.v; st.x = E.y; st.v0 = E.v; st.T = 0; st.s_energy = 0; st.c_energy = 0;
+      st.n_tr = 0; st.n_pts = 0; st.n_slots = 0;
+      st.n_segs = wk.y;         // -> segs[sb + seg_ci index]
+      st.n_stored = 0;          // provisional: K3c numbers the stores
+      st.n_rows = E.first;      // provisional row offset: rows land inside the epoch's frame range (len <= its frames)
+      st.n_syls = E.first;      // provisional syllable offset, same argument
+      st.overflow = 0;
+      for (int r = lane; r < ACAP; r += 32) { S.t_id[r] = -1; S.t_wm[r] = 0u; }
       if (lane <= FA_MAX_BANDS / 32) S.pmask[lane] = 0u;
+      for (int r = lane; r < 2 * FA_MAX_BANDS; r += 32) (&S.wmask[0][0])[r] = 0u;
       __syncwarp();
+      // software prefetch of the next frame's control record, thresholds, count, g and first 32 candidates
+      unsigned ctl_n = 0u;
+      double v_n = 0, vmin_n = 0, g_n = 0;
+      int nc_n = 0;
+      uint4 a_n = make_uint4(0u, 0u, 0u, 0u), b_n = a_n;
+      auto prefetch = [&](const int t) {
+        const size_t row = (size_t)(bs.row0 + t);
+        ctl_n = __ldg(p.fr_ctl + row);
+        v_n = t > 0 ? __ldg(p.fr_v + row - 1) : p.v0;   // the gate at the start of the frame
+        vmin_n = __ldg(p.fr_v + row);                   // ... and after C(h): what accumulate_fm receives
+        nc_n = __ldg(p.ncand + row);
+        g_n = __ldg(p.gsum + row);
+        if (lane < maxp) {
+          const uint4* c4 = reinterpret_cast<const uint4*>(p.cand + row * maxp + lane);
+          a_n = __ldg(c4); b_n = __ldg(c4 + 1);
+        }
+      };
+      if (E.first <= E.last) prefetch(E.first);
+      for (int t = E.first; t <= E.last && !st.overflow; t++) {
+        const size_t row = (size_t)(bs.row0 + t);
+        const unsigned ctl = ctl_n;
+        const double v = v_n, vmin = vmin_n, g = g_n;
+        const int nc = min(nc_n, maxp);
+        const uint4 a0 = a_n, b0 = b_n;
+        if (t < E.last) prefetch(t + 1);
+        if (!(ctl >> 31)) continue;
+        int n = 0;
+        PeakRegs pr;
+        pr.m = 0u; pr.pkd = a0.x; pr.amp = a0.y; pr.pl = a0.z | ((unsigned long long)a0.w << 32); pr.ph = b0.x | ((unsigned long long)b0.y << 32);
+        if (fast && nc <= 32) {
+          pr.m = __ballot_sync(FULL, lane < nc && (double)a0.y > v);
+          n = __popc(pr.m);
+        } else {
+          for (int c0 = 0; c0 < nc; c0 += 32) {
+            uint4 a = a0, b = b0;
+            if (c0 > 0) {
+              a = make_uint4(0u, 0u, 0u, 0u); b = a;
+              if (c0 + lane < nc) {
+                const uint4* c4 = reinterpret_cast<const uint4*>(p.cand + row * maxp + c0 + lane);
+                a = __ldg(c4); b = __ldg(c4 + 1);
+              }
+            }
+            const uint32_t pkd = a.x, amp = a.y;
+            const bool acc = c0 + lane < nc && (double)amp > v;
+            const unsigned m = __ballot_sync(FULL, acc);
+            if (m == 0u) continue;
+            if (acc) {
+              const int pk = (pkd >> 16) & 0xff;
+              const int pos = n + __popc(m & lt);
+              if (pos < (fast ? 32 : PCAP)) {
+                S.pa[pos] = make_uint2(pkd, amp);
+                S.plh[pos] = make_ulonglong2(a.z | ((unsigned long long)a.w << 32), b.x | ((unsigned long long)b.y << 32));
+                if (!fast) {
+                  S.best[pos] = 0ull; S.owner[pos] = BIG;
+                  S.pidx[pk] = (unsigned char)pos;
+                  atomicOr(&S.pmask[pk >> 5], 1u << (pk & 31));
+                }
+              }
+            }
+            n += __popc(m);
+          }
+          if (fast) {
+            if (n > 32) { st.overflow = 2; break; }
+            __syncwarp();
+            pr.m = n >= 32 ? FULL : ((1u << n) - 1u);
+            if (lane < n) {
+              const uint2 a = S.pa[lane];
+              const ulonglong2 e2 = S.plh[lane];
+              pr.pkd = a.x; pr.amp = a.y; pr.pl = e2.x; pr.ph = e2.y;
+            }
+          }
+        }
+        if (n > PCAP) { st.overflow = 1; break; }
+        __syncwarp();
+        if (fast) {
+          accumulate_fm2(p, S, st, bs, pr.m, pr.pkd, pr.amp, pr.pl, pr.ph, (int)(ctl & kCtlLabel), g, vmin, lane);
+        } else {
+          accumulate_fm(p, S, st, bs, n, (int)(ctl & kCtlLabel), g, vmin, lane);
+          __syncwarp();
+          if (lane <= FA_MAX_BANDS / 32) S.pmask[lane] = 0u;
+        }
+        __syncwarp();
+      }
+      if (fast && st.overflow == 2) {   // hand the epoch to the general path
+        if (lane == 0 && p.redo_count) atomicAdd(p.redo_count, 1);
+        continue;
+      }
+      break;
     }
     if (!st.overflow) {
       const int len = E.n_arg - st.no_fm_segs;
