@@ -27,7 +27,13 @@ struct SlotAcc {
 // Per row: the expensive part (20*log10(E), fdlibm, ~150 dependent FP64 ops) is done lane-per-frame into
 // shared memory; the order-sensitive part (sums in array order, run / jump / accent automaton) is done by three
 // lanes, one per formant slot, over the precomputed values.  Two passes: sums, then squared deviations.
+// The walkers read the chunk's rows from SHARED memory (lane-parallel, coalesced staging of the 9-float rows next to the dB
+// values) instead of loading F[row] from global memory inside the loop: 0.109 -> 0.100 ms on C2.  Measured and rejected in round
+// 2: ten rows per warp through a flattened work list (lanes 3g .. 3g + 2 walk row g: 0.37 ms -- the ten rows' log10 phases
+// queue up in one warp) and one row per CTA with each walk in its own warp (0.116 ms): the walk is a chain of dependent FP64
+// compares and branches, ~500 cycles per frame and pass, whatever the mapping.
 __device__ void row_features(const float* __restrict__ F, const int len, const double ymax, double (*sdb)[kChunk],
+                             float* __restrict__ sF /* [(kChunk + 1) * 9]: row -1 of the chunk first */,
                              const int lane, double* __restrict__ out /* 48 = 3 x 16 */) {
   SlotAcc A;
   A.cnt = A.runs = A.up = A.down = A.sum_c = A.sum_w = A.sum_T = A.sum_k = A.sum_knz = A.sum_M = A.sum_Anz = A.L = 0;
@@ -42,20 +48,23 @@ __device__ void row_features(const float* __restrict__ F, const int len, const d
     for (int c0 = 0; c0 < len; c0 += kChunk) {
       const int cn = min(kChunk, len - c0);
       __syncwarp();
+      // rows c0 - 1 .. c0 + cn - 1 of the segment (the row in front of the chunk feeds the first jump test)
+      for (int i = lane + (c0 > 0 ? 0 : 9); i < 9 * (cn + 1); i += 32) sF[i] = F[(size_t)c0 * 9 - 9 + i];
+      __syncwarp();
       for (int i = lane; i < 3 * cn; i += 32) {
         const int sl = i / cn, t = i - sl * cn;
-        const double a = (double)F[(size_t)(c0 + t) * 9 + 3 * sl + 1];
+        const double a = (double)sF[(size_t)(t + 1) * 9 + 3 * sl + 1];
         sdb[sl][t] = a > 0 ? 20.0 * fa_js_log10(a) : 0.0;
       }
       __syncwarp();
       if (lane < 3) {
         for (int t = 0; t < cn; t++) {
-          const size_t row = (size_t)(c0 + t) * 9 + 3 * n;
-          const double r = (double)F[row], a = (double)F[row + 1];
+          const int row = (t + 1) * 9 + 3 * n;
+          const double r = (double)sF[row], a = (double)sF[row + 1];
           if (r > 0 && a > 0) {
             const double d = sdb[n][t];
             if (pass == 0) {
-              const double f = (double)F[row + 2];
+              const double f = (double)sF[row + 2];
               A.sum_c += r * d; A.sum_w += r; A.sum_M += f * d; A.sum_T += a; A.sum_k += d;
               if (d > 0) { A.sum_knz += d; A.n_knz++; }
               A.m++;
@@ -66,7 +75,7 @@ __device__ void row_features(const float* __restrict__ F, const int len, const d
             }
             if (prev) {
               if (pass == 0) {
-                const double j = r - (double)F[row - 9];
+                const double j = r - (double)sF[row - 9];
                 if (j > 1) A.up += j; else if (j < -1) A.down += -1 * j;
               }
               if (a > L) { L = a; S = 1; }
@@ -118,6 +127,7 @@ __device__ void row_features(const float* __restrict__ F, const int len, const d
 
 __global__ void __launch_bounds__(kFeatThreads) fa_features_kernel(const FaFeatureParams p) {
   __shared__ double s_db[kFeatThreads / 32][3][kChunk];
+  __shared__ float s_F[kFeatThreads / 32][(kChunk + 1) * 9];
   const int u = p.utt_begin + blockIdx.x;
   const long long row0 = p.frame_off[u], sb = row0 + u;
   const int nseg = p.n_segs[u];
@@ -160,7 +170,7 @@ __global__ void __launch_bounds__(kFeatThreads) fa_features_kernel(const FaFeatu
       out[3] = fa_js_log10(sg->ymax);
       out[4] = sg->vmin;
     }
-    row_features(F, len, sg->ymax, s_db[warp], lane, out + 5);
+    row_features(F, len, sg->ymax, s_db[warp], s_F[warp], lane, out + 5);
   }
 }
 
