@@ -261,6 +261,13 @@ FA_API int fa_copy_counts_table(fa_handle* h, fa_counts* dst, size_t cap);
 FA_API int fa_copy_spectrum(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows);      /* rows of fft_size/2 dB values (FA_SPECTRUM_F32) */
 FA_API int fa_copy_spectrum_raw(fa_handle* h, int64_t utt_id, void* dst, size_t cap_rows);   /* rows of fft_size/2 elements, any spectrum_format */
 FA_API int fa_copy_frames(fa_handle* h, int64_t utt_id, uint32_t* dst, size_t cap_rows);     /* rows of `bands` uint32 */
+/* Live streams (the reference fires its callback after every pause WHILE audio is still arriving, P() @B28869): the segmentor is
+ * causal, so the segments that a PREFIX of the stream finalises on its own -- without segment_truncate @B30800, which only runs
+ * when the source stops -- are exactly the ones the reference has called back by then.  fa_set_truncate(h, 0) switches the
+ * final segment_truncate off for the following runs (default 1 = on): submit the stream so far, run, fire the callbacks of the
+ * stores that are new; when the stream ends, run once more with truncation on.  (The whole prefix is re-analysed at every call:
+ * at > 300 000 x real time that costs 0.2 ms per minute of audio.)  Host shim: webspeechanalyzer_b200/api.py LiveSession. */
+FA_API int fa_set_truncate(fa_handle* h, int on);
 FA_API int fa_copy_segments(fa_handle* h, int64_t utt_id, fa_segment* dst, size_t cap_rows);
 FA_API int fa_copy_formants(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows);      /* rows of 9 float32 */
 FA_API int fa_copy_energy(fa_handle* h, int64_t utt_id, float* dst, size_t cap_rows);        /* rows of 3 float32 */

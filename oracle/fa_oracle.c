@@ -929,7 +929,7 @@ FAO_API fao_result* fao_analyze_frames(const fa_config* c, const uint32_t* frame
   if (st.auto_gate) { st.y = 50; st.v = 2; }
   else { st.y = fa_js_pow(10, c->voiced_max_db / 20); st.v = fa_js_pow(10, c->voiced_min_db / 20); }
   st.x = st.y; st.v0 = st.v;
-  if (want_trace && F > 0) {
+  if ((want_trace & 1) && F > 0) {
     R->tr_n = (int*)calloc(F, sizeof(int)); R->tr_p = (int*)calloc(F, sizeof(int));
     R->tr_cstart = (int*)calloc(F, sizeof(int)); R->tr_cci = (int*)calloc(F, sizeof(int));
     R->tr_nofm = (int*)calloc(F, sizeof(int));
@@ -946,10 +946,13 @@ FAO_API fao_result* fao_analyze_frames(const fa_config* c, const uint32_t* frame
         if (fin >= 0) fire_callbacks(R, &processed);
       }
     }
-    /* segment_truncate @B30800 */
-    int fin = finalize_segment(&st, R, st.c_ci);
-    seg_reset(&st, 1);
-    if (fin >= 0) fire_callbacks(R, &processed);
+    /* segment_truncate @B30800 (want_trace bit 1: the frames are the prefix of a stream that is still running -- the source has
+     * not stopped, nothing is truncated) */
+    if (!(want_trace & 2)) {
+      int fin = finalize_segment(&st, R, st.c_ci);
+      seg_reset(&st, 1);
+      if (fin >= 0) fire_callbacks(R, &processed);
+    }
   }
   clear_fm(&st);
   free(st.tr);

@@ -134,11 +134,12 @@ TRACK_POINT_DTYPE = np.dtype([("frame", "<i4"), ("lo", "<i2"), ("hi", "<i2"), ("
 assert SEG_DTYPE.itemsize == C.sizeof(FaSegment) and SYL_DTYPE.itemsize == C.sizeof(FaSyllable) and TRACK_POINT_DTYPE.itemsize == 24
 
 
-def analyze_frames(cfg: FaConfig, frames: np.ndarray, trace: bool = False) -> Analysis:
+def analyze_frames(cfg: FaConfig, frames: np.ndarray, trace: bool = False, truncate: bool = True) -> Analysis:
+    """truncate=False: the frames are the prefix of a stream that is still running (no segment_truncate @B30800 at the end)."""
     frames = np.ascontiguousarray(frames, np.uint32)
     F = frames.shape[0]
     assert F == 0 or frames.shape[1] == cfg.bands
-    R = _lib.fao_analyze_frames(C.byref(cfg), _p(frames, _u32p), F, 1 if trace else 0)
+    R = _lib.fao_analyze_frames(C.byref(cfg), _p(frames, _u32p), F, (1 if trace else 0) | (0 if truncate else 2))
     try:
         cnt = (C.c_int * 8)()
         _lib.fao_counts(R, cnt)

@@ -262,3 +262,30 @@ def test_node_shim_configure_executed_by_minijs_matches_the_reference_module():
                 assert mine[f] == before[f]
                 continue
             assert mine[f] == ref[f], (f, mine[f], ref[f])
+
+
+# ---------------------------------------------------------------------------- incremental callbacks (live streams)
+@pytest.mark.parametrize("level", [3, 5, 11, 13])
+def test_prefix_without_truncate_gives_the_callbacks_fired_so_far(level):
+    """The premise of api.LiveSession / fa_set_truncate: the segmentor is causal, so what a PREFIX of a stream finalises without
+    segment_truncate is a prefix of what the whole stream calls back -- same arguments, same order (oracle on both sides)."""
+    sr, step = 16000, 25.0
+    pcm = np.concatenate([synth_speech(4 * sr, sr, 7, k) for k in range(4)])
+    cfg = FaConfig.default(output_level=level, window_step_ms=step)
+    frames = oracle.frontend(cfg, pcm, sr, spectrum=False)["frames"]
+
+    def calls(fr, truncate):
+        an = oracle.analyze_frames(cfg, fr, truncate=truncate)
+        res = UtteranceResult({}, an.segments, an.formants, an.energy, an.syllables, an.features, an.utterance, an.track_points)
+        return [_norm(c) for c in api.segment_callbacks(level, step, [1.0], res)]
+
+    full = calls(frames, True)
+    assert len(full) >= 3
+    seen = 0
+    for n in range(0, frames.shape[0] + 1, 13):
+        part = calls(frames[:n], False)
+        assert json.dumps(part) == json.dumps(full[: len(part)])      # a prefix of the final list, bit for bit
+        assert len(part) >= seen                                       # and it only grows
+        seen = len(part)
+    assert seen >= len(full) - 1                                       # only the truncated tail waits for the source to stop
+    assert 0 < len(calls(frames[: frames.shape[0] // 2], False)) < len(full)

@@ -23,7 +23,7 @@ EXPORTS = [
     "fa_set_stream", "fa_set_d2h_stream", "fa_set_pipeline", "fa_set_spectrum_sink", "fa_set_spectrum_sink_raw", "fa_reset", "fa_submit_pcm", "fa_submit_pcm_i16", "fa_submit_pcm_batch", "fa_submit_pcm_i16_batch", "fa_submit_frames", "fa_run", "fa_sync", "fa_upload",
     "fa_run_resident", "fa_download", "fa_stage_times", "fa_launch_count", "fa_stream_fixups", "fa_num_utterances", "fa_result_counts",
     "fa_total_counts", "fa_copy_counts_table", "fa_pcie_probe", "fa_copy_spectrum", "fa_copy_spectrum_raw", "fa_copy_frames", "fa_copy_segments", "fa_copy_formants", "fa_copy_energy",
-    "fa_copy_syllables", "fa_copy_features", "fa_copy_utterance_features", "fa_copy_curve_features", "fa_copy_track_points", "fa_mlp_create", "fa_mlp_destroy", "fa_mlp_last_error",
+    "fa_copy_syllables", "fa_copy_features", "fa_copy_utterance_features", "fa_copy_curve_features", "fa_copy_track_points", "fa_set_truncate", "fa_mlp_create", "fa_mlp_destroy", "fa_mlp_last_error",
     "fa_mlp_classify", "fa_mlp_classify_features", "fa_copy_peak_candidates", "fa_copy_gsum", "fa_hop_samples", "fa_frames_for",
     "fa_spec_bands", "fa_host_alloc", "fa_host_free",
 ]
@@ -68,6 +68,7 @@ def lib() -> C.CDLL:
     L.fa_submit_pcm_i16_batch.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.fa_submit_frames.argtypes = [H, C.c_int64, C.c_void_p, C.c_size_t, C.c_int]
     L.fa_set_pipeline.argtypes = [H, C.c_int]
+    L.fa_set_truncate.argtypes = [H, C.c_int]
     L.fa_set_spectrum_sink.argtypes = [H, C.c_void_p, C.c_size_t]
     L.fa_set_spectrum_sink_raw.argtypes = [H, C.c_void_p, C.c_size_t]
     for n in ("fa_run", "fa_sync", "fa_upload", "fa_run_resident", "fa_download", "fa_launch_count", "fa_num_utterances"):

@@ -168,6 +168,7 @@ struct fa_handle {
   DevBuf g_segs, g_syls, g_formants, g_energy, g_features;
   DevBuf d_curve_work, d_curve_status, d_curve_list, d_curve_count;   // level 12 (K8)
   DevBuf d_pt_amp;                       // level 3: amplitudes of the pool points
+  int no_truncate = 0;                   // fa_set_truncate(h, 0): prefixes of running streams
   size_t row_bytes() const { return cfg.output_level == FA_LEVEL_SEGMENTS ? sizeof(fa_track_point) : 9 * sizeof(float); }
   int n_weights = 0;
   long long track_total = 0, urow_total = 0;
@@ -994,6 +995,7 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
     g.row_count = h->d_rows.as<int>(); g.row_off = g.row_count + R; g.row_list = h->d_rowlist.as<int>();
     g.cs_spill = h->d_spill.as<unsigned long long>();
     g.finalize_in_smem = h->k3_finalize_smem;
+    g.no_truncate = h->no_truncate;
     g.impl = h->k3_impl; g.warps_per_cta = h->k3_warps; g.reg_cap = h->k3_regs; g.redo_count = h->d_fix.as<int>() + 2;
     g.mode = h->k3_mode;
     if (g.mode == 1) {
@@ -1414,6 +1416,12 @@ static int copy_dense(fa_handle* h, int64_t utt_id, int kind, int table, size_t 
   if (nr && !dst) return FA_ERR_INVALID_ARG;
   if (nr) memcpy(dst, (const char*)host + (size_t)r0 * row_bytes, (size_t)nr * row_bytes);
   return (int)nr;
+}
+
+int fa_set_truncate(fa_handle* h, int on) {
+  if (!h) return FA_ERR_INVALID_ARG;
+  h->no_truncate = on ? 0 : 1;
+  return FA_OK;
 }
 
 int fa_copy_segments(fa_handle* h, int64_t utt_id, fa_segment* dst, size_t cap) {

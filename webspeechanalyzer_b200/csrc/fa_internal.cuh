@@ -125,6 +125,7 @@ struct FaSegmentParams {
   int* row_list;                      // [F_total * maxp]
   unsigned long long* cs_spill;       // [n_utt][6][128] candidate scores beyond the three kept in shared memory
   int finalize_in_smem;               // 1: segments that fit are finalised in shared memory (0 forces the HBM path: tests)
+  int no_truncate;                    // 1: the utterances are prefixes of running streams: no segment_truncate @B30800 at their end
   // impl 2 (default): tracking with peak-lane ownership (accumulate_fm2: <= 64 live tracks, <= 32 accepted peaks per frame);
   // an utterance / epoch that needs more is flagged (overflow == 2) and redone by the general kernel (impl 1) in a second,
   // normally empty launch with redo_only = 1

@@ -995,8 +995,8 @@ __global__ void __launch_bounds__(kBound, 1) fa_segment_kernel(const FaSegmentPa
     if (n > 0 && lane <= FA_MAX_BANDS / 32) S.pmask[lane] = 0u;
     __syncwarp();
   }
-  // segment_truncate @B30800
-  if (!st.overflow) {
+  // segment_truncate @B30800 (not for the prefix of a stream that is still running: fa_set_truncate)
+  if (!st.overflow && !p.no_truncate) {
     finalize_copy(p, S, st, bs, st.c_ci, lane);
     seg_reset(st, S, 1, lane);
   }
@@ -1362,8 +1362,8 @@ __global__ void __launch_bounds__(kBound, 1) fa_segment2_kernel(const FaSegmentP
       seg_reset(st, S, -1, lane);                  // the promise's micro-task runs before the next frame
     }
   }
-  // segment_truncate @B30800
-  if (!st.overflow) {
+  // segment_truncate @B30800 (not for the prefix of a stream that is still running: fa_set_truncate)
+  if (!st.overflow && !p.no_truncate) {
     finalize_copy(p, S, st, bs, st.c_ci, lane);
     seg_reset(st, S, 1, lane);
   }
@@ -1542,6 +1542,7 @@ __device__ __forceinline__ void pipe_producer(const FaSegmentParams& p, PipeShar
   PipeRec e;
   e.label = 0; e.nc = 0; e.fin = 0; e.v_filter = 0; e.vmin = 0;
   if (stop) e.flags = kRecStop | ((unsigned)stop << 8);
+  else if (p.no_truncate) e.flags = kRecStop;              // prefix of a running stream: no segment_truncate, overflow code 0
   else { e.flags = kRecEnd; e.fin = put_fin(st.c_ci); }   // segment_truncate @B30800
   publish(t, e);
 }
@@ -1883,7 +1884,7 @@ __global__ void __launch_bounds__(kCtlWarps * 32) fa_segctl_kernel(const FaSegme
   int n_events = 0;
   segctl_range(p, u, row0, 0, F, st, epoch_first, fired, n_events, true, false, sb, true, maxp, lane);
   st.current_frame = F;
-  if (!st.overflow) ctl_attempt(p, st, epoch_first, st.c_ci, F - 1, maxp, sb, u, true, true, lane);   // segment_truncate @B30800
+  if (!st.overflow && !p.no_truncate) ctl_attempt(p, st, epoch_first, st.c_ci, F - 1, maxp, sb, u, true, true, lane);   // segment_truncate @B30800
   if (lane == 0) {
     p.n_segs[u] = st.n_segs;
     p.overflow[u] = st.overflow;
@@ -1996,7 +1997,7 @@ __global__ void __launch_bounds__(kCtlWarps * 32) fa_segctl_verify_kernel(const 
   st.n_segs = n_segs;
   st.current_frame = F;
   st.overflow = overflow;
-  if (!overflow) ctl_attempt(p, st, epoch_first, st.c_ci, F - 1, maxp, sb, u, true, true, lane);   // segment_truncate @B30800
+  if (!overflow && !p.no_truncate) ctl_attempt(p, st, epoch_first, st.c_ci, F - 1, maxp, sb, u, true, true, lane);   // segment_truncate @B30800
   if (lane == 0) {
     p.n_segs[u] = st.n_segs;
     p.overflow[u] = overflow;

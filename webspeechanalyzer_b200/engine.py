@@ -150,6 +150,10 @@ class Engine:
         return self._check(self._lib.fa_submit_pcm_batch(self._h, first_utt_id, pcm.ctypes.data, offsets.ctypes.data,
                                                          offsets.size - 1, sample_rate))
 
+    def set_truncate(self, on: bool):
+        """False: the submitted utterances are prefixes of streams still running -- no segment_truncate at their end."""
+        self._check(self._lib.fa_set_truncate(self._h, 1 if on else 0))
+
     def set_pipeline(self, n_sub: int):
         self._check(self._lib.fa_set_pipeline(self._h, n_sub))
 

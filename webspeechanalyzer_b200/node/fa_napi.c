@@ -117,6 +117,19 @@ static napi_value DestroyEngine(napi_env env, napi_callback_info info) {
   return NULL;
 }
 
+/* setTruncate(handle, on): fa_set_truncate -- off while the analysed audio is the prefix of a stream that is still running */
+static napi_value SetTruncate(napi_env env, napi_callback_info info) {
+  size_t argc = 2;
+  napi_value argv[2];
+  void* bp = NULL;
+  bool on = true;
+  if (napi_get_cb_info(env, info, &argc, argv, NULL, NULL) != napi_ok || argc < 2) return NULL;
+  if (napi_get_value_external(env, argv[0], &bp) != napi_ok || !bp || !((engine_box*)bp)->h) return NULL;
+  if (napi_get_value_bool(env, argv[1], &on) != napi_ok) return NULL;
+  fa_set_truncate(((engine_box*)bp)->h, on ? 1 : 0);
+  return NULL;
+}
+
 typedef struct {
   napi_async_work work;
   napi_deferred deferred;
@@ -314,5 +327,6 @@ __attribute__((visibility("default"))) napi_value napi_register_module_v1(napi_e
   if (napi_create_function(env, "createEngine", NAPI_AUTO_LENGTH, CreateEngine, NULL, &f) == napi_ok) napi_set_named_property(env, exports, "createEngine", f);
   if (napi_create_function(env, "destroyEngine", NAPI_AUTO_LENGTH, DestroyEngine, NULL, &f) == napi_ok) napi_set_named_property(env, exports, "destroyEngine", f);
   if (napi_create_function(env, "analyze", NAPI_AUTO_LENGTH, Analyze, NULL, &f) == napi_ok) napi_set_named_property(env, exports, "analyze", f);
+  if (napi_create_function(env, "setTruncate", NAPI_AUTO_LENGTH, SetTruncate, NULL, &f) == napi_ok) napi_set_named_property(env, exports, "setTruncate", f);
   return exports;
 }

@@ -214,4 +214,36 @@ function set_predicted_label_for_segment(seg_index, label_index, predicted_label
   f[label_index] = predicted_label;
 }
 
-module.exports = { configure, LaunchAudioNodes, StopAudioNodes, set_predicted_label_for_segment };
+// Incremental callbacks for audio that is still arriving (the reference's microphone / <audio> sources): the segmentor is
+// causal, so what a PREFIX of the stream finalises without segment_truncate @B30800 is what the reference has called back by
+// then.  push() appends a chunk, re-analyses the stream so far with truncation off (> 300 000 x real time) and fires the new
+// callbacks; stop() runs once more with truncation on.  Python twin (tested on the GPU): api.LiveSession.
+function createLiveSession(sampleRate, callback, file_labels = []) {
+  if (a.output_level <= 2) throw new Error('LiveSession delivers segment callbacks: output_level must be >= 3');
+  const eng = engine(), level = a.output_level;
+  let pcm = new Float32Array(0), fired = 0, chain = Promise.resolve(0);
+  const run = (truncate) => {
+    native.setTruncate(eng, truncate);
+    return native.analyze(eng, pcm, sampleRate, false, a.fftSize, level).then((res) => {
+      native.setTruncate(eng, true);
+      const calls = segmentCallbacks(level, res, file_labels), fresh = calls.slice(fired);
+      fired = calls.length;
+      if (callback) for (const c of fresh) callback(...c);
+      return fresh.length;
+    });
+  };
+  return {
+    push(chunk) {
+      chain = chain.then(() => {
+        const grown = new Float32Array(pcm.length + chunk.length);
+        grown.set(pcm); grown.set(chunk, pcm.length);
+        pcm = grown;
+        return run(false);
+      });
+      return chain;
+    },
+    stop() { chain = chain.then(() => run(true)); return chain; },
+  };
+}
+
+module.exports = { configure, LaunchAudioNodes, StopAudioNodes, set_predicted_label_for_segment, createLiveSession };
