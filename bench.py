@@ -363,7 +363,7 @@ def run_c3(args, world, rank, local):
     eng.download()
     eng.sync()
     tot = eng.counts()
-    cand_per_frame = mean_candidates_per_frame(eng, utt_ids)
+    cand_per_frame = mean_candidates_per_frame(eng, range(n_utt))     # engine-local ids (the global ones only key the gather)
     value = world * audio_per_step * args.steps / (ms_max / 1e3)
 
     # ---- end to end: host PCM -> device -> feature rows -> host -> gathered on rank 0 ----
