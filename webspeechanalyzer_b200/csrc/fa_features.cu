@@ -15,7 +15,8 @@ namespace {
 
 constexpr int kFeatThreads = 64;
 
-constexpr int kChunk = 256;   // frames per chunk: dB values of 3 slots x 256 frames in shared memory per warp
+constexpr int kChunk = 128;   // frames per chunk: dB values of 3 slots x 128 frames + the staged rows in shared memory per warp (7.7 KB:
+                              // with 256 the 31 KB per CTA capped the resident CTAs and a 36 k-row shard ran 15 % slower)
 
 struct SlotAcc {
   double cnt, runs, up, down, sum_c, sum_w, sum_T, sum_k, sum_knz, sum_M, sum_Anz, L;
@@ -28,7 +29,7 @@ struct SlotAcc {
 // shared memory; the order-sensitive part (sums in array order, run / jump / accent automaton) is done by three
 // lanes, one per formant slot, over the precomputed values.  Two passes: sums, then squared deviations.
 // The walkers read the chunk's rows from SHARED memory (lane-parallel, coalesced staging of the 9-float rows next to the dB
-// values) instead of loading F[row] from global memory inside the loop: 0.109 -> 0.100 ms on C2.  Measured and rejected in round
+// values) instead of loading F[row] from global memory inside the loop: 0.109 -> 0.098 ms on C2, 0.45 -> 0.41 ms on 24 k syllable rows.  Measured and rejected in round
 // 2: ten rows per warp through a flattened work list (lanes 3g .. 3g + 2 walk row g: 0.37 ms -- the ten rows' log10 phases
 // queue up in one warp) and one row per CTA with each walk in its own warp (0.116 ms): the walk is a chain of dependent FP64
 // compares and branches, ~500 cycles per frame and pass, whatever the mapping.
