@@ -160,6 +160,7 @@ struct fa_handle {
   int k3_impl = 2;       // FA_K3_IMPL: 2 = accumulate_fm2 kernel + redo launch (default), 1 = the general kernel alone
   int k3_warps = 0, k3_regs = 0, k3_finalize_smem = 1;   // FA_K3_WARPS, FA_K3_REGS, FA_K3_FINALIZE_HBM
   bool debug_sync = false;  // FA_DEBUG_SYNC
+  int k1a_variant = 0;      // FA_K1A_VARIANT (see fa_launch_spectrum)
   int k1_fused = 0;         // FA_K1_FUSED=1: the fused K1 kernel (fft_size 2048, utterance mode) instead of K1a + K1b.  Measured
                             // slower on B200 (C2: 0.99 vs 0.94 ms with dB rows, 0.93 vs 0.86 ms without; the stage is FP32-issue
                             // bound and the fused kernel's barriers idle issue slots), so it is a knob: it moves 1.19 instead of
@@ -345,6 +346,7 @@ int fa_create(const fa_config* cfg, int device, fa_handle** out) {
   if (getenv("FA_K3_FINALIZE_HBM")) h->k3_finalize_smem = 0;
   if (getenv("FA_DEBUG_SYNC")) h->debug_sync = true;
   if (const char* ev = getenv("FA_K1_FUSED")) h->k1_fused = atoi(ev) != 0;
+  if (const char* ev = getenv("FA_K1A_VARIANT")) h->k1a_variant = atoi(ev);
 
   // Streams are created on first use (ensure_sub_streams): the device has at most 32 hardware work queues
   // (CUDA_DEVICE_MAX_CONNECTIONS, default 8) and streams beyond that alias onto the same queue, where a stream that waits
@@ -931,6 +933,7 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
   sp.scratch_mag = 1;
   sp.write_db = h->want_spec;
   sp.fused = h->use_fused();
+  sp.k1a_variant = h->k1a_variant;
   sp.spec_fmt = h->spec_fmt();
   sp.spec_q = h->d_specq.p;
   sp.byte_scale = (float)(255.0 / (c.max_db - c.min_db));

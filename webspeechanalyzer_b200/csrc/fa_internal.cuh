@@ -42,6 +42,7 @@ struct FaSpectrumParams {
                                  // generic path: dB rows or nullptr
   int scratch_mag;               // 1: spec_db is allocated and may be used as the K1a -> K1b magnitude buffer
   int write_db;                  // 1: the caller wants the dB rows
+  int k1a_variant;               // FA_K1A_VARIANT: launch shapes 1-3 (overlap experiments), 4 = sqrt.rn for every magnitude (A/B)
   int fused;                     // 1: fft_size 2048 in utterance mode runs the fused K1 kernel (no magnitude round trip)
   int spec_fmt;                  // FA_SPECTRUM_F32 / _U8 / _F16: element type of the rows the caller gets
   void* spec_q;                  // [F_total][M] uint8 or half rows (spec_fmt != F32); the magnitudes then stay in spec_db

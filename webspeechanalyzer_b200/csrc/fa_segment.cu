@@ -106,12 +106,11 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 // _() @B37340
 __device__ __forceinline__ double fm_score(int gap, double dist, int count, int bin_old, int bin_new, double amp_old,
                                            double amp_new, double velocity) {
-  double s;
-  if (amp_old >= amp_new) s = amp_new / amp_old;
-  else {
-    if (!(amp_new > 0)) return 0;
-    s = amp_old / amp_new;
-  }
+  // s = amp_new / amp_old when amp_old >= amp_new, else amp_old / amp_new (the reference's "amp_new <= 0 -> 0" exit is dead
+  // there: amp_new > amp_old >= 0): ONE division of the smaller by the larger amplitude instead of two divergent ones.
+  // Amplitudes are uint32 values (never NaN); 0 / 0 stays NaN and fails every test below exactly as in the reference.
+  const double s_num = amp_old >= amp_new ? amp_new : amp_old, s_den = amp_old >= amp_new ? amp_old : amp_new;
+  double s = s_num / s_den;
   if (gap == 0) return s > 0.1 ? 300.0 * s / dist : 0;
   if (s < 0.001) return 0;
   if (s >= 1) s = 10; else if (s < 0.1) s = 1; else s *= 10;
