@@ -61,7 +61,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {s}")
-    subprocess.check_call([NVCC, "-shared", "-o", LIB + ".tmp"] + objs + ["-Xcompiler", "-fPIC", "-cudart", "static"])
+    subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB + ".tmp"] + objs +
+                          ["-Xcompiler", "-fPIC", "-cudart", "static"])   # the arch on the link line keeps nvcc from adding an (empty) sm_52 stub
     os.replace(LIB + ".tmp", LIB)
     build_node_addon()
     return LIB

@@ -2191,7 +2191,7 @@ cudaError_t fa_launch_segment(const FaSegmentParams& p_in, cudaStream_t s, int* 
   // per SM leaves ~4 KB of L1 for the candidate / pool reads and the stack, and every variant of the scan lost 0.35 ms.)
   p.smem_per_warp = (int)sizeof(WarpShared);
   const int bytes = p.smem_per_warp * kw;
-  const int regs = p.reg_cap > 0 ? p.reg_cap : 128;
+  const int regs = p.reg_cap > 0 ? p.reg_cap : 255;
   if (p.mode == 1) {
     if (p.ctl_chunk > 0) {
       if (p.n_cchunks > 0) fa_segctl_chunk_kernel<<<(p.n_cchunks + kCtlWarps - 1) / kCtlWarps, kCtlWarps * 32, 0, s>>>(p);
@@ -2235,7 +2235,10 @@ cudaError_t fa_launch_segment(const FaSegmentParams& p_in, cudaStream_t s, int* 
     p.redo_only = 1;
   } else if (p.impl == 2) {
     p.redo_only = 0;
-    e = regs <= 64 ? launch(fa_segment2_kernel<1024>) : regs <= 96 ? launch(fa_segment2_kernel<640>) : launch(fa_segment2_kernel<128>);
+    // FA_K3_REGS: register cap through the launch bound (65536 / bound, rounded down to a multiple of 8): 64, 96, 120, 136, 144
+    e = regs <= 64 ? launch(fa_segment2_kernel<1024>) : regs <= 96 ? launch(fa_segment2_kernel<640>)
+        : regs <= 120 ? launch(fa_segment2_kernel<544>) : regs <= 136 ? launch(fa_segment2_kernel<480>)
+        : regs <= 144 ? launch(fa_segment2_kernel<448>) : launch(fa_segment2_kernel<128>);
     if (launches) (*launches)++;
     if (e != cudaSuccess) return e;
     p.redo_only = 1;   // whatever fa_segment2_kernel handed back (overflow == 2): normally nothing, every warp exits at once
