@@ -54,9 +54,8 @@ struct WarpShared {
   uint32_t pad0[3];
   uint32_t wmask[2][FA_MAX_BANDS];            // K3 v2: [set][bin] lanes whose track slot holds the peak at `bin` in its window
                                               // (all zero between frames)
-  // ---- everything from here to the end of the warp's shared-memory slice (this struct + the extra bytes the launch adds
-  //      behind it) is dead while a segment is finalised: finalize_fast uses it as scratch ----
-  unsigned long long cs[CSM][ACAP];           // [j][slot]: score of the slot's j-th retained candidate
+  // ---- everything from here to the end of the warp's shared-memory slice is dead while a segment is finalised:
+  //      finalize_fast uses it as scratch ----
   // accepted peaks of the frame
   ulonglong2 plh[PCAP];                       // P[lo-1], P[hi]
   uint2 pa[PCAP];                             // packed lo | hi<<8 | pk<<16 | last<<24, amplitude e[pk]
@@ -72,9 +71,14 @@ struct WarpShared {
   uint32_t t_wm[ACAP];                        // this frame: retained candidates (bit j = bin wlo + j); v2: peak lanes per owner
   unsigned char pidx[FA_MAX_BANDS];           // index of the accepted peak at bin b in the accepted list
   unsigned char newlist[PCAP];                // un-owned peaks above the gate, in peak order
+  unsigned char pad1[8];
+  // ---- only the general kernel (accumulate_fm) from here on: fa_segment2_kernel's slice ends in front of it (kSlimBytes) ----
+  unsigned long long cs[CSM][ACAP];           // [j][slot]: score of the slot's j-th retained candidate
 };
-static_assert(offsetof(WarpShared, cs) % 16 == 0 && sizeof(WarpShared) % 16 == 0, "16-byte aligned slices");
-constexpr int kScratchOff = (int)offsetof(WarpShared, cs);
+static_assert(offsetof(WarpShared, plh) % 16 == 0 && offsetof(WarpShared, cs) % 16 == 0 && sizeof(WarpShared) % 16 == 0,
+              "16-byte aligned slices");
+constexpr int kScratchOff = (int)offsetof(WarpShared, plh);
+constexpr int kSlimBytes = (int)offsetof(WarpShared, cs);   // what accumulate_fm2 + finalize_fast touch: 3 KB less per warp
 
 
 struct ScanState {
@@ -390,7 +394,7 @@ __device__ __noinline__ int finalize_fast(const FaSegmentParams p, WarpShared& S
   const int start = st.current_frame - len;
   const double vmin = st.v;
   const int T = st.n_tr, NP = st.n_pts;
-  unsigned char* W = reinterpret_cast<unsigned char*>(&S.cs[0][0]);
+  unsigned char* W = reinterpret_cast<unsigned char*>(&S) + kScratchOff;
   double* mean = reinterpret_cast<double*>(W);
   unsigned char* rank = W + 8 * T;
   signed char* slot = reinterpret_cast<signed char*>(rank + T);
@@ -2235,10 +2239,29 @@ cudaError_t fa_launch_segment(const FaSegmentParams& p_in, cudaStream_t s, int* 
     p.redo_only = 1;
   } else if (p.impl == 2) {
     p.redo_only = 0;
-    // FA_K3_REGS: register cap through the launch bound (65536 / bound, rounded down to a multiple of 8): 64, 96, 120, 136, 144
-    e = regs <= 64 ? launch(fa_segment2_kernel<1024>) : regs <= 96 ? launch(fa_segment2_kernel<640>)
-        : regs <= 120 ? launch(fa_segment2_kernel<544>) : regs <= 136 ? launch(fa_segment2_kernel<480>)
-        : regs <= 144 ? launch(fa_segment2_kernel<448>) : launch(fa_segment2_kernel<128>);
+    // The fast kernel never touches the general kernel's score table at the end of WarpShared: its slice is kSlimBytes, so that
+    // 16 warps fit an SM's shared memory.  Registers: 153 by default; a launch with more warps than one resident wave of those
+    // (12 per SM) is throughput bound -- the 128-register build (launch bound 480: no spills, 1 % slower alone) keeps 16 warps
+    // per SM resident instead of 12.  FA_K3_REGS forces a cap through the launch bound (65536 / bound, rounded down to a
+    // multiple of 8): 64, 96, 128 (<= 144), else the default.
+    static int num_sms = 0;
+    if (!num_sms) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int regs2 = p.reg_cap > 0 ? p.reg_cap : (p.utt_count > num_sms * 12 ? 128 : 255);
+    const int full = p.smem_per_warp;
+    p.smem_per_warp = kSlimBytes;
+    auto launch2 = [&](auto kernel) -> cudaError_t {
+      cudaError_t e2 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSlimBytes * kw);
+      if (e2 != cudaSuccess) return e2;
+      kernel<<<grid, kw * 32, kSlimBytes * kw, s>>>(p);
+      return cudaGetLastError();
+    };
+    e = regs2 <= 64 ? launch2(fa_segment2_kernel<1024>) : regs2 <= 96 ? launch2(fa_segment2_kernel<640>)
+        : regs2 <= 144 ? launch2(fa_segment2_kernel<480>) : launch2(fa_segment2_kernel<128>);
+    p.smem_per_warp = full;
     if (launches) (*launches)++;
     if (e != cudaSuccess) return e;
     p.redo_only = 1;   // whatever fa_segment2_kernel handed back (overflow == 2): normally nothing, every warp exits at once
