@@ -40,7 +40,8 @@ for N in (512, 1024, 2048, 4096, 8192):
         alg = {"spectrum": F * (4 * hop + 4 * (N // 2) + 4 * B), "peaks": F * (4 * B + 36), "segment": F * (4 * B + 36) + tot["formant_rows"] * 48,
                "features": tot["formant_rows"] * 36 + tot["feature_rows"] * 424}
         row = {"fft_size": N, "tau": tau, "audio_s_per_s": n_utt * SECONDS / (acc[4] * 1e-3), "ms": {}, "frac_hbm": {},
-               "kernel_path": "fast (K1a+K1b)" if N == 2048 else "generic shared-memory radix-2"}
+               "kernel_path": "fast (K1a+K1b)" if N == 2048 else "generic shared-memory radix-2" if N < 2048 else
+               "big: register path for 10 stages + shared-memory tail"}
         for i, k in enumerate(("spectrum", "peaks", "segment", "features")):
             row["ms"][k] = float(acc[i])
             row["frac_hbm"][k] = alg[k] / (acc[i] * 1e-3) / 1e9 / peak if acc[i] > 0 else None
