@@ -13,9 +13,13 @@ name_re = re.compile(r"(?:__device__|__global__)[^;{]*?\b([A-Za-z_][A-Za-z0-9_]*
 lines = open(src_path).read().split("\n")
 for i, l in enumerate(lines, 1):
     if l.startswith(("__device__", "__global__", "template")) or "__global__ void" in l:
-        mm = name_re.search(" ".join(lines[i - 1:i + 2]))
+        mm = name_re.search(re.sub(r"__launch_bounds__\([^)]*\)", "", " ".join(lines[i - 1:i + 2])))
         if mm:
             regions.append((i, mm.group(1)))
+    else:   # "// ---- phase N ..." comments split a long function into sub-regions
+        ph = re.search(r"// ---- (phase [0-9a-z +]+?)[,:]", l)
+        if ph and regions:
+            regions.append((i, regions[-1][1].split(" / ")[0] + " / " + ph.group(1).strip()))
 base = src_path.split("/")[-1]
 
 
@@ -65,7 +69,7 @@ reg, regi = collections.Counter(), collections.Counter()
 for k, v in agg.items():
     reg[region(k[0], k[1])] += v[0]
     regi[region(k[0], k[1])] += v[1]
-for k, v in reg.most_common(16):
+for k, v in reg.most_common(28):
     print(f"  {k:30s} samples {100 * v / ts:5.1f}%  inst {100 * regi[k] / ti:5.1f}%")
 st = collections.Counter()
 for v in agg.values():
