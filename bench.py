@@ -157,6 +157,23 @@ def ncu_warp_instructions(kernels):
     return tot
 
 
+def kernel_table(stage_ms, fft_ms, alg_k, peak, with_ncu=True):
+    """Per-KERNEL rows of the serial step (the spectrum stage is two launches, split by fa_spectrum_split_times; every other
+    stage is one kernel): live CUDA-event ms, share of the step, algorithmic bytes of the kernel (for the two spectrum kernels
+    these include the |X|/N rows the first hands the second through HBM), achieved GB/s, fraction of the measured HBM peak,
+    DRAM bytes from the committed ncu capture.  Returns (rows, name of the kernel with the longest launch)."""
+    ms = {"fa_fftmag_2048_kernel": float(fft_ms), "fa_smooth_bands_kernel": float(stage_ms[0] - fft_ms),
+          "fa_peaks2_kernel": float(stage_ms[1]), "fa_segment2_kernel": float(stage_ms[2]), "fa_features_kernel": float(stage_ms[3])}
+    rows = {}
+    for k, t in ms.items():
+        a = alg_k[k]
+        rows[k] = {"ms": t, "share_of_step": t / max(float(stage_ms[4]), 1e-9), "algorithmic_bytes": int(a),
+                   "achieved_gbs": a / (t * 1e-3) / 1e9 if t > 0 else None,
+                   "frac_of_hbm_peak": a / (t * 1e-3) / 1e9 / peak if t > 0 else None,
+                   "ncu_dram_bytes": ncu_traffic(k) if with_ncu else None}    # the committed capture is of the C2 step
+    return rows, max(ms, key=ms.get)
+
+
 ISSUE_PEAK = 148 * 4 * 1.965e9     # warp-instructions per second: 148 SMs x 4 schedulers x 1 per clock at 1965 MHz
 
 
@@ -354,12 +371,15 @@ def run_c3(args, world, rank, local):
     stage_acc = np.zeros(5)
     eng.set_pipeline(1)
     eng.run_resident()
+    fft_acc = 0.0
     for _ in range(3):
         eng.run_resident()
         eng.sync()
         st = eng.stage_times()
         stage_acc += np.array([st["spectrum"], st["peaks"], st["segment"], st["features"], st["total"]])
+        fft_acc += eng.spectrum_split_times()["fft"]
     stage_ms = stage_acc / 3
+    fft_ms = fft_acc / 3
     eng.download()
     eng.sync()
     tot = eng.counts()
@@ -517,9 +537,12 @@ def run_c3(args, world, rank, local):
                       "achieved_gbs": alg[k] / (stage_ms[i] * 1e-3) / 1e9 if stage_ms[i] > 0 else None,
                       "frac_of_hbm_peak": alg[k] / (stage_ms[i] * 1e-3) / 1e9 / peak if stage_ms[i] > 0 else None}
                   for i, k in enumerate(names)}
-        kern = {"spectrum": "fa_fftmag_2048_kernel", "peaks": "fa_peaks2_kernel", "segment": "fa_segment2_kernel",
-                "features": "fa_features_kernel"}[top]
-        ach = stages[top]["achieved_gbs"]
+        kernels, kern = kernel_table(stage_ms, fft_ms, {
+            "fa_fftmag_2048_kernel": frames_per_step * (2 * hop + 4 * (N // 2)),      # int16 PCM once (converted on the way in), |X|/N row out
+            "fa_smooth_bands_kernel": frames_per_step * (4 * (N // 2) + 4 * B),       # |X|/N row in, u32 frame out (no dB rows at this level)
+            "fa_peaks2_kernel": alg["peaks"], "fa_segment2_kernel": alg["segment"], "fa_features_kernel": alg["features"]}, peak,
+            with_ncu=False)
+        ach = kernels[kern]["achieved_gbs"]
         line = {
             "metric": C3_METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -531,9 +554,11 @@ def run_c3(args, world, rank, local):
                        "l2": f"inputs ({pcm.array.nbytes / 1e9:.1f} GB of PCM per step and GPU) exceed the 126 MB L2; no flush needed",
                        "workload_generation_s": t_gen},
             "roofline": {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src, "share_of_step": shares[top],
-                         "note": "spectrum is FP32-issue bound, segment scan / features latency bound (DESIGN.md)"},
-            "stages": stages, "e2e": e2e, "pcie_floor": floor, "one_rank_alone_same_box": alone, "host_affinity": numa,
+                         "traffic": None, "peak_source": peak_src, "share_of_step": kernels[kern]["share_of_step"],
+                         "note": "the kernel with the longest launch of the serial step (CUDA events inside the library); the FFT "
+                                 "kernel is FP32-issue bound, the segment scan / features latency bound (DESIGN.md); every kernel: "
+                                 "`kernels`, by stage: `stages`"},
+            "kernels": kernels, "stages": stages, "e2e": e2e, "pcie_floor": floor, "one_rank_alone_same_box": alone, "host_affinity": numa,
             "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks,
             "results": {"segments": tot["segments"], "feature_rows": tot["feature_rows"], "formant_rows": tot["formant_rows"],
                         "overflow": tot["overflow"]},
@@ -643,12 +668,15 @@ def main():
     eng.set_pipeline(1)
     for _ in range(2):
         eng.run_resident()
+    fft_acc = 0.0
     for _ in range(min(args.steps, 5)):
         eng.run_resident()
         eng.sync()
         st = eng.stage_times()
         stage_acc += np.array([st["spectrum"], st["peaks"], st["segment"], st["features"], st["total"]])
+        fft_acc += eng.spectrum_split_times()["fft"]
     stage_ms = stage_acc / min(args.steps, 5)
+    fft_ms = fft_acc / min(args.steps, 5)
     eng.set_pipeline(1 if args.serial else 0)
     eng.download()
     eng.sync()
@@ -876,7 +904,11 @@ def main():
                       "achieved_gbs": alg[k] / (stage_ms[i] * 1e-3) / 1e9 if stage_ms[i] > 0 else None,
                       "frac_of_hbm_peak": alg[k] / (stage_ms[i] * 1e-3) / 1e9 / peak if stage_ms[i] > 0 else None}
                   for i, k in enumerate(names)}
-        ach = stages[top]["achieved_gbs"]
+        kernels, kern = kernel_table(stage_ms, fft_ms, {
+            "fa_fftmag_2048_kernel": frames_per_step * (4 * hop + 4 * (N // 2)),          # PCM once, |X|/N row out
+            "fa_smooth_bands_kernel": frames_per_step * (8 * (N // 2) + 4 * B),           # |X|/N row in, dB row + u32 frame out
+            "fa_peaks2_kernel": alg["peaks"], "fa_segment2_kernel": alg["segment"], "fa_features_kernel": alg["features"]}, peak)
+        ach = kernels[kern]["achieved_gbs"]
         line = {
             "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -885,13 +917,14 @@ def main():
             "config": {"workload": WORKLOAD, "utterances_per_gpu": n_utt, "parallelism": f"shard-by-utterance x{world}",
                        "batches_in_flight": depth,
                        "l2": "inputs (320 MB PCM + 819 MB spectrum rows per step) exceed the 126 MB L2; no flush needed"},
-            "roofline": {"bound": "hbm", "kernel": {"spectrum": "fa_fftmag_2048_kernel", "peaks": "fa_peaks2_kernel",
-                                                    "segment": "fa_segment2_kernel", "features": "fa_features_kernel"}[top],
-                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": ncu_traffic({"spectrum": "fa_fftmag_2048_kernel", "peaks": "fa_peaks2_kernel",
-                                                 "segment": "fa_segment2_kernel", "features": "fa_features_kernel"}[top]),
-                         "peak_source": peak_src, "share_of_step": shares[top],
-                         "note": "segment scan / features are latency bound (sequential state machine), spectrum is FP32-issue bound; see DESIGN.md"},
+            "roofline": {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": kernels[kern]["ncu_dram_bytes"], "peak_source": peak_src,
+                         "share_of_step": kernels[kern]["share_of_step"],
+                         "note": "the kernel with the longest launch of the serial step (CUDA events inside the library): the segment "
+                                 "scan is a sequential state machine per utterance, latency bound -- kilobytes per utterance, so its "
+                                 "fraction of the HBM peak is small by nature; the FFT kernel is FP32-issue bound, the smoothing kernel "
+                                 "HBM bound.  Every kernel: `kernels`; by stage, with HBM and issue floors: `stages`; DESIGN.md section 5"},
+            "kernels": kernels,
             "stages": stages,
             "e2e": e2e,
             "e2e_feature_modes": e2e_feat,

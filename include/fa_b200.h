@@ -239,6 +239,9 @@ FA_API int fa_download(fa_handle* h);
 /* Per-stage device time of the last run in milliseconds (CUDA events on the handle's stream):
  * [0] spectrum, [1] peaks, [2] segment scan, [3] features, [4] whole run incl. copies. */
 FA_API int fa_stage_times(fa_handle* h, float ms[5]);
+/* The spectrum stage of the last run, kernel by kernel (its two launches): [0] frame-parallel FFT magnitudes |X|/N,
+ * [1] smoothing recursion + dB view + band projection.  Like the stage times, only meaningful for a run with one sub-batch. */
+FA_API int fa_spectrum_split_times(fa_handle* h, float ms[2]);
 /* Number of kernel launches issued by the last run. */
 FA_API int fa_launch_count(fa_handle* h);
 /* Stream mode (utterances of >= 1000 frames on average): the smoothing recursion (stage 0) and the segmentor's control

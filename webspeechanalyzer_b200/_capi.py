@@ -21,7 +21,7 @@ FA_ERR_CAPACITY, FA_ERR_OUT_OF_MEMORY, FA_ERR_BUSY, FA_ERR_UNSUPPORTED = -6, -7,
 EXPORTS = [
     "fa_config_default", "fa_abi_version", "fa_status_string", "fa_create", "fa_destroy", "fa_last_error", "fa_get_config",
     "fa_set_stream", "fa_set_d2h_stream", "fa_set_pipeline", "fa_set_spectrum_sink", "fa_set_spectrum_sink_raw", "fa_reset", "fa_submit_pcm", "fa_submit_pcm_i16", "fa_submit_pcm_batch", "fa_submit_pcm_i16_batch", "fa_submit_frames", "fa_run", "fa_sync", "fa_upload",
-    "fa_run_resident", "fa_download", "fa_stage_times", "fa_launch_count", "fa_stream_fixups", "fa_num_utterances", "fa_result_counts",
+    "fa_run_resident", "fa_download", "fa_stage_times", "fa_spectrum_split_times", "fa_launch_count", "fa_stream_fixups", "fa_num_utterances", "fa_result_counts",
     "fa_total_counts", "fa_copy_counts_table", "fa_pcie_probe", "fa_copy_spectrum", "fa_copy_spectrum_raw", "fa_copy_frames", "fa_copy_segments", "fa_copy_formants", "fa_copy_energy",
     "fa_copy_syllables", "fa_copy_features", "fa_copy_utterance_features", "fa_copy_curve_features", "fa_copy_track_points", "fa_set_truncate", "fa_mlp_create", "fa_mlp_destroy", "fa_mlp_last_error",
     "fa_mlp_classify", "fa_mlp_classify_features", "fa_copy_peak_candidates", "fa_copy_gsum", "fa_hop_samples", "fa_frames_for",
@@ -75,6 +75,7 @@ def lib() -> C.CDLL:
         getattr(L, n).argtypes = [H]
     L.fa_stream_fixups.argtypes = [H, C.c_int]
     L.fa_stage_times.argtypes = [H, C.POINTER(C.c_float)]
+    L.fa_spectrum_split_times.argtypes = [H, C.POINTER(C.c_float)]
     L.fa_result_counts.argtypes = [H, C.c_int64, C.POINTER(FaCounts)]
     L.fa_total_counts.argtypes = [H, C.POINTER(FaCounts)]
     L.fa_copy_counts_table.argtypes = [H, C.c_void_p, C.c_size_t]

@@ -183,6 +183,7 @@ struct fa_handle {
   bool have_table[5] = {false, false, false, false, false};   // dense tables fetched so far: segs, formants, energy, syls, features
   cudaEvent_t ev[8] = {};
   float stage_ms[5] = {0, 0, 0, 0, 0};
+  float fft_ms = 0;   // first part of stage_ms[0]: the frame-parallel |X|/N kernel (serial mode)
   int launches = 0;
 };
 
@@ -952,7 +953,8 @@ static int launch_sub(fa_handle* h, const SubBatch& sb, int slot, cudaStream_t s
     sp.spec_out = (h->want_spec && h->spec_fmt() == FA_SPECTRUM_F32) ? h->d_specdb.as<float>() : nullptr;
     sp.fixups = h->d_fix.as<int>();
   }
-  if (!h->frames_mode) FA_CUDA(fa_launch_spectrum(sp, s, &h->launches));
+  if (!h->frames_mode) FA_CUDA(fa_launch_spectrum(sp, s, &h->launches, ev ? h->ev[7] : nullptr));
+  else if (ev) FA_CUDA(cudaEventRecord(h->ev[7], s));
   if (h->debug_sync) FA_CUDA(cudaStreamSynchronize(s));
   if (ev) FA_CUDA(cudaEventRecord(ev[1], s));
   if (!ev) FA_CUDA(cudaEventRecord(h->spec_done[slot], s));  // the dB rows of this sub-batch are final
@@ -1123,6 +1125,7 @@ static int run_device(fa_handle* h, bool with_h2d, bool with_sink) {
       if (sink && subs[b].r1 > subs[b].r0) FA_CUDA(cudaStreamWaitEvent(s, h->copy_done[b], 0));
     }
     for (int i = 1; i <= 4; i++) FA_CUDA(cudaEventRecord(h->ev[i], s));  // per-stage times only exist in serial mode
+    FA_CUDA(cudaEventRecord(h->ev[7], s));
   }
   if (c.output_level >= 3) {
     int* cnt = h->d_counts.as<int>();
@@ -1213,6 +1216,10 @@ int fa_sync(fa_handle* h) {
   if (h->ran) {
     for (int i = 0; i < 4; i++) cudaEventElapsedTime(&h->stage_ms[i], h->ev[i], h->ev[i + 1]);
     cudaEventElapsedTime(&h->stage_ms[4], h->ev[0], h->ev[5]);
+    if (cudaEventElapsedTime(&h->fft_ms, h->ev[0], h->ev[7]) != cudaSuccess || h->fft_ms > h->stage_ms[0]) {
+      cudaGetLastError();
+      h->fft_ms = 0.f;   // no split available (sub-batch pipeline): everything counts as the second part
+    }
     if (h->trace && !h->from_host) {
       static cudaEvent_t base = nullptr;   // first traced run of the process: the common time origin of all handles
       if (!base) base = h->ev[0];
@@ -1251,6 +1258,16 @@ int fa_stage_times(fa_handle* h, float ms[5]) {
   const int rc = fa_sync(h);
   if (rc != FA_OK) return rc;
   for (int i = 0; i < 5; i++) ms[i] = h->stage_ms[i];
+  return FA_OK;
+}
+
+int fa_spectrum_split_times(fa_handle* h, float ms[2]) {
+  if (!h || !ms) return FA_ERR_INVALID_ARG;
+  if (!h->ran) return fail(h, FA_ERR_NOT_RUN, "no run yet");
+  const int rc = fa_sync(h);
+  if (rc != FA_OK) return rc;
+  ms[0] = h->fft_ms;
+  ms[1] = h->stage_ms[0] - h->fft_ms;
   return FA_OK;
 }
 

@@ -224,7 +224,8 @@ struct FaGatherArgs {
 };
 
 cudaError_t fa_launch_pcm_i16(const int16_t* src, float* dst, long long n, cudaStream_t s, int* launches);
-cudaError_t fa_launch_spectrum(const FaSpectrumParams& p, cudaStream_t s, int* launches);
+// mid (optional): recorded between the frame-parallel |X|/N kernel and the smoothing / dB / band kernel
+cudaError_t fa_launch_spectrum(const FaSpectrumParams& p, cudaStream_t s, int* launches, cudaEvent_t mid = nullptr);
 cudaError_t fa_launch_peaks(const FaPeaksParams& p, cudaStream_t s, int* launches);
 cudaError_t fa_launch_segment(const FaSegmentParams& p, cudaStream_t s, int* launches);
 cudaError_t fa_launch_features(const FaFeatureParams& p, cudaStream_t s, int* launches);

@@ -187,6 +187,12 @@ class Engine:
         self._check(self._lib.fa_stage_times(self._h, ms))
         return dict(zip(("spectrum", "peaks", "segment", "features", "total"), [float(x) for x in ms]))
 
+    def spectrum_split_times(self):
+        """The spectrum stage of the last (serial) run kernel by kernel: FFT magnitudes, smoothing + dB + bands (ms)."""
+        ms = (C.c_float * 2)()
+        self._check(self._lib.fa_spectrum_split_times(self._h, ms))
+        return {"fft": float(ms[0]), "smooth_bands": float(ms[1])}
+
     @property
     def stream_fixups(self) -> int:
         """Chunks the verification pass of the chunk-parallel smoothing had to recompute in the last run (stream mode)."""
