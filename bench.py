@@ -12,7 +12,8 @@ batch (sharded by utterance, no data-path collective) => weak scaling.
   e2e       the same metric through the C-ABI with HOST buffers: fa_submit_pcm_batch (pinned caller PCM, zero copy),
             H2D, kernels, D2H of every result table and of the dB spectrum inside the timed region; --depth batches in
             flight, all batches drained before the clock stops
-  roofline  the dominant kernel's algorithmic bytes / its CUDA-event time vs the measured HBM peak
+  roofline  the longest-running kernel's algorithmic bytes / its CUDA-event time vs the measured HBM peak; `kernels` has every
+            kernel, `stages` the per-stage HBM and issue floors
   cpu_baseline  the CPU oracle (a restatement: kind "port") on the host cores, same workload
 
 With --gpus N > 1 (torchrun, one rank per GPU) the workload is BASELINE.json configs[2] (C3): 48 kHz utterances, Syllable
@@ -532,7 +533,6 @@ def run_c3(args, world, rank, local):
         }
         names = ["spectrum", "peaks", "segment", "features"]
         shares = {k: float(stage_ms[i] / max(stage_ms[4], 1e-9)) for i, k in enumerate(names)}
-        top = max(names, key=lambda k: stage_ms[names.index(k)])
         stages = {k: {"ms": float(stage_ms[i]), "share": shares[k], "algorithmic_bytes": int(alg[k]),
                       "achieved_gbs": alg[k] / (stage_ms[i] * 1e-3) / 1e9 if stage_ms[i] > 0 else None,
                       "frac_of_hbm_peak": alg[k] / (stage_ms[i] * 1e-3) / 1e9 / peak if stage_ms[i] > 0 else None}
@@ -875,7 +875,6 @@ def main():
         peak, peak_src = measured_peaks()
         N, B, hop = cfg.fft_size, cfg.bands, 400
         # algorithmic bytes per unit: per frame unless noted
-        seg_rows = max(tot["formant_rows"] // max(world, 1), 1) if False else tot["formant_rows"]
         alg = {
             "spectrum": frames_per_step * (4 * hop + 4 * (N // 2) + 4 * B),                       # PCM once + dB row + u32 frame
             "peaks": frames_per_step * (4 * B + 32 * cand_per_frame + 12),                         # u32 frame in, 32 B per candidate (measured count) + (n, g) out
@@ -884,7 +883,6 @@ def main():
         }
         names = ["spectrum", "peaks", "segment", "features"]
         shares = {k: float(stage_ms[i] / max(stage_ms[4], 1e-9)) for i, k in enumerate(names)}
-        top = max(names, key=lambda k: stage_ms[names.index(k)])
         stage_kernels = {"spectrum": ["fa_fftmag_2048_kernel", "fa_smooth_bands_kernel"], "peaks": ["fa_peaks2_kernel"],
                          "segment": ["fa_segment2_kernel"], "features": ["fa_features_kernel"]}
 
