@@ -171,6 +171,7 @@ def kernel_table(stage_ms, fft_ms, alg_k, peak, with_ncu=True):
         rows[k] = {"ms": t, "share_of_step": t / max(float(stage_ms[4]), 1e-9), "algorithmic_bytes": int(a),
                    "achieved_gbs": a / (t * 1e-3) / 1e9 if t > 0 else None,
                    "frac_of_hbm_peak": a / (t * 1e-3) / 1e9 / peak if t > 0 else None,
+                   "frac_of_nominal_8tbs": a / (t * 1e-3) / 1e9 / 8000.0 if t > 0 else None,
                    "ncu_dram_bytes": ncu_traffic(k) if with_ncu else None}    # the committed capture is of the C2 step
     return rows, max(ms, key=ms.get)
 
